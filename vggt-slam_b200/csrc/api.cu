@@ -1,0 +1,193 @@
+// api.cu -- library plumbing: errors, device buffers, map life cycle.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "state.cuh"
+
+namespace vsm {
+
+static thread_local char g_err[1024] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::ensure(size_t need, cudaStream_t s, size_t keep_bytes, double slack) {
+  if (need <= bytes && p != nullptr) return VSM_OK;
+  if (need == 0) need = 16;
+  size_t want = (size_t)((double)need * slack);
+  want = (want + 255) & ~(size_t)255;
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, want);
+  if (e != cudaSuccess && want > need) {
+    cudaGetLastError();
+    want = (need + 255) & ~(size_t)255;
+    e = cudaMalloc(&np, want);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    return VSM_E_NOMEM;
+  }
+  if (p != nullptr) {
+    if (keep_bytes) {
+      VSM_CUDA(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+      VSM_CUDA(cudaStreamSynchronize(s));
+    }
+    VSM_CUDA(cudaFree(p));  // cudaFree waits for work that may still use the old block
+  }
+  p = np;
+  bytes = want;
+  return VSM_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
+  if (m->pinned_bytes < bytes) {
+    if (m->pinned) cudaFreeHost(m->pinned);
+    m->pinned = nullptr;
+    m->pinned_bytes = 0;
+    VSM_CUDA(cudaMallocHost(&m->pinned, std::max<size_t>(bytes, 4096)));
+    m->pinned_bytes = std::max<size_t>(bytes, 4096);
+  }
+  VSM_CUDA(cudaMemcpyAsync(m->pinned, src_dev, bytes, cudaMemcpyDeviceToHost, s));
+  VSM_CUDA(cudaStreamSynchronize(s));
+  memcpy(dst_host, m->pinned, bytes);
+  return VSM_OK;
+}
+
+}  // namespace vsm
+
+using namespace vsm;
+
+extern "C" int vsm_abi_version(void) { return VSM_ABI_VERSION; }
+extern "C" const char* vsm_last_error(void) { return g_err; }
+extern "C" int64_t vsm_launch_count(void) { return g_launches; }
+
+extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
+  if (!cfg || !out) {
+    set_error("null config or output");
+    return VSM_E_INVALID;
+  }
+  *out = nullptr;
+  if (!(cfg->voxel_size > 0.0)) {
+    set_error("voxel_size must be > 0");  // submap.py:236, map.py:185
+    return VSM_E_INVALID;
+  }
+  if (cfg->emb_dtype != VSM_F32 && cfg->emb_dtype != VSM_BF16) {
+    set_error("emb_dtype must be VSM_F32 or VSM_BF16");
+    return VSM_E_INVALID;
+  }
+  const int esize = cfg->emb_dtype == VSM_BF16 ? 2 : 4;
+  if (cfg->dim <= 0 || cfg->dim % 8 != 0 || (int64_t)cfg->dim * esize > 32 * 8 * 16) {
+    set_error("dim must be a positive multiple of 8 with at most %d bytes per row", 32 * 8 * 16);
+    return VSM_E_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: libvsm has no CPU fallback");
+    return VSM_E_CUDA;
+  }
+  int dev = cfg->device;
+  if (dev < 0) VSM_CUDA(cudaGetDevice(&dev));
+  if (dev >= ndev) {
+    set_error("device %d out of range (%d devices)", dev, ndev);
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(dev));
+  vsm_map* m = new vsm_map();
+  m->cfg = *cfg;
+  m->device = dev;
+  m->d = cfg->dim;
+  m->esize = esize;
+  m->vs_f = (float)cfg->voxel_size;
+  int st = m->d_n_vox.ensure(sizeof(uint32_t), nullptr);
+  if (st == VSM_OK) st = cudaMemset(m->d_n_vox.p, 0, sizeof(uint32_t)) == cudaSuccess ? VSM_OK : VSM_E_CUDA;
+  if (st == VSM_OK) st = map_grow(m, std::max<int64_t>(cfg->voxel_capacity, 1024), nullptr);
+  if (st != VSM_OK) {
+    vsm_map_destroy(m);
+    return st;
+  }
+  VSM_CUDA(cudaDeviceSynchronize());
+  *out = m;
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_destroy(vsm_map* m) {
+  if (!m) return VSM_OK;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  vsm::DevBuf* bufs[] = {&m->gkeys,     &m->gids,      &m->vkey,       &m->vcount,    &m->vsum,       &m->d_n_vox,
+                         &m->log_gid,   &m->log_fuse,  &m->log_mask,   &m->ctr,       &m->sel,        &m->sel_hist,
+                         &m->pw,        &m->pt_slot,   &m->ta_keys,    &m->ta_count,  &m->ta_lid,     &m->ta_list,
+                         &m->tb_keys,   &m->tb_count,  &m->tb_lid,     &m->tb_list,   &m->tb_mask,    &m->lv_cnt,
+                         &m->lv_off,    &m->lv_cursor, &m->lv_gid,     &m->sorted_pix, &m->sorted_gid, &m->cub_tmp,
+                         &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
+                         &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
+                         &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm};
+  for (auto* b : bufs) b->release();
+  for (auto& f : m->fuses) f.point_gid.release();
+  if (m->pinned) cudaFreeHost(m->pinned);
+  for (int b = 0; b < 2; ++b) {
+    if (m->pinned_stage[b]) cudaFreeHost(m->pinned_stage[b]);
+    if (m->ev_stage[b]) cudaEventDestroy(m->ev_stage[b]);
+    if (m->ev_copy[b]) cudaEventDestroy(m->ev_copy[b]);
+  }
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  cudaGetLastError();
+  delete m;
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
+  if (!m) {
+    set_error("null map");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, m->gcap * 8, s));
+  VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, m->gcap * 4, s));
+  VSM_CUDA(cudaMemsetAsync(m->vcount.p, 0, (size_t)m->vcap * 4, s));
+  VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, (size_t)m->vcap * m->d * 4, s));
+  VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, sizeof(uint32_t), s));
+  VSM_CUDA(cudaStreamSynchronize(s));
+  m->n_vox = 0;
+  m->log_n = 0;
+  for (auto& f : m->fuses) f.point_gid.release();
+  m->fuses.clear();
+  m->finalized = false;
+  m->dense_loaded = false;
+  m->ck_built = false;
+  m->csr_entries = 0;
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream) {
+  if (!m) {
+    set_error("null map");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  return map_grow(m, voxel_capacity, (cudaStream_t)stream);
+}
+
+extern "C" int vsm_num_voxels(const vsm_map* m, int64_t* out_host) {
+  if (!m || !out_host) {
+    set_error("null argument");
+    return VSM_E_INVALID;
+  }
+  *out_host = m->n_vox;
+  return VSM_OK;
+}

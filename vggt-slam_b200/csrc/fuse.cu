@@ -1,0 +1,1084 @@
+// fuse.cu -- the fusion hot path: world-frame transform, confidence / outlier
+// filters, voxel keys, submap-local hash with warp-level key dedup, global hash
+// merge, voxel-sorted point lists and the embedding accumulate kernel.
+//
+// Reference behaviour restated here:
+//   Submap.get_semantic_voxel_in_world_frame   vggt_slam/submap.py:246-293
+//   GraphMap.build_semantic_voxel_map          vggt_slam/map.py:196-291 (per-submap loop, three filters)
+//                                              vggt_slam/map.py:351-362 (global voxelisation, numpy branch)
+//
+// Pipeline of one fuse call (all on one stream):
+//   world_points      px -> (x,y,z,flags) float4; conf mask, stride grid, f64 transform, finite test
+//   [filters]         radix-select percentiles -> bbox; coarse-cell hash count -> isolation filter
+//   fine_insert       packed voxel key -> submap-local hash (count + frame mask), point -> slot
+//   local_compact     dense local voxel ids, counts; exclusive scan -> segment offsets
+//   global_merge      one thread per DISTINCT voxel inserts into the global hash (V_sub, not N, probes)
+//   scatter           counting sort of the points by local voxel -> (pixel, voxel id) lists
+//   accumulate        warps walk 32-point chunks of the sorted list, sum embedding rows in registers and
+//                     flush with one vector RED burst per voxel boundary (fp32 accumulate)
+#include <cub/device/device_scan.cuh>
+
+#include "hash.cuh"
+
+namespace vsm {
+
+constexpr uint32_t PF_SEL = 1u;     // conf >= thr, on the stride grid, frame < end_idx
+constexpr uint32_t PF_FINITE = 2u;  // world point (and embedding row, if a mask was given) finite
+
+// ---------------------------------------------------------------------------
+// world points
+// ---------------------------------------------------------------------------
+struct WorldArgs {
+  const float* pts;
+  const float* conf;
+  const uint8_t* emb_ok;
+  float4* pw;
+  int64_t n_px;
+  int H, W, stride;
+  float thr;
+};
+
+__device__ __forceinline__ float4 world_one(const WorldArgs& a, const HMat& Hm, int64_t pix, float px, float py,
+                                            float pz, float c, uint32_t& flags) {
+  flags = 0u;
+  float x = 0.f, y = 0.f, z = 0.f;
+  bool on_grid = true;
+  if (a.stride > 1) {
+    const int w = (int)(pix % a.W);
+    const int h = (int)((pix / a.W) % a.H);
+    on_grid = (w % a.stride == 0) && (h % a.stride == 0);
+  }
+  if (on_grid && c >= a.thr) {
+    transform_f32(Hm, px, py, pz, x, y, z);
+    flags = PF_SEL;
+    if (finite3(x, y, z) && (a.emb_ok == nullptr || a.emb_ok[pix] != 0)) flags |= PF_FINITE;
+  }
+  return make_float4(x, y, z, __uint_as_float(flags));
+}
+
+// 4 pixels per thread: three 128-bit loads of xyz, one of conf, four 128-bit stores
+__global__ void __launch_bounds__(256) world_points_vec4_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
+  const int64_t n4 = a.n_px >> 2;
+  unsigned n_sel = 0, n_fin = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+    const float4* p4 = reinterpret_cast<const float4*>(a.pts) + 3 * t;
+    const uint4 r0 = ld_stream_v4(p4), r1 = ld_stream_v4(p4 + 1), r2 = ld_stream_v4(p4 + 2);
+    const uint4 rc = ld_stream_v4(reinterpret_cast<const float4*>(a.conf) + t);
+    const float v[12] = {__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w),
+                         __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w),
+                         __uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), __uint_as_float(r2.w)};
+    const float c[4] = {__uint_as_float(rc.x), __uint_as_float(rc.y), __uint_as_float(rc.z), __uint_as_float(rc.w)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t f;
+      const float4 o = world_one(a, Hm, 4 * t + j, v[3 * j], v[3 * j + 1], v[3 * j + 2], c[j], f);
+      a.pw[4 * t + j] = o;
+      n_sel += (f & PF_SEL) ? 1u : 0u;
+      n_fin += (f & PF_FINITE) ? 1u : 0u;
+    }
+  }
+  // tail (n_px % 4) by the first threads of block 0
+  if (blockIdx.x == 0 && threadIdx.x < (a.n_px & 3)) {
+    const int64_t pix = (n4 << 2) + threadIdx.x;
+    uint32_t f;
+    a.pw[pix] = world_one(a, Hm, pix, a.pts[3 * pix], a.pts[3 * pix + 1], a.pts[3 * pix + 2], a.conf[pix], f);
+    n_sel += (f & PF_SEL) ? 1u : 0u;
+    n_fin += (f & PF_FINITE) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
+    n_fin += __shfl_xor_sync(0xffffffffu, n_fin, o);
+  }
+  if (lane_id() == 0) {
+    if (n_sel) atomicAdd(&ctr->n_conf, (unsigned long long)n_sel);
+    if (n_fin) atomicAdd(&ctr->n_finite, (unsigned long long)n_fin);
+  }
+}
+
+// one pixel per thread (unaligned inputs)
+__global__ void __launch_bounds__(256) world_points_scalar_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
+  unsigned n_sel = 0, n_fin = 0;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < a.n_px;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t f;
+    a.pw[pix] = world_one(a, Hm, pix, a.pts[3 * pix], a.pts[3 * pix + 1], a.pts[3 * pix + 2], a.conf[pix], f);
+    n_sel += (f & PF_SEL) ? 1u : 0u;
+    n_fin += (f & PF_FINITE) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
+    n_fin += __shfl_xor_sync(0xffffffffu, n_fin, o);
+  }
+  if (lane_id() == 0) {
+    if (n_sel) atomicAdd(&ctr->n_conf, (unsigned long long)n_sel);
+    if (n_fin) atomicAdd(&ctr->n_finite, (unsigned long long)n_fin);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// submap-local hash: insert with warp-level key dedup
+// ---------------------------------------------------------------------------
+// Consecutive pixels mostly fall into the same voxel, so the lanes of a warp first
+// group equal keys (match.any) and only each group's leader touches the table, adding
+// the whole group's count with one atomic.
+__device__ __forceinline__ int table_claim(const LocalTable& t, unsigned long long key, uint32_t add,
+                                           FuseCounters* ctr) {
+  uint32_t h = (uint32_t)mix64(key) & t.cap_mask;
+  for (uint32_t probes = 0; probes <= t.cap_mask; ++probes) {
+    unsigned long long cur = t.keys[h];
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(&t.keys[h], kEmptyKey, key);
+      if (cur == kEmptyKey) {
+        const uint32_t lid = atomicAdd(t.n_occ, 1u);
+        t.slot_list[lid] = h;
+        cur = key;
+      }
+    }
+    if (cur == key) {
+      atomicAdd(&t.count[h], add);
+      return (int)h;
+    }
+    h = (h + 1u) & t.cap_mask;
+  }
+  atomicAdd(&ctr->internal_err, 1u);
+  return -1;
+}
+
+// all 32 lanes must call; inactive lanes pass active=false.  frame < 0: no frame mask.
+__device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, unsigned long long key, int frame,
+                                           FuseCounters* ctr) {
+  const unsigned long long k = active ? key : kEmptyKey;
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(grp) - 1;
+  int slot = -1;
+  if (active && lane_id() == leader) slot = table_claim(t, key, (uint32_t)__popc(grp), ctr);
+  slot = __shfl_sync(0xffffffffu, slot, leader);
+  if (frame >= 0) {
+    const int lf = __shfl_sync(0xffffffffu, frame, leader);
+    if (active && slot >= 0 && (lane_id() == leader || frame != lf))
+      atomicOr(&t.mask[(size_t)slot * 2 + (frame >> 6)], 1ull << (frame & 63));
+  }
+  return active ? slot : -1;
+}
+
+struct FilterArgs {
+  const float4* pw;
+  int32_t* pt_slot;
+  int64_t n_px;
+  int64_t px_per_frame;
+  float cell;      // coarse cell (bbox_coarse) or voxel size (fine)
+  uint32_t min_pts;
+};
+
+// filter 2 (inclusive percentile box, map.py:257-263) + count per coarse cell (map.py:271-275)
+__global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, LocalTable ta, FuseCounters* ctr) {
+  const float lx = ctr->bounds[0], hx = ctr->bounds[1], ly = ctr->bounds[2], hy = ctr->bounds[3], lz = ctr->bounds[4],
+              hz = ctr->bounds[5];
+  unsigned n_in = 0;
+  const int64_t n_round = (a.n_px + 31) & ~(int64_t)31;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    bool act = false;
+    unsigned long long key = kEmptyKey;
+    if (pix < a.n_px) {
+      const float4 p = a.pw[pix];
+      const uint32_t f = __float_as_uint(p.w);
+      if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) {
+        act = (p.x >= lx) && (p.x <= hx) && (p.y >= ly) && (p.y <= hy) && (p.z >= lz) && (p.z <= hz);
+        if (act) {
+          bool rerr = false;
+          key = pack_key(p.x, p.y, p.z, a.cell, rerr);
+          if (rerr) atomicAdd(&ctr->range_err, 1u);
+        }
+      }
+    }
+    const int slot = warp_insert(ta, act, key, -1, ctr);
+    if (pix < a.n_px) a.pt_slot[pix] = slot;
+    n_in += act ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
+}
+
+// filter 3 (cells with >= min_pts points, map.py:276-280) + fine voxel keys (map.py:351 / submap.py:282)
+template <bool FILTERS>
+__global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTable ta, LocalTable tb, FuseCounters* ctr) {
+  unsigned n_in = 0;
+  const int64_t n_round = (a.n_px + 31) & ~(int64_t)31;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    bool act = false;
+    unsigned long long key = kEmptyKey;
+    int frame = 0;
+    if (pix < a.n_px) {
+      const float4 p = a.pw[pix];
+      if (FILTERS) {
+        const int sa = a.pt_slot[pix];
+        act = sa >= 0 && ta.count[sa] >= a.min_pts;
+      } else {
+        act = (__float_as_uint(p.w) & PF_SEL) != 0u;
+      }
+      if (act) {
+        bool rerr = false;
+        key = pack_key(p.x, p.y, p.z, a.cell, rerr);
+        if (rerr) atomicAdd(&ctr->range_err, 1u);
+        frame = (int)(pix / a.px_per_frame);
+      }
+    }
+    const int slot = warp_insert(tb, act, key, frame, ctr);
+    if (pix < a.n_px) a.pt_slot[pix] = slot;
+    n_in += act ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_fused, (unsigned long long)n_in);
+}
+
+// dense local ids: lid = position in the claim list
+__global__ void local_compact_kernel(LocalTable tb, uint32_t n_occ, uint32_t* __restrict__ lv_cnt) {
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
+    const uint32_t slot = tb.slot_list[lid];
+    lv_cnt[lid] = tb.count[slot];
+    tb.lid[slot] = lid;
+  }
+}
+
+__global__ void table_cleanup_kernel(LocalTable t, uint32_t n_occ) {
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
+    const uint32_t slot = t.slot_list[lid];
+    t.keys[slot] = kEmptyKey;
+    t.count[slot] = 0u;
+    if (t.mask) {
+      t.mask[(size_t)slot * 2] = 0ull;
+      t.mask[(size_t)slot * 2 + 1] = 0ull;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *t.n_occ = 0u;
+}
+
+// ---------------------------------------------------------------------------
+// global hash
+// ---------------------------------------------------------------------------
+__global__ void rehash_kernel(GlobalStore g, uint32_t n) {
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    const unsigned long long key = g.vkey[id];
+    uint64_t h = mix64(key) & g.gmask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&g.gkeys[h], kEmptyKey, key);
+      if (prev == kEmptyKey) {
+        g.gids[h] = (int32_t)id;
+        break;
+      }
+      h = (h + 1) & g.gmask;
+    }
+  }
+}
+
+// one thread per distinct voxel of this call: global insert, counts, contributor log
+__global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, uint32_t n_occ, GlobalStore g,
+                                                           const uint32_t* __restrict__ lv_cnt,
+                                                           int32_t* __restrict__ lv_gid, int32_t* __restrict__ log_gid,
+                                                           int32_t* __restrict__ log_sub,
+                                                           unsigned long long* __restrict__ log_mask, int64_t log_base,
+                                                           int32_t submap_id, FuseCounters* ctr) {
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
+    const uint32_t slot = tb.slot_list[lid];
+    const unsigned long long key = tb.keys[slot];
+    const int gid = global_find_or_insert(g, key, &ctr->internal_err);
+    lv_gid[lid] = gid;
+    if (gid >= 0) atomicAdd(&g.vcount[gid], lv_cnt[lid]);
+    log_gid[log_base + lid] = gid;
+    log_sub[log_base + lid] = submap_id;
+    log_mask[2 * (log_base + lid)] = tb.mask[(size_t)slot * 2];
+    log_mask[2 * (log_base + lid) + 1] = tb.mask[(size_t)slot * 2 + 1];
+  }
+}
+
+// counting sort of the fused points by local voxel.  Lanes with the same voxel claim a block of
+// consecutive positions with one atomic and keep their pixel order inside it.
+__global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict__ pt_slot, int64_t n_px, LocalTable tb,
+                                                      const uint32_t* __restrict__ lv_off,
+                                                      uint32_t* __restrict__ lv_cursor,
+                                                      const int32_t* __restrict__ lv_gid,
+                                                      uint32_t* __restrict__ sorted_pix,
+                                                      int32_t* __restrict__ sorted_gid, int32_t* __restrict__ point_gid) {
+  const int64_t n_round = (n_px + 31) & ~(int64_t)31;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    const int slot = pix < n_px ? pt_slot[pix] : -1;
+    const bool act = slot >= 0;
+    const uint32_t lid = act ? tb.lid[slot] : 0xFFFFFFFFu;
+    const unsigned grp = __match_any_sync(0xffffffffu, lid);
+    const int leader = __ffs(grp) - 1;
+    uint32_t base = 0;
+    if (act && lane_id() == leader) base = atomicAdd(&lv_cursor[lid], (uint32_t)__popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    int gid = -1;
+    if (act) {
+      const uint32_t pos = lv_off[lid] + base + (uint32_t)__popc(grp & ((1u << lane_id()) - 1u));
+      gid = lv_gid[lid];
+      sorted_pix[pos] = (uint32_t)pix;
+      sorted_gid[pos] = gid;
+    }
+    if (point_gid != nullptr && pix < n_px) point_gid[pix] = gid;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// embedding accumulate
+// ---------------------------------------------------------------------------
+// A row is d embedding channels of one pixel (bf16: 2d bytes, f32: 4d bytes), read as 16-byte vectors:
+// lane l of a warp owns vectors l, l+32, ... (VPL of them), i.e. a warp reads 512 contiguous bytes per
+// vector index.  Each warp walks a chunk of 32 entries of a (pixel, voxel id) list; rows are summed in
+// fp32 registers and flushed with vector REDs whenever the voxel id changes.  U rows are in flight.
+template <bool BF16>
+struct RowVec;
+template <>
+struct RowVec<true> {
+  static constexpr int EPV = 8;  // elements per 16-byte vector
+  __device__ static __forceinline__ void add(float* acc, const uint4& v) {
+    acc[0] += __uint_as_float(v.x << 16);
+    acc[1] += __uint_as_float(v.x & 0xFFFF0000u);
+    acc[2] += __uint_as_float(v.y << 16);
+    acc[3] += __uint_as_float(v.y & 0xFFFF0000u);
+    acc[4] += __uint_as_float(v.z << 16);
+    acc[5] += __uint_as_float(v.z & 0xFFFF0000u);
+    acc[6] += __uint_as_float(v.w << 16);
+    acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
+  }
+  __device__ static __forceinline__ bool nonfinite(const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      bad |= ((w[i] & 0x7F800000u) == 0x7F800000u) || ((w[i] & 0x00007F80u) == 0x00007F80u);
+    return bad;
+  }
+};
+template <>
+struct RowVec<false> {
+  static constexpr int EPV = 4;
+  __device__ static __forceinline__ void add(float* acc, const uint4& v) {
+    acc[0] += __uint_as_float(v.x);
+    acc[1] += __uint_as_float(v.y);
+    acc[2] += __uint_as_float(v.z);
+    acc[3] += __uint_as_float(v.w);
+  }
+  __device__ static __forceinline__ bool nonfinite(const uint4& v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bad |= (w[i] & 0x7F800000u) == 0x7F800000u;
+    return bad;
+  }
+};
+
+struct AccArgs {
+  const uint8_t* emb;          // row of pixel p starts at emb + (p - pix_base) * row_bytes
+  int64_t pix_base;
+  int64_t row_bytes;
+  const uint32_t* sorted_pix;  // SORTED mode: entry lists
+  const int32_t* sorted_gid;
+  const int32_t* point_gid;    // PIXEL mode: voxel id per pixel (-1: skip); entries are pixels [pix_base, pix_base+n)
+  int64_t n;                   // entries
+  float* vsum;
+  int d;
+  int nvec;                    // 16-byte vectors per row
+  FuseCounters* ctr;
+};
+
+template <bool BF16, int VPL, bool SORTED, bool CHECK>
+__global__ void __launch_bounds__(256) accumulate_kernel(AccArgs a) {
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_chunks = (a.n + 31) >> 5;
+  unsigned n_bad = 0;
+
+  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+    const int64_t base = chunk << 5;
+    const int cnt = (int)min((int64_t)32, a.n - base);
+    int64_t my_pix = 0;
+    int my_gid = -1;
+    if (lane < cnt) {
+      if (SORTED) {
+        my_pix = (int64_t)a.sorted_pix[base + lane];
+        my_gid = a.sorted_gid[base + lane];
+      } else {
+        my_pix = a.pix_base + base + lane;
+        my_gid = a.point_gid[my_pix];
+      }
+    }
+    // pixel mode: -1 = not selected; -2 = selected but filtered out (its row is only checked for non-finite values)
+    if (!SORTED && __ballot_sync(0xffffffffu, CHECK ? (my_gid != -1) : (my_gid >= 0)) == 0u) continue;
+
+    float acc[VPL * EPV];
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+    int cur = -1;
+
+    auto flush = [&]() {
+      if (cur >= 0) {
+        float* dst = a.vsum + (size_t)cur * a.d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = lane + 32 * v;
+          if (c < a.nvec) {
+#pragma unroll
+            for (int q = 0; q < EPV / 4; ++q)
+              red_add_v4(dst + c * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
+                         acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+    };
+
+    for (int j = 0; j < cnt; j += U) {
+      uint4 rows[U][VPL];
+      int gids[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int src = (j + u) & 31;
+        const int64_t pj = __shfl_sync(0xffffffffu, my_pix, src);
+        int gj = __shfl_sync(0xffffffffu, my_gid, src);
+        if (j + u >= cnt) gj = -1;
+        gids[u] = gj;
+        const bool want_row = CHECK ? (gj != -1) : (gj >= 0);
+        const uint8_t* row = a.emb + (pj - a.pix_base) * a.row_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          const int c = lane + 32 * v;
+          rows[u][v] = (want_row && c < a.nvec) ? ld_stream_v4(row + (size_t)c * 16) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int gj = gids[u];
+        if (gj == -1) continue;  // warp-uniform
+        if (CHECK) {
+          bool bad = false;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(rows[u][v]);
+          if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) ++n_bad;
+            continue;
+          }
+        }
+        if (gj < 0) continue;  // -2: checked only
+        if (gj != cur) {
+          flush();
+          cur = gj;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+      }
+    }
+    flush();
+  }
+  if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+}
+
+template <bool BF16, int VPL>
+static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
+  const int block = 256;
+  const int64_t n_chunks = (a.n + 31) >> 5;
+  int grid = (int)std::min<int64_t>(cdiv(n_chunks, block / 32), (int64_t)148 * 8);
+  if (grid < 1) grid = 1;
+  if (sorted) {
+    if (check)
+      accumulate_kernel<BF16, VPL, true, true><<<grid, block, 0, s>>>(a);
+    else
+      accumulate_kernel<BF16, VPL, true, false><<<grid, block, 0, s>>>(a);
+  } else {
+    if (check)
+      accumulate_kernel<BF16, VPL, false, true><<<grid, block, 0, s>>>(a);
+    else
+      accumulate_kernel<BF16, VPL, false, false><<<grid, block, 0, s>>>(a);
+  }
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
+int launch_accumulate(const AccArgs& a, bool bf16, bool sorted, bool check, cudaStream_t s) {
+  if (a.n <= 0) return VSM_OK;
+  const int vpl = (a.nvec + 31) / 32;
+  if (bf16) {
+    if (vpl <= 1) return launch_accumulate_t<true, 1>(a, sorted, check, s);
+    if (vpl <= 2) return launch_accumulate_t<true, 2>(a, sorted, check, s);
+    if (vpl <= 4) return launch_accumulate_t<true, 4>(a, sorted, check, s);
+    if (vpl <= 8) return launch_accumulate_t<true, 8>(a, sorted, check, s);
+  } else {
+    if (vpl <= 1) return launch_accumulate_t<false, 1>(a, sorted, check, s);
+    if (vpl <= 2) return launch_accumulate_t<false, 2>(a, sorted, check, s);
+    if (vpl <= 4) return launch_accumulate_t<false, 4>(a, sorted, check, s);
+    if (vpl <= 8) return launch_accumulate_t<false, 8>(a, sorted, check, s);
+  }
+  set_error("embedding dimension %d too large (max %d)", a.d, bf16 ? 2048 : 1024);
+  return VSM_E_INVALID;
+}
+
+// uint8 row mask: 1 where the pixel passes conf/stride/end_idx and all d channels are finite (map.py:247)
+template <bool BF16>
+__global__ void __launch_bounds__(256) emb_row_mask_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ emb,
+                                                           int64_t row_bytes, int nvec, int64_t n_px, int H, int W,
+                                                           int stride, float thr, uint8_t* __restrict__ out) {
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pix = warp; pix < n_px; pix += n_warps) {
+    bool on = conf[pix] >= thr;
+    if (on && stride > 1) {
+      const int w = (int)(pix % W), h = (int)((pix / W) % H);
+      on = (w % stride == 0) && (h % stride == 0);
+    }
+    bool bad = false;
+    if (on) {
+      const uint8_t* row = emb + pix * row_bytes;
+      for (int c = lane; c < nvec; c += 32) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + (size_t)c * 16));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) out[pix] = (on && !bad) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+int map_grow(vsm_map* m, int64_t need, cudaStream_t s) {
+  if (need <= m->vcap && m->gcap >= (uint64_t)2 * (uint64_t)std::max<int64_t>(m->vcap, 1)) return VSM_OK;
+  if (need >= (int64_t)1 << 31) {
+    set_error("voxel capacity %lld exceeds 2^31", (long long)need);
+    return VSM_E_INVALID;
+  }
+  int64_t new_cap = std::max<int64_t>(need, m->vcap + m->vcap / 2);
+  new_cap = std::max<int64_t>(new_cap, 1024);
+  const size_t d = (size_t)m->d;
+  const size_t keep = (size_t)m->n_vox;
+  VSM_CUDA(cudaStreamSynchronize(s));
+  // dense arrays (new space zeroed)
+  {
+    DevBuf nk, nc, ns;
+    VSM_TRY(nk.ensure((size_t)new_cap * 8, s));
+    VSM_TRY(nc.ensure((size_t)new_cap * 4, s));
+    VSM_TRY(ns.ensure((size_t)new_cap * d * 4, s));
+    VSM_CUDA(cudaMemsetAsync(nc.p, 0, (size_t)new_cap * 4, s));
+    VSM_CUDA(cudaMemsetAsync(ns.p, 0, (size_t)new_cap * d * 4, s));
+    if (keep) {
+      VSM_CUDA(cudaMemcpyAsync(nk.p, m->vkey.p, keep * 8, cudaMemcpyDeviceToDevice, s));
+      VSM_CUDA(cudaMemcpyAsync(nc.p, m->vcount.p, keep * 4, cudaMemcpyDeviceToDevice, s));
+      VSM_CUDA(cudaMemcpyAsync(ns.p, m->vsum.p, keep * d * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    VSM_CUDA(cudaStreamSynchronize(s));
+    m->vkey.release();
+    m->vcount.release();
+    m->vsum.release();
+    m->vkey = nk;
+    m->vcount = nc;
+    m->vsum = ns;
+  }
+  m->vcap = new_cap;
+  // hash table at load <= 0.5
+  const uint64_t gcap = next_pow2((uint64_t)2 * (uint64_t)new_cap);
+  if (gcap != m->gcap) {
+    m->gkeys.release();
+    m->gids.release();
+    VSM_TRY(m->gkeys.ensure(gcap * 8, s));
+    VSM_TRY(m->gids.ensure(gcap * 4, s));
+    m->gcap = gcap;
+    VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, gcap * 8, s));
+    VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, gcap * 4, s));
+    if (keep && !m->dense_loaded) {
+      rehash_kernel<<<grid_for((int64_t)keep, 256), 256, 0, s>>>(global_store(m), (uint32_t)keep);
+      VSM_LAUNCHED();
+    }
+  }
+  return VSM_OK;
+}
+
+int log_grow(vsm_map* m, int64_t need, cudaStream_t s) {
+  if (need <= m->log_cap) return VSM_OK;
+  const int64_t new_cap = std::max<int64_t>(need, m->log_cap * 2);
+  const size_t keep = (size_t)m->log_n;
+  VSM_TRY(m->log_gid.ensure((size_t)new_cap * 4, s, keep * 4));
+  VSM_TRY(m->log_fuse.ensure((size_t)new_cap * 4, s, keep * 4));
+  VSM_TRY(m->log_mask.ensure((size_t)new_cap * 16, s, keep * 16));
+  m->log_cap = new_cap;
+  return VSM_OK;
+}
+
+static int ensure_local_table(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& list, DevBuf* mask, uint64_t& cap,
+                              uint64_t need_cap, cudaStream_t s) {
+  if (cap >= need_cap) return VSM_OK;
+  VSM_TRY(keys.ensure(need_cap * 8, s));
+  VSM_TRY(count.ensure(need_cap * 4, s));
+  VSM_TRY(lid.ensure(need_cap * 4, s));
+  VSM_TRY(list.ensure(need_cap / 2 * 4 + 64, s));
+  VSM_CUDA(cudaMemsetAsync(keys.p, 0xFF, need_cap * 8, s));
+  VSM_CUDA(cudaMemsetAsync(count.p, 0, need_cap * 4, s));
+  if (mask) {
+    VSM_TRY(mask->ensure(need_cap * 16, s));
+    VSM_CUDA(cudaMemsetAsync(mask->p, 0, need_cap * 16, s));
+  }
+  cap = need_cap;
+  return VSM_OK;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// pixel -> voxel id without the sorted lists (pixel-order / host-streaming path).  With the filters on, pixels
+// that passed the confidence and finite tests but were dropped by the bbox / coarse filters get -2: their
+// embedding rows are still checked for non-finite values, because the reference removes such rows BEFORE it
+// computes the percentiles (map.py:247-258) and the optimistic pass must notice every one of them.
+__global__ void __launch_bounds__(256) point_gid_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
+                                                        int64_t n_px, LocalTable tb, const int32_t* __restrict__ lv_gid,
+                                                        int mark_checks, int32_t* __restrict__ point_gid) {
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_px;
+       pix += (int64_t)gridDim.x * blockDim.x) {
+    const int slot = pt_slot[pix];
+    int g = -1;
+    if (slot >= 0) {
+      g = lv_gid[tb.lid[slot]];
+    } else if (mark_checks) {
+      const uint32_t f = __float_as_uint(pw[pix].w);
+      if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) g = -2;
+    }
+    point_gid[pix] = g;
+  }
+}
+
+// voxel-sorted path: check the rows of the selected-but-filtered pixels (see point_gid_kernel)
+template <bool BF16>
+__global__ void __launch_bounds__(256) emb_check_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
+                                                        int64_t n_px, const uint8_t* __restrict__ emb, int64_t row_bytes,
+                                                        int nvec, FuseCounters* ctr) {
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned n_bad = 0;
+  for (int64_t base = warp << 5; base < n_px; base += n_warps << 5) {
+    const int64_t pix = base + lane;
+    bool need = false;
+    if (pix < n_px && pt_slot[pix] < 0) {
+      const uint32_t f = __float_as_uint(pw[pix].w);
+      need = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint8_t* row = emb + (base + j) * row_bytes;
+      bool bad = false;
+      for (int c = lane; c < nvec; c += 32) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + (size_t)c * 16));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+  }
+  if (n_bad) atomicAdd(&ctr->n_bad_emb, (unsigned long long)n_bad);
+}
+
+static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
+  if (!m || !p) {
+    set_error("null map or params");
+    return VSM_E_INVALID;
+  }
+  if (p->S <= 0 || p->H <= 0 || p->W <= 0 || p->end_idx < 0 || p->end_idx > p->S) {
+    set_error("bad dims S=%d H=%d W=%d end_idx=%d", p->S, p->H, p->W, p->end_idx);
+    return VSM_E_INVALID;
+  }
+  if (p->stride < 1) {
+    set_error("stride must be >= 1");  // map.py:187-188
+    return VSM_E_INVALID;
+  }
+  if (p->end_idx > VSM_MAX_FRAMES) {
+    set_error("%d frames in one submap, max %d", p->end_idx, VSM_MAX_FRAMES);
+    return VSM_E_TOO_MANY_FRAMES;
+  }
+  if ((int64_t)p->end_idx * p->H * p->W >= ((int64_t)1 << 32)) {
+    set_error("more than 2^32 pixels in one fuse call");
+    return VSM_E_INVALID;
+  }
+  if (m->dense_loaded) {
+    set_error("map was loaded from dense rows; fusing into it is not supported");
+    return VSM_E_STATE;
+  }
+  return VSM_OK;
+}
+
+
+struct HostEmb {
+  const uint8_t* emb_host = nullptr;  // (S,H,W,d) rows on the host, map dtype
+};
+
+static int ensure_stream_objects(vsm_map* m, size_t chunk_bytes) {
+  if (!m->copy_stream) VSM_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    if (!m->ev_stage[b]) VSM_CUDA(cudaEventCreateWithFlags(&m->ev_stage[b], cudaEventDisableTiming));
+    if (!m->ev_copy[b]) VSM_CUDA(cudaEventCreateWithFlags(&m->ev_copy[b], cudaEventDisableTiming));
+    VSM_TRY(m->stage_emb[b].ensure(chunk_bytes, nullptr));
+  }
+  return VSM_OK;
+}
+
+// One fuse call.  emb_dev: device embeddings (may be null when host != null: embeddings are then streamed
+// from the host frame by frame and accumulated in pixel order).
+static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
+                     const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s) {
+  const bool filters = (p->flags & VSM_FUSE_FILTERS) != 0;
+  const bool keep_index = (p->flags & VSM_FUSE_KEEP_POINT_INDEX) != 0;
+  const bool pixel_order = (p->flags & VSM_FUSE_PIXEL_ORDER) != 0 || host != nullptr;
+  const bool bf16 = m->cfg.emb_dtype == VSM_BF16;
+  const int64_t n_px = (int64_t)p->end_idx * p->H * p->W;
+  const int64_t px_per_frame = (int64_t)p->H * p->W;
+  const int64_t row_bytes = (int64_t)m->d * m->esize;
+  vsm_fuse_stats st{};
+  st.n_map_voxels = m->n_vox;
+  for (int i = 0; i < 3; ++i) st.bbox_lo[i] = st.bbox_hi[i] = __builtin_nanf("");
+
+  VSM_TRY(m->ctr.ensure(sizeof(FuseCounters), s));
+  FuseCounters* ctr = m->ctr.as<FuseCounters>();
+  VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters), s));
+  m->finalized = false;
+  m->ck_built = false;
+
+  FuseRecord rec{};
+  rec.submap_id = p->submap_id;
+  rec.S = p->S;
+  rec.H = p->H;
+  rec.W = p->W;
+  rec.end_idx = p->end_idx;
+  rec.stride = p->stride;
+  rec.log_begin = rec.log_end = m->log_n;
+  if (n_px == 0) {
+    m->fuses.push_back(rec);
+    if (stats) *stats = st;
+    return VSM_OK;
+  }
+
+  const int64_t hs = cdiv(p->H, p->stride), ws = cdiv(p->W, p->stride);
+  const uint64_t n_sel_max = (uint64_t)p->end_idx * hs * ws;
+  const uint64_t lcap = std::max<uint64_t>(next_pow2(2 * n_sel_max), 1024);
+  VSM_TRY(m->pw.ensure((size_t)n_px * 16, s));
+  VSM_TRY(m->pt_slot.ensure((size_t)n_px * 4, s));
+  VSM_TRY(ensure_local_table(m->tb_keys, m->tb_count, m->tb_lid, m->tb_list, &m->tb_mask, m->tb_cap, lcap, s));
+  if (filters)
+    VSM_TRY(ensure_local_table(m->ta_keys, m->ta_count, m->ta_lid, m->ta_list, nullptr, m->ta_cap, lcap, s));
+
+  LocalTable ta{}, tb{};
+  tb.keys = m->tb_keys.as<unsigned long long>();
+  tb.count = m->tb_count.as<uint32_t>();
+  tb.lid = m->tb_lid.as<uint32_t>();
+  tb.mask = m->tb_mask.as<unsigned long long>();
+  tb.slot_list = m->tb_list.as<uint32_t>();
+  tb.n_occ = &ctr->n_occ_b;
+  tb.cap_mask = (uint32_t)(m->tb_cap - 1);
+  if (filters) {
+    ta.keys = m->ta_keys.as<unsigned long long>();
+    ta.count = m->ta_count.as<uint32_t>();
+    ta.lid = m->ta_lid.as<uint32_t>();
+    ta.mask = nullptr;
+    ta.slot_list = m->ta_list.as<uint32_t>();
+    ta.n_occ = &ctr->n_occ_a;
+    ta.cap_mask = (uint32_t)(m->ta_cap - 1);
+  }
+
+  // optional exact finite-row filter on the embeddings (second read of the rows)
+  DevBuf precheck_mask;
+  if (filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr && emb_dev != nullptr) {
+    VSM_TRY(precheck_mask.ensure((size_t)n_px, s));
+    const int nvec = (int)(row_bytes / 16);
+    if (bf16)
+      emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
+                                                        p->conf_threshold, precheck_mask.as<uint8_t>());
+    else
+      emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
+                                                         p->conf_threshold, precheck_mask.as<uint8_t>());
+    VSM_LAUNCHED();
+    emb_ok = precheck_mask.as<uint8_t>();
+  }
+  struct Releaser {
+    DevBuf& b;
+    ~Releaser() { b.release(); }
+  } releaser{precheck_mask};
+
+  HMat Hm;
+  for (int i = 0; i < 16; ++i) Hm.m[i] = p->H_world_map[i];
+  WorldArgs wa;
+  wa.pts = pts;
+  wa.conf = conf;
+  wa.emb_ok = emb_ok;
+  wa.pw = m->pw.as<float4>();
+  wa.n_px = n_px;
+  wa.H = p->H;
+  wa.W = p->W;
+  wa.stride = p->stride;
+  wa.thr = p->conf_threshold;
+  if (aligned16(pts) && aligned16(conf) && n_px >= 4) {
+    world_points_vec4_kernel<<<grid_for(n_px >> 2, 256), 256, 0, s>>>(wa, Hm, ctr);
+  } else {
+    world_points_scalar_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(wa, Hm, ctr);
+  }
+  VSM_LAUNCHED();
+
+  FilterArgs fa;
+  fa.pw = m->pw.as<float4>();
+  fa.pt_slot = m->pt_slot.as<int32_t>();
+  fa.n_px = n_px;
+  fa.px_per_frame = px_per_frame;
+  fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
+  const int grid = grid_for(n_px, 256);
+  if (filters) {
+    SelectState* sst;
+    uint32_t* hist;
+    float* sel_out;
+    VSM_TRY(select_scratch(&sst, &hist, &sel_out));
+    SelSrc src;
+    src.base = reinterpret_cast<const float*>(m->pw.p);
+    src.stride = 4;
+    src.ncol = 3;
+    src.flag_off = 3;
+    src.flag_need = PF_SEL | PF_FINITE;
+    src.n_items = n_px;
+    const float q0 = (float)p->bbox_lo_pct / 100.0f;  // numpy: q / float32(100) in float32
+    const float q1 = (float)p->bbox_hi_pct / 100.0f;
+    VSM_TRY(run_percentiles(sst, hist, src, 2, q0, q1, ctr->bounds, s));
+    fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
+    bbox_coarse_kernel<<<grid, 256, 0, s>>>(fa, ta, ctr);
+    VSM_LAUNCHED();
+    fa.cell = m->vs_f;
+    fine_insert_kernel<true><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
+    VSM_LAUNCHED();
+  } else {
+    fa.cell = m->vs_f;
+    fine_insert_kernel<false><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
+    VSM_LAUNCHED();
+  }
+  FuseCounters hc{};
+  VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));
+  st.n_conf = (int64_t)hc.n_conf;
+  st.n_finite = (int64_t)hc.n_finite;
+  st.n_bbox = filters ? (int64_t)hc.n_bbox : (int64_t)hc.n_conf;
+  st.n_fused = (int64_t)hc.n_fused;
+  st.n_submap_voxels = hc.n_occ_b;
+  if (filters)
+    for (int i = 0; i < 3; ++i) {
+      st.bbox_lo[i] = hc.bounds[2 * i];
+      st.bbox_hi[i] = hc.bounds[2 * i + 1];
+    }
+  if (filters && hc.n_occ_a) {
+    table_cleanup_kernel<<<grid_for(hc.n_occ_a, 256), 256, 0, s>>>(ta, hc.n_occ_a);
+    VSM_LAUNCHED();
+  }
+  auto cleanup_b = [&]() -> int {
+    if (hc.n_occ_b) {
+      table_cleanup_kernel<<<grid_for(hc.n_occ_b, 256), 256, 0, s>>>(tb, hc.n_occ_b);
+      VSM_LAUNCHED();
+    }
+    return VSM_OK;
+  };
+  if (hc.internal_err || hc.range_err) {
+    VSM_TRY(cleanup_b());
+    if (stats) *stats = st;
+    if (hc.internal_err) {
+      set_error("internal: local hash probe limit hit (%u)", hc.internal_err);
+      return VSM_E_INTERNAL;
+    }
+    set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", hc.range_err);
+    return VSM_E_COORD_RANGE;
+  }
+  const uint32_t n_occ = hc.n_occ_b;
+  const int64_t n_fused = (int64_t)hc.n_fused;
+  if (n_occ == 0) {
+    m->fuses.push_back(rec);
+    if (stats) *stats = st;
+    return VSM_OK;
+  }
+
+  VSM_TRY(map_grow(m, m->n_vox + n_occ, s));
+  VSM_TRY(log_grow(m, m->log_n + n_occ, s));
+  VSM_TRY(m->lv_cnt.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  VSM_TRY(m->lv_off.ensure(((size_t)n_occ + 1) * 4, s, 0, 1.25));
+  VSM_TRY(m->lv_cursor.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  VSM_TRY(m->lv_gid.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  local_compact_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, m->lv_cnt.as<uint32_t>());
+  VSM_LAUNCHED();
+  global_merge_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, global_store(m), m->lv_cnt.as<uint32_t>(),
+                                                           m->lv_gid.as<int32_t>(), m->log_gid.as<int32_t>(),
+                                                           m->log_fuse.as<int32_t>(),
+                                                           m->log_mask.as<unsigned long long>(), m->log_n,
+                                                           p->submap_id, ctr);
+  VSM_LAUNCHED();
+  rec.log_end = m->log_n + n_occ;
+  rec.n_fused = n_fused;
+
+  int32_t* point_gid = nullptr;
+  if (keep_index) {
+    VSM_TRY(rec.point_gid.ensure((size_t)p->S * px_per_frame * 4, s));
+    point_gid = rec.point_gid.as<int32_t>();
+    if (p->end_idx < p->S)
+      VSM_CUDA(cudaMemsetAsync(point_gid + n_px, 0xFF, (size_t)(p->S - p->end_idx) * px_per_frame * 4, s));
+  } else if (pixel_order) {
+    VSM_TRY(m->sorted_gid.ensure((size_t)n_px * 4, s, 0, 1.1));  // reused as the per-pixel id array
+    point_gid = m->sorted_gid.as<int32_t>();
+  }
+
+  AccArgs aa{};
+  aa.row_bytes = row_bytes;
+  aa.vsum = m->vsum.as<float>();
+  aa.d = m->d;
+  aa.nvec = (int)(row_bytes / 16);
+  aa.ctr = ctr;
+  if (!pixel_order) {
+    size_t tmp_bytes = 0;
+    VSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m->lv_cnt.as<uint32_t>(), m->lv_off.as<uint32_t>(),
+                                           (int)n_occ, s));
+    VSM_TRY(m->cub_tmp.ensure(tmp_bytes, s));
+    VSM_CUDA(cub::DeviceScan::ExclusiveSum(m->cub_tmp.p, tmp_bytes, m->lv_cnt.as<uint32_t>(),
+                                           m->lv_off.as<uint32_t>(), (int)n_occ, s));
+    ++g_launches;
+    VSM_CUDA(cudaMemsetAsync(m->lv_cursor.p, 0, (size_t)n_occ * 4, s));
+    VSM_TRY(m->sorted_pix.ensure((size_t)n_fused * 4, s, 0, 1.1));
+    VSM_TRY(m->sorted_gid.ensure((size_t)n_fused * 4, s, 0, 1.1));
+    scatter_kernel<<<grid, 256, 0, s>>>(m->pt_slot.as<int32_t>(), n_px, tb, m->lv_off.as<uint32_t>(),
+                                        m->lv_cursor.as<uint32_t>(), m->lv_gid.as<int32_t>(),
+                                        m->sorted_pix.as<uint32_t>(), m->sorted_gid.as<int32_t>(), point_gid);
+    VSM_LAUNCHED();
+    VSM_TRY(cleanup_b());
+    aa.emb = emb_dev;
+    aa.pix_base = 0;
+    aa.sorted_pix = m->sorted_pix.as<uint32_t>();
+    aa.sorted_gid = m->sorted_gid.as<int32_t>();
+    aa.n = n_fused;
+    const bool check = filters && emb_ok == nullptr;
+    VSM_TRY(launch_accumulate(aa, bf16, true, check, s));
+    if (check && (int64_t)hc.n_finite > n_fused) {
+      if (bf16)
+        emb_check_kernel<true><<<grid_for(n_px, 256), 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px,
+                                                                   emb_dev, row_bytes, aa.nvec, ctr);
+      else
+        emb_check_kernel<false><<<grid_for(n_px, 256), 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px,
+                                                                    emb_dev, row_bytes, aa.nvec, ctr);
+      VSM_LAUNCHED();
+    }
+  } else {
+    const bool check = filters && emb_ok == nullptr;
+    point_gid_kernel<<<grid, 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px, tb,
+                                          m->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid);
+    VSM_LAUNCHED();
+    VSM_TRY(cleanup_b());
+    aa.point_gid = point_gid;
+    if (host == nullptr) {
+      aa.emb = emb_dev;
+      aa.pix_base = 0;
+      aa.n = n_px;
+      VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
+    } else {
+      // stream the embeddings frame by frame through two device buffers
+      const size_t chunk_bytes = (size_t)px_per_frame * row_bytes;
+      VSM_TRY(ensure_stream_objects(m, chunk_bytes));
+      for (int f = 0; f < p->end_idx; ++f) {
+        const int b = f & 1;
+        if (f >= 2) VSM_CUDA(cudaStreamWaitEvent(m->copy_stream, m->ev_stage[b], 0));
+        VSM_CUDA(cudaMemcpyAsync(m->stage_emb[b].p, host->emb_host + (size_t)f * chunk_bytes, chunk_bytes,
+                                 cudaMemcpyHostToDevice, m->copy_stream));
+        VSM_CUDA(cudaEventRecord(m->ev_copy[b], m->copy_stream));
+        VSM_CUDA(cudaStreamWaitEvent(s, m->ev_copy[b], 0));
+        aa.emb = m->stage_emb[b].as<uint8_t>();
+        aa.pix_base = (int64_t)f * px_per_frame;
+        aa.n = px_per_frame;
+        VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
+        VSM_CUDA(cudaEventRecord(m->ev_stage[b], s));
+      }
+    }
+  }
+
+  struct Tail {
+    unsigned long long n_bad;
+    uint32_t internal_err;
+    uint32_t n_vox;
+  };
+  VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));
+  uint32_t n_vox_dev = 0;
+  VSM_TRY(read_back(m, &n_vox_dev, m->d_n_vox.p, sizeof(uint32_t), s));
+  m->n_vox = (int64_t)n_vox_dev;
+  m->log_n = rec.log_end;
+  m->fuses.push_back(rec);
+  st.n_map_voxels = m->n_vox;
+  st.n_bad_emb_rows = (int64_t)hc.n_bad_emb;
+  if (stats) *stats = st;
+  if (hc.internal_err) {
+    set_error("internal: global hash overflow (%u)", hc.internal_err);
+    return VSM_E_INTERNAL;
+  }
+  if (hc.n_bad_emb) {
+    set_error("%llu non-finite embedding rows met in the optimistic filter pass; clear the map and fuse again with "
+              "VSM_FUSE_EMB_PRECHECK",
+              (unsigned long long)hc.n_bad_emb);
+    return VSM_E_NONFINITE_EMB;
+  }
+  return VSM_OK;
+}
+
+}  // namespace vsm
+
+using namespace vsm;
+
+extern "C" int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* conf_dev, const void* emb_dev,
+                               const uint8_t* emb_ok_dev, const vsm_fuse_params* p, vsm_fuse_stats* stats_host,
+                               void* stream) {
+  VSM_TRY(validate_params(m, p));
+  if (!pts_dev || !conf_dev || !emb_dev) {
+    set_error("null device pointer");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  return fuse_core(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p, stats_host,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const float* conf_host, const void* emb_host,
+                                    const vsm_fuse_params* p, vsm_fuse_stats* stats_host, void* stream) {
+  VSM_TRY(validate_params(m, p));
+  if (!pts_host || !conf_host || !emb_host) {
+    set_error("null host pointer");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n_px = (size_t)p->end_idx * p->H * p->W;
+  VSM_TRY(m->stage_pts.ensure(std::max<size_t>(n_px * 12, 16), s));
+  VSM_TRY(m->stage_conf.ensure(std::max<size_t>(n_px * 4, 16), s));
+  if (n_px) {
+    VSM_CUDA(cudaMemcpyAsync(m->stage_pts.p, pts_host, n_px * 12, cudaMemcpyHostToDevice, s));
+    VSM_CUDA(cudaMemcpyAsync(m->stage_conf.p, conf_host, n_px * 4, cudaMemcpyHostToDevice, s));
+  }
+  HostEmb he;
+  he.emb_host = (const uint8_t*)emb_host;
+  vsm_fuse_params q = *p;
+  q.flags &= ~VSM_FUSE_EMB_PRECHECK;  // not available when streaming from the host
+  return fuse_core(m, m->stage_pts.as<float>(), m->stage_conf.as<float>(), nullptr, nullptr, &he, &q, stats_host, s);
+}
+
+extern "C" int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, const void* emb_dev,
+                                      const vsm_fuse_params* p, uint8_t* out_mask_dev, void* stream) {
+  VSM_TRY(validate_params(m, p));
+  if (!conf_dev || !emb_dev || !out_mask_dev) {
+    set_error("null device pointer");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n_px = (int64_t)p->end_idx * p->H * p->W;
+  if (n_px == 0) return VSM_OK;
+  const int64_t row_bytes = (int64_t)m->d * m->esize;
+  const int nvec = (int)(row_bytes / 16);
+  if (m->cfg.emb_dtype == VSM_BF16)
+    emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, row_bytes, nvec, n_px, p->H,
+                                                      p->W, p->stride, p->conf_threshold, out_mask_dev);
+  else
+    emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, row_bytes, nvec, n_px, p->H,
+                                                       p->W, p->stride, p->conf_threshold, out_mask_dev);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}

@@ -1,0 +1,148 @@
+// state.cuh -- host-side state of a vsm_map and its device workspaces.
+//
+// Data layout in HBM:
+//   global hash     gkeys[GCAP] u64 (packed key | kEmptyKey), gids[GCAP] i32 -> dense voxel id
+//   dense store     vkey[VCAP] u64, vcount[VCAP] u32, vsum[VCAP*d] f32 (fp32 sums, never normalised in place)
+//   contributor log one entry per (fuse call, voxel): voxel id, fuse index, 2 x u64 frame mask
+//   per-call scratch world points float4[N_px], point->slot i32[N_px], two submap-local hash tables,
+//                   voxel-sorted (pixel, voxel id) lists for the accumulate kernel
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vsm {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  // grow to at least `need` bytes; old contents are dropped unless keep_bytes > 0
+  int ensure(size_t need, cudaStream_t s, size_t keep_bytes = 0, double slack = 1.0);
+  void release();
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+// submap-local open-addressing table (device view)
+struct LocalTable {
+  unsigned long long* keys;  // kEmptyKey when free
+  uint32_t* count;           // points per key
+  uint32_t* lid;             // local dense id of the slot (index into slot_list)
+  unsigned long long* mask;  // 2 x u64 frame mask per slot (fine table only, else nullptr)
+  uint32_t* slot_list;       // occupied slots in claim order
+  uint32_t* n_occ;           // number of occupied slots (device counter)
+  uint32_t cap_mask;         // capacity - 1
+};
+
+// device-resident counters of one fuse call (zeroed at the start of every call)
+struct FuseCounters {
+  unsigned long long n_conf, n_finite, n_bbox, n_fused, n_bad_emb;
+  uint32_t n_occ_a, n_occ_b;
+  uint32_t range_err, internal_err;
+  uint32_t n_new_voxels, pad;
+  float bounds[6];  // bbox filter bounds laid out [axis][lo,hi]
+};
+
+// radix-select state (device)
+constexpr int kSelMaxTargets = 12;
+struct SelectState {
+  unsigned long long n;                    // valid elements per column
+  unsigned long long rank[kSelMaxTargets]; // 0-based rank wanted
+  unsigned long long rem[kSelMaxTargets];  // rank inside the current prefix bucket
+  uint32_t prefix[kSelMaxTargets];
+  float value[kSelMaxTargets];
+  float gamma[kSelMaxTargets];             // lerp weight of the (lo,hi) pair the target belongs to
+  uint32_t nan_count[4];
+  int n_targets;
+  int targets_per_col;
+};
+
+struct FuseRecord {
+  int32_t submap_id;
+  int32_t S, H, W, end_idx, stride;
+  int64_t n_fused;
+  int64_t log_begin, log_end;  // entries of the contributor log written by this call
+  DevBuf point_gid;            // int32[S*H*W] voxel id per pixel (-1: not fused) if KEEP_POINT_INDEX
+};
+
+}  // namespace vsm
+
+struct vsm_map {
+  vsm_config cfg{};
+  int device = 0;
+  int d = 0;
+  int esize = 4;      // bytes per embedding element
+  float vs_f = 0.f;   // (float)voxel_size
+
+  // global hash + dense store
+  uint64_t gcap = 0;
+  vsm::DevBuf gkeys, gids;
+  int64_t vcap = 0;
+  int64_t n_vox = 0;  // host mirror of *d_n_vox
+  vsm::DevBuf vkey, vcount, vsum;
+  vsm::DevBuf d_n_vox;  // uint32 voxel counter on device
+
+  // contributor log
+  int64_t log_n = 0, log_cap = 0;
+  vsm::DevBuf log_gid, log_fuse, log_mask;
+  std::vector<vsm::FuseRecord> fuses;
+
+  // per-call scratch
+  vsm::DevBuf ctr;       // FuseCounters
+  vsm::DevBuf sel;       // SelectState
+  vsm::DevBuf sel_hist;  // histograms
+  vsm::DevBuf pw;        // float4[N_px]
+  vsm::DevBuf pt_slot;   // int32[N_px]
+  vsm::DevBuf ta_keys, ta_count, ta_lid, ta_list;           // coarse table
+  vsm::DevBuf tb_keys, tb_count, tb_lid, tb_list, tb_mask;  // fine table
+  uint64_t ta_cap = 0, tb_cap = 0;
+  vsm::DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
+  vsm::DevBuf sorted_pix, sorted_gid;
+  vsm::DevBuf cub_tmp;
+  vsm::DevBuf stage_pts, stage_conf, stage_emb[2];  // host-entry staging
+  void* pinned = nullptr;                           // pinned host scratch (counters read-back)
+  size_t pinned_bytes = 0;
+  void* pinned_stage[2] = {nullptr, nullptr};
+  size_t pinned_stage_bytes = 0;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+
+  // finalisation products
+  bool finalized = false;
+  bool dense_loaded = false;  // rows came from vsm_map_load_dense: rank == id, keys unknown
+  vsm::DevBuf sorted_keys, id_of_rank, rank_of_id;
+  vsm::DevBuf csr_off, csr_sub, csr_mask;
+  int64_t csr_entries = 0;
+  vsm::DevBuf dense_centers;  // float[V*3] for loaded maps
+  // compat lookup table keyed by reconstructed coords (3 x int64 hashed)
+  vsm::DevBuf ck_keys, ck_val;
+  uint64_t ck_cap = 0;
+  bool ck_built = false;
+  // query scratch
+  vsm::DevBuf q_cand, q_tmp, q_norm;
+};
+
+namespace vsm {
+// strided float source with an optional flag word per element
+struct SelSrc {
+  const float* base;  // element i, column c at base[i*stride + c]
+  int stride;
+  int ncol;
+  int flag_off;        // offset of the flag word inside the element, -1: no flags
+  uint32_t flag_need;  // (flags & flag_need) == flag_need -> element takes part
+  int64_t n_items;
+};
+
+// out_dev receives ncol*npct floats laid out [col][pct]; valid elements are counted in pass 0.
+int run_percentiles(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1, float* out_dev,
+                    cudaStream_t s);
+// process-wide scratch per device: select state, histograms, 16 result floats
+int select_scratch(SelectState** st, uint32_t** hist, float** out);
+int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);
+int log_grow(vsm_map* m, int64_t need_entries, cudaStream_t s);
+int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
+}  // namespace vsm

@@ -1,0 +1,251 @@
+"""SemanticVoxel / SemanticVoxelMap with the reference's API (vggt_slam/semantic_voxel.py:12-165),
+backed by a device-resident map: queries, position lookups and the index order come from libvsm
+kernels; numpy arrays and Python contributor lists are materialised from the device lazily.
+
+Behaviour kept from the reference, on purpose:
+  * voxel features are NOT normalised by ``query_with_embedding`` (A-1); ``normalize=True`` is an opt-in;
+  * ``_voxel_coords`` is the reference's lossy float32 reconstruction floor(centers/vs - 0.5) (A-4) and is what
+    ``query_with_embedding`` returns and what ``get_index_at_position`` looks up; ``exact_coords=True`` switches
+    the lookup to the true integer keys;
+  * ``get_latest_frame_at_voxel`` orders frame ids as *strings* and sorts the stored list in place (A-6).
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .voxel_map import DeviceVoxelMap, require_cuda
+
+
+class LazyContributors(Sequence):
+    """list[list[(submap_id, frame_id_str)]] produced on demand from the device's contributor tables.
+
+    ``maker(i)`` builds the list of voxel i; built lists are cached so that in-place mutation by
+    ``get_latest_frame_at_voxel`` persists, as it does for the reference's plain lists."""
+
+    def __init__(self, n: int, maker):
+        self._n = int(n)
+        self._maker = maker
+        self._cache: Dict[int, list] = {}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        i = int(i)
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError("voxel index out of range")
+        got = self._cache.get(i)
+        if got is None:
+            got = self._maker(i)
+            self._cache[i] = got
+        return got
+
+    def __iter__(self):
+        for i in range(self._n):
+            yield self[i]
+
+    def __eq__(self, other):
+        if isinstance(other, (list, LazyContributors)):
+            return len(other) == self._n and all(a == b for a, b in zip(self, other))
+        return NotImplemented
+
+    def tolist(self) -> list:
+        return [self[i] for i in range(self._n)]
+
+
+class SemanticVoxel:
+    """Same fields as the reference dataclass (vggt_slam/semantic_voxel.py:12-26): voxel_size,
+    centers_world (N,3), features (N,d), contributors (length-N list of lists of (submap_id, frame_id)).
+
+    When built by the device path, ``features`` and ``contributors`` are fetched from the GPU the first
+    time they are read."""
+
+    def __init__(self, voxel_size, centers_world, features, contributors):
+        self.voxel_size = voxel_size
+        self.centers_world = centers_world
+        self._features = features
+        self._features_fn = None
+        self.contributors = contributors
+
+    @classmethod
+    def lazy(cls, voxel_size, centers_world, features_fn, contributors):
+        v = cls(voxel_size, centers_world, None, contributors)
+        v._features_fn = features_fn
+        return v
+
+    @property
+    def features(self):
+        if self._features is None and self._features_fn is not None:
+            self._features = self._features_fn()
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._features = value
+
+    def __repr__(self):
+        n = 0 if self.centers_world is None else len(self.centers_world)
+        return f"SemanticVoxel(voxel_size={self.voxel_size}, n_voxels={n})"
+
+
+class SemanticVoxelMap:
+    """Semantic voxel map: saving, loading, querying (vggt_slam/semantic_voxel.py:29-165)."""
+
+    def __init__(self, voxels: SemanticVoxel, frame_name_maps: Dict[str, Dict[str, str]], _device_map=None,
+                 exact_coords: bool = False):
+        self.voxels = voxels
+        self.voxel_size = float(voxels.voxel_size)
+        self.frame_name_maps = frame_name_maps
+        self.exact_coords = bool(exact_coords)
+        self._dm: Optional[DeviceVoxelMap] = _device_map
+        self._coord_dict = None
+        n = 0 if voxels.centers_world is None else int(np.asarray(voxels.centers_world).shape[0])
+        if self._dm is None and n > 0:
+            # a map made from host arrays (load_from_directory, or user code): upload once
+            require_cuda()
+            feats = np.ascontiguousarray(np.asarray(voxels.features), dtype=np.float32)
+            d = int(feats.shape[1])
+            if d % 8 != 0:
+                raise ValueError("feature dimension must be a multiple of 8")
+            self._dm = DeviceVoxelMap(self.voxel_size, d, N.F32, capacity=max(n, 1024))
+            self._dm.load_dense(np.ascontiguousarray(voxels.centers_world, dtype=np.float32), feats)
+        if self._dm is not None and self._dm.num_voxels > 0:
+            _, _, _, recon = self._dm.export_geometry(coords=False, centers=False, counts=False, recon=True)
+            self._voxel_coords = recon.cpu().numpy()
+        else:
+            self._voxel_coords = np.zeros((0, 3), dtype=np.int64)
+
+    # -- getters (semantic_voxel.py:43-56) -----------------------------------
+    def get_voxels(self) -> SemanticVoxel:
+        return self.voxels
+
+    def get_voxel_size(self) -> float:
+        return self.voxel_size
+
+    def get_centers_world(self) -> np.ndarray:
+        return self.voxels.centers_world
+
+    def get_features(self) -> np.ndarray:
+        return self.voxels.features
+
+    def get_contributors(self):
+        return self.voxels.contributors
+
+    def resolve_contributor(self, submap_id: int, frame_id: str) -> Optional[str]:
+        return self.frame_name_maps[str(submap_id)][str(frame_id)]
+
+    # -- coordinates -----------------------------------------------------------
+    @staticmethod
+    def _centers_to_voxel_coords(centers_world: np.ndarray, voxel_size: float) -> np.ndarray:
+        """Host restatement kept for API compatibility (semantic_voxel.py:62-66); the map itself takes the
+        same values from the device (vsm_export_geometry's recon_coords)."""
+        return np.floor(centers_world / voxel_size - 0.5).astype(np.int64)
+
+    @staticmethod
+    def _position_to_voxel_coord(position_world: np.ndarray, voxel_size: float) -> Tuple[int, int, int]:
+        p = np.asarray(position_world, dtype=np.float32).reshape(3)
+        c = np.floor(p / voxel_size).astype(np.int64)
+        return int(c[0]), int(c[1]), int(c[2])
+
+    @property
+    def _coord_to_index(self) -> Dict[Tuple[int, int, int], int]:
+        """The reference's dict; built only if somebody asks for it (O(V) Python)."""
+        if self._coord_dict is None:
+            self._coord_dict = {(int(c[0]), int(c[1]), int(c[2])): i for i, c in enumerate(self._voxel_coords)}
+        return self._coord_dict
+
+    def get_indices_at_positions(self, positions_world: np.ndarray) -> np.ndarray:
+        """Batched get_index_at_position: (M,3) -> (M,) int64, -1 where no voxel exists."""
+        if self._dm is None:
+            return np.full((np.asarray(positions_world).reshape(-1, 3).shape[0],), -1, dtype=np.int64)
+        return self._dm.lookup(positions_world, compat=not self.exact_coords)
+
+    def get_index_at_position(self, position_world: np.ndarray) -> Optional[int]:
+        idx = int(self.get_indices_at_positions(np.asarray(position_world, dtype=np.float32).reshape(1, 3))[0])
+        return None if idx < 0 else idx
+
+    def get_features_at_position(self, position_world: np.ndarray) -> Optional[np.ndarray]:
+        idx = self.get_index_at_position(position_world)
+        if idx is None:
+            return None
+        return self.voxels.features[idx]
+
+    def get_voxel_coord_at_index(self, index: int):
+        return self._voxel_coords[index]
+
+    def get_contributors_at_position(self, position_world: np.ndarray):
+        idx = self.get_index_at_position(position_world)
+        if idx is None:
+            return None
+        return self.voxels.contributors[idx]
+
+    # -- query (semantic_voxel.py:97-116) --------------------------------------
+    def query_with_embeddings(self, qe: np.ndarray, top_k: int = 1, normalize: bool = False, engine: int = 0):
+        """Batched query: qe (P,d) -> (indices (P,k) int64, coords (P,k,3) int64, scores (P,k) float32), numpy."""
+        if self._dm is None or self._dm.num_voxels == 0:
+            raise RuntimeError("selected index k out of range")  # torch.topk on an empty map (Appendix A-13)
+        q = np.asarray(qe, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        try:
+            idx, sc = self._dm.query(q, top_k=top_k, normalize=normalize, engine=engine)
+        except ValueError as e:
+            if "exceeds" in str(e):
+                raise RuntimeError("selected index k out of range") from e
+            raise
+        idx = idx.cpu().numpy()
+        return idx, self._voxel_coords[idx], sc.cpu().numpy()
+
+    def query_with_embedding(self, qe: np.ndarray, top_k: int = 1, normalize: bool = False):
+        """One prompt, the reference's return types: (list[int], (k,3) int64 array, list[float])."""
+        q = np.asarray(qe, dtype=np.float32)
+        if q.ndim == 2 and q.shape[0] != 1:
+            raise ValueError("query_with_embedding scores one prompt; use query_with_embeddings for (P,d) batches")
+        idx, coords, sc = self.query_with_embeddings(q.reshape(1, -1), top_k=top_k, normalize=normalize)
+        return idx[0].tolist(), coords[0], [float(s) for s in sc[0]]
+
+    def get_latest_frame_at_voxel(self, voxel_index: int):
+        voxel_contributors = self.voxels.contributors[voxel_index]
+        voxel_contributors.sort(key=lambda x: (x[0], x[1]), reverse=True)
+        submap_id, frame_id = voxel_contributors[0]
+        return self.resolve_contributor(submap_id, frame_id), submap_id, frame_id
+
+    # -- persistence (semantic_voxel.py:128-165): same files, loadable by the reference ----------
+    def save_to_directory(self, directory_path: str) -> None:
+        os.makedirs(directory_path, exist_ok=True)
+        contribs = self.voxels.contributors
+        contribs = contribs.tolist() if isinstance(contribs, LazyContributors) else contribs
+        np.savez_compressed(
+            os.path.join(directory_path, "semantic_voxels.npz"),
+            voxel_size=np.float32(self.voxel_size),
+            centers_world=np.asarray(self.voxels.centers_world).astype(np.float32),
+            features=np.asarray(self.voxels.features).astype(np.float32),
+            contributors=np.array(contribs, dtype=object),
+        )
+        with open(os.path.join(directory_path, "frame_names.json"), "w") as f:
+            json.dump(self.frame_name_maps, f, indent=2)
+
+    @staticmethod
+    def load_from_directory(directory_path: str) -> "SemanticVoxelMap":
+        data = np.load(os.path.join(directory_path, "semantic_voxels.npz"), allow_pickle=True)
+        json_path = os.path.join(directory_path, "frame_names.json")
+        frame_name_maps: Dict[str, Dict[str, str]] = {}
+        if os.path.exists(json_path):
+            with open(json_path, "r") as f:
+                frame_name_maps = json.load(f)
+        vox = SemanticVoxel(
+            voxel_size=float(data["voxel_size"]),
+            centers_world=data["centers_world"],
+            features=data["features"],
+            contributors=list(data["contributors"].tolist()),
+        )
+        return SemanticVoxelMap(vox, frame_name_maps=frame_name_maps)
