@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- points fused / s of the semantic voxel-mapping hot path on B200.
+
+A step = one GraphMap.build_semantic_voxel_map over the workload (BASELINE.json configs[1]:
+20 submaps x 32 frames of 518x294 pointmaps, 512-d bf16 embeddings, 5 cm voxels, SL(4) transforms,
+the three outlier filters on) + finalisation.  Synthetic inputs (vsm.synth_device), larger than L2.
+
+  value      whole-job points fused / s with inputs resident in HBM (device tensors in the Submaps)
+  e2e        the same build through the public API with HOST (pinned) arrays: every step copies the
+             point maps, confidences and embeddings host->device inside the timed region and reads the
+             finished map (centres + features) back device->host
+  roofline   accumulate kernel: algorithmic bytes / CUDA-event time (events recorded inside libvsm on the
+             launching stream) against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample, 1 core
+
+`--impl reference` times that CPU port alone (the reference arm).  N>1 (torchrun): every rank fuses its own
+20 submaps (weak scaling), then voxels are exchanged by key-hash owner with an NCCL all-to-all and merged.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "vggt-slam_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "points fused/sec"
+UNIT = "points/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--submaps", type=int, default=20)
+    ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--height", type=int, default=294)
+    ap.add_argument("--width", type=int, default=518)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--voxel-size", type=float, default=0.05)
+    ap.add_argument("--emb-dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-submaps", type=int, default=-1, help="-1: all")
+    ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one submap in the CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--query", action="store_true", help="also report query latency on the built map")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of vggt_slam/map.py:170-381, numpy branch) on a bounded sample
+# ---------------------------------------------------------------------------
+def cpu_sample_inputs(args, seed=1234):
+    """One submap's first `cpu_frames` frames, host numpy.  Generated on the GPU when there is one (identical
+    generator to the GPU workload), else with the numpy generator."""
+    import torch
+
+    S = args.cpu_frames
+    if torch.cuda.is_available():
+        from vsm import synth_device
+
+        d = synth_device.make_submap_device(seed, 0, S=S, H=args.height, W=args.width, d=args.dim, mode="sl4")
+        pts, conf = d.points.cpu().numpy(), d.conf.cpu().numpy()
+        emb = d.emb.float().cpu().numpy()
+        Hm, paths = d.H_world_map, d.frame_paths
+        del d
+        torch.cuda.empty_cache()
+    else:
+        from vsm import synth
+
+        s = synth.make_submap(seed, 0, S=S, H=args.height, W=args.width, d=args.dim, mode="sl4", room=(12.0, 8.0, 3.0))
+        pts, conf, emb, Hm, paths = s.points, s.conf, s.emb, s.H_world_map, s.frame_paths
+    from oracle import voxel_oracle as vo
+
+    fids = [vo.frame_id_from_name(p) for p in paths]
+    names = {str(f): p for f, p in zip(fids, paths)}
+    return vo.OracleSubmap(0, pts, conf, vo.conf_threshold(conf, 25.0), emb, Hm, fids, names, S - 1)
+
+
+def cpu_run_once(sm, voxel_size):
+    from oracle import voxel_oracle as vo
+
+    t0 = time.perf_counter()
+    with np.errstate(all="ignore"):
+        out = vo.build_global([sm], voxel_size, exact_order=True, with_contributors=True)
+    vo.coord_index(vo.coords_from_centers(out.centers_world, voxel_size))  # SemanticVoxelMap.__init__'s dict
+    dt = time.perf_counter() - t0
+    return out.n_points, dt
+
+
+def cpu_baseline(args):
+    sm = cpu_sample_inputs(args)
+    n, dt = cpu_run_once(sm, args.voxel_size)
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32, "
+                      f"{n} points fused in {dt:.1f} s by the numpy oracle (np.unique + np.add.at are single-threaded)",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sm = cpu_sample_inputs(args)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run_once(sm, args.voxel_size)
+    n_tot, t_tot = 0, 0.0
+    for _ in range(args.steps):
+        n, dt = cpu_run_once(sm, args.voxel_size)
+        n_tot += n
+        t_tot += dt
+    v = n_tot / t_tot
+    sample = (f"each step: 1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32 "
+              f"({n_tot // max(args.steps, 1)} points) through the numpy oracle port of GraphMap.build_semantic_voxel_map")
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"8thfloor_small_static0-shaped synthetic: {args.submaps} submaps x {args.frames} frames per GPU, "
+                        f"{args.width}x{args.height} pointmaps, {args.dim}-d {args.emb_dtype} embeddings, "
+                        f"{args.voxel_size * 100:g} cm voxels, SL(4), outlier filters on",
+            "submaps_per_gpu": args.submaps, "frames": args.frames, "height": args.height, "width": args.width,
+            "dim": args.dim, "voxel_size": args.voxel_size, "emb_dtype": args.emb_dtype,
+            "parallelism": f"submaps sharded over {world} GPU(s)" + (", voxels owned by key hash, NCCL all-to-all + merge" if world > 1 else ""),
+            "l2_policy": "inputs larger than L2 (>= 4.9 GB of embeddings per submap, read once)"}
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the voxel-mapping path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import vsm
+    from vsm import _native as N
+    from vsm import synth_device
+    from vsm import dist as vdist
+
+    emb_dtype = torch.bfloat16 if args.emb_dtype == "bf16" else torch.float32
+    esize = 2 if args.emb_dtype == "bf16" else 4
+
+    # ---- inputs resident in HBM ------------------------------------------------
+    gm = vsm.GraphMap()
+    datas = []
+    for i in range(args.submaps):
+        sid = rank * args.submaps + i
+        d = synth_device.make_submap_device(1234, sid, S=args.frames, H=args.height, W=args.width, d=args.dim,
+                                            mode="sl4", emb_dtype=emb_dtype, first_frame_number=sid * args.frames)
+        datas.append(d)
+        gm.add_submap(synth_device.to_submap(d, host=False))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cap_hint = [1 << 18]
+
+    def step():
+        if world > 1:
+            m, stats = vdist.build_sharded(gm, args.voxel_size, capacity_hint=cap_hint[0], profile=True)
+        else:
+            m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], profile=True)
+            stats = gm.last_build_stats
+        cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.05) + 1024)
+        return m, stats
+
+    for _ in range(args.warmup):
+        m, stats = step()
+        del m
+    n_fused_step = sum(s["n_fused"] for s in stats)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = N.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = {"fuse_ms": 0.0, "accumulate_ms": 0.0, "accumulate_launches": 0, "accumulate_bytes": 0, "points_fused": 0}
+    ev0.record()
+    points = 0
+    last = None
+    for _ in range(args.steps):
+        last = None
+        m, stats = step()
+        points += sum(s["n_fused"] for s in stats)
+        for k in prof:
+            prof[k] += gm.last_profile[k]
+        last = m
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = N.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([elapsed_ms, float(points)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, points_all = float(tmax[0]), float(tsum[1])
+    else:
+        points_all = float(points)
+    value = points_all / (elapsed_ms * 1e-3)
+    n_vox = last._dm.num_voxels
+
+    # ---- roofline of the accumulate kernel ---------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    acc_gbs = prof["accumulate_bytes"] / max(prof["accumulate_ms"], 1e-9) * 1e-6
+    px_total = args.submaps * args.frames * args.height * args.width
+    fuse_bytes_step = px_total * 16 + n_fused_step * args.dim * esize + sum(s["n_submap_voxels"] for s in stats) * (4 * args.dim + 16)
+    roofline = {"bound": "hbm", "kernel": "vsm::accumulate_kernel", "achieved": acc_gbs, "peak": peak, "unit": "GB/s",
+                "frac": acc_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "accumulate_ms_per_launch": prof["accumulate_ms"] / max(prof["accumulate_launches"], 1),
+                "accumulate_share_of_step": prof["accumulate_ms"] * (1.0 if world == 1 else 1.0) / max(elapsed_ms, 1e-9),
+                "fuse_calls_GBps": fuse_bytes_step * args.steps / max(prof["fuse_ms"], 1e-9) * 1e-6,
+                "fuse_calls_frac": fuse_bytes_step * args.steps / max(prof["fuse_ms"], 1e-9) * 1e-6 / peak}
+
+    # ---- query latency (optional, reported inside config) ---------------------------
+    extra = {}
+    if args.query:
+        rng = np.random.default_rng(0)
+        for P in (1, 8):
+            q = rng.normal(size=(P, args.dim)).astype(np.float32)
+            q /= np.linalg.norm(q, axis=1, keepdims=True)
+            qt = torch.from_numpy(q).to(dev)
+            for _ in range(3):
+                last._dm.query(qt, top_k=10)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                last._dm.query(qt, top_k=10)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            extra[f"query_ms_P{P}_k10"] = ms
+            extra[f"query_GBps_P{P}"] = n_vox * args.dim * 4 / (ms * 1e-3) * 1e-9
+    del last, m
+
+    # ---- e2e: host arrays through the public API --------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = args.submaps if args.e2e_submaps < 0 else min(args.e2e_submaps, args.submaps)
+        gmh = vsm.GraphMap()
+        h2d = 0
+        for d in datas[:n_e2e]:
+            sm = synth_device.to_submap(d, host=True, pin=True)
+            sm.release_device_cache()
+            gmh.add_submap(sm)
+            h2d += d.points.numel() * 4 + d.conf.numel() * 4 + d.emb.numel() * esize
+        # free the device-resident copies: the e2e arm starts from host memory only
+        for sm in gm.get_submaps():
+            sm.release_device_cache()
+        del gm
+        datas.clear()
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            for sm in gmh.get_submaps():
+                sm.release_device_cache()
+            if world > 1:
+                mm, st = vdist.build_sharded(gmh, args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
+            else:
+                mm = gmh.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
+                st = gmh.last_build_stats
+            loc = mm.local if hasattr(mm, "local") else mm
+            feats = loc.get_features()  # device -> host read of the finished map
+            cen = loc.get_centers_world()
+            return sum(s["n_fused"] for s in st), feats.nbytes + cen.nbytes
+
+        e2e_step()  # warm-up (pinned staging, allocations)
+        barrier()
+        t0 = time.perf_counter()
+        pts_e2e, d2h = 0, 0
+        for _ in range(args.e2e_steps):
+            n, b = e2e_step()
+            pts_e2e += n
+            d2h = b
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt, float(pts_e2e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dt, pts_e2e = float(tmax[0]), float(tsum[1])
+        e2e = {"value": pts_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "submaps_per_gpu": n_e2e, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / max(args.e2e_steps, 1),
+               "api": "GraphMap.build_semantic_voxel_map on pinned host arrays -> vsm_fuse_submap_host; "
+                      "get_features()/get_centers_world() read the map back"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        cfg = workload_config(args, world)
+        cfg.update({"voxels": int(n_vox), "points_fused_per_step_per_gpu": int(n_fused_step)})
+        cfg.update(extra)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 accumulate of " + args.emb_dtype + " embeddings; f64 transform",
+                "data": "synthetic (device-generated box-room pointmaps, 1+Gamma(2,2) confidence, N(0,1) embeddings)",
+                "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,19 @@ VSM_API int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* conf_
 VSM_API int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const float* conf_host, const void* emb_host,
                          const vsm_fuse_params* p, vsm_fuse_stats* stats_host, void* stream);
 
+/* Device-time profile of the fuse calls since vsm_profile_enable(m, 1): CUDA events recorded on the caller's
+ * stream around the whole call and around the accumulate kernel (bench.py's roofline numbers). */
+typedef struct vsm_profile {
+  double fuse_ms;             /* device time of the fuse calls, first kernel to last */
+  double accumulate_ms;       /* device time of the accumulate kernel launches */
+  int64_t fuse_calls;
+  int64_t accumulate_launches;
+  int64_t accumulate_bytes;   /* algorithmic bytes of those launches: n_fused*d*elem_size + n_submap_voxels*d*4 */
+  int64_t points_fused;
+} vsm_profile;
+VSM_API int vsm_profile_enable(vsm_map* m, int on);
+VSM_API int vsm_profile_get(const vsm_map* m, vsm_profile* out_host);
+
 /* uint8[S*H*W] : 1 where conf>=thr (on the stride grid, frame<end_idx) and all d channels are finite (map.py:247) */
 VSM_API int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, const void* emb_dev, const vsm_fuse_params* p,
                            uint8_t* out_mask_dev, void* stream);

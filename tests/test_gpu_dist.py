@@ -1,0 +1,76 @@
+"""Multi-GPU exchange kernels on ONE GPU: two 'ranks' are two local maps in one process; their packed
+partials are routed by hand exactly as vsm.dist.build_sharded routes them with all-to-all, merged into two
+owner maps, and the union is compared with the single-map build (keys, counts bit-exact; features 1e-3)."""
+import numpy as np
+import pytest
+
+import golden_io as gio
+from vsm import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _local_map(vsm, subs, voxel_size):
+    from test_gpu_parity import to_submap
+
+    gm = vsm.GraphMap()
+    for s in subs:
+        gm.add_submap(to_submap(vsm, s, device_inputs=True))
+    return gm
+
+
+def test_pack_route_merge_equals_single_map():
+    import torch
+    import vsm
+    from vsm import voxel_map as vm
+    from vsm.map import wrap_device_map
+
+    world = 2
+    subs = [synth.make_submap(61, i, S=4, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
+                              first_frame_number=4 * i) for i in range(4)]
+    single = _local_map(vsm, subs, 0.05).build_semantic_voxel_map(0.05)
+    s_coords, _, s_counts, _ = single._dm.export_geometry()
+    s_keys = single._dm.export_packed_keys().cpu().numpy()
+
+    packs, cpacks, fused_all, names = [], [], [], {}
+    for r in range(world):
+        gm = _local_map(vsm, subs[r::world], 0.05)
+        dm, fused, nm = gm.fuse_into_device_map(0.05)
+        packs.append(dm.partials_pack(world))
+        cpacks.append(dm.contrib_pack(world))
+        # the size query agrees with the real pack
+        np.testing.assert_array_equal(dm.partials_counts(world), packs[-1][3])
+        assert int(packs[-1][3].sum()) == dm.num_voxels
+        fused_all += fused
+        names.update(nm)
+    owners = []
+    for o in range(world):
+        om = vm.DeviceVoxelMap(0.05, 64, 0, capacity=1024)  # small: exercises growth + rehash
+        for r in range(world):
+            keys, counts, sums, cnt = packs[r]
+            lo = int(cnt[:o].sum())
+            hi = lo + int(cnt[o])
+            om.partials_merge(keys[lo:hi].contiguous(), counts[lo:hi].contiguous(), sums[lo:hi].contiguous())
+            ckeys, csubs, cmasks, ccnt = cpacks[r]
+            lo = int(ccnt[:o].sum())
+            hi = lo + int(ccnt[o])
+            om.contrib_merge(ckeys[lo:hi].contiguous(), csubs[lo:hi].contiguous(), cmasks[lo:hi].contiguous())
+        om.finalize()
+        owners.append(om)
+    all_keys = np.concatenate([o.export_packed_keys().cpu().numpy() for o in owners])
+    assert len(np.unique(all_keys)) == len(all_keys) == len(s_keys)   # disjoint ownership, nothing lost
+    order = np.argsort(all_keys.view(np.uint64), kind="stable")
+    np.testing.assert_array_equal(all_keys[order], s_keys)
+    coords = np.concatenate([o.export_geometry()[0].cpu().numpy() for o in owners])[order]
+    counts = np.concatenate([o.export_geometry()[2].cpu().numpy() for o in owners])[order]
+    feats = np.concatenate([o.features_to_host() for o in owners])[order]
+    np.testing.assert_array_equal(coords, s_coords.cpu().numpy())
+    np.testing.assert_array_equal(counts, s_counts.cpu().numpy())
+    np.testing.assert_allclose(feats, single.get_features(), rtol=1e-3, atol=1e-5)
+    # contributors of the union == contributors of the single map
+    contribs = []
+    for o in owners:
+        m = wrap_device_map(o, fused_all, names, 0.05)
+        contribs += m.get_contributors().tolist()
+    contribs = [contribs[i] for i in order]
+    assert contribs == single.get_contributors().tolist()

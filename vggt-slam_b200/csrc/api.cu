@@ -52,6 +52,15 @@ void DevBuf::release() {
   bytes = 0;
 }
 
+Workspace* workspace_for_device(int device) {
+  static Workspace* table[64] = {nullptr};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return nullptr;
+  if (!table[device]) table[device] = new Workspace();
+  return table[device];
+}
+
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
   if (m->pinned_bytes < bytes) {
     if (m->pinned) cudaFreeHost(m->pinned);
@@ -112,6 +121,12 @@ extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
   m->d = cfg->dim;
   m->esize = esize;
   m->vs_f = (float)cfg->voxel_size;
+  m->ws = workspace_for_device(dev);
+  if (!m->ws) {
+    delete m;
+    set_error("device ordinal %d not supported", dev);
+    return VSM_E_INVALID;
+  }
   int st = m->d_n_vox.ensure(sizeof(uint32_t), nullptr);
   if (st == VSM_OK) st = cudaMemset(m->d_n_vox.p, 0, sizeof(uint32_t)) == cudaSuccess ? VSM_OK : VSM_E_CUDA;
   if (st == VSM_OK) st = map_grow(m, std::max<int64_t>(cfg->voxel_capacity, 1024), nullptr);
@@ -130,9 +145,7 @@ extern "C" int vsm_map_destroy(vsm_map* m) {
   cudaDeviceSynchronize();
   vsm::DevBuf* bufs[] = {&m->gkeys,     &m->gids,      &m->vkey,       &m->vcount,    &m->vsum,       &m->d_n_vox,
                          &m->log_gid,   &m->log_fuse,  &m->log_mask,   &m->ctr,       &m->sel,        &m->sel_hist,
-                         &m->pw,        &m->pt_slot,   &m->ta_keys,    &m->ta_count,  &m->ta_lid,     &m->ta_list,
-                         &m->tb_keys,   &m->tb_count,  &m->tb_lid,     &m->tb_list,   &m->tb_mask,    &m->lv_cnt,
-                         &m->lv_off,    &m->lv_cursor, &m->lv_gid,     &m->sorted_pix, &m->sorted_gid, &m->cub_tmp,
+                         &m->cub_tmp,
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
                          &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm};
@@ -145,6 +158,8 @@ extern "C" int vsm_map_destroy(vsm_map* m) {
     if (m->ev_copy[b]) cudaEventDestroy(m->ev_copy[b]);
   }
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (int i = 0; i < 3; ++i)
+    if (m->ev_prof[i]) cudaEventDestroy(m->ev_prof[i]);
   cudaGetLastError();
   delete m;
   return VSM_OK;

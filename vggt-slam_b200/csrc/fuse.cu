@@ -741,6 +741,9 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters), s));
   m->finalized = false;
   m->ck_built = false;
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  const bool prof = m->profiling && host == nullptr;
+  if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[0], s));
 
   FuseRecord rec{};
   rec.submap_id = p->submap_id;
@@ -759,28 +762,28 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   const int64_t hs = cdiv(p->H, p->stride), ws = cdiv(p->W, p->stride);
   const uint64_t n_sel_max = (uint64_t)p->end_idx * hs * ws;
   const uint64_t lcap = std::max<uint64_t>(next_pow2(2 * n_sel_max), 1024);
-  VSM_TRY(m->pw.ensure((size_t)n_px * 16, s));
-  VSM_TRY(m->pt_slot.ensure((size_t)n_px * 4, s));
-  VSM_TRY(ensure_local_table(m->tb_keys, m->tb_count, m->tb_lid, m->tb_list, &m->tb_mask, m->tb_cap, lcap, s));
+  VSM_TRY(m->ws->pw.ensure((size_t)n_px * 16, s));
+  VSM_TRY(m->ws->pt_slot.ensure((size_t)n_px * 4, s));
+  VSM_TRY(ensure_local_table(m->ws->tb_keys, m->ws->tb_count, m->ws->tb_lid, m->ws->tb_list, &m->ws->tb_mask, m->ws->tb_cap, lcap, s));
   if (filters)
-    VSM_TRY(ensure_local_table(m->ta_keys, m->ta_count, m->ta_lid, m->ta_list, nullptr, m->ta_cap, lcap, s));
+    VSM_TRY(ensure_local_table(m->ws->ta_keys, m->ws->ta_count, m->ws->ta_lid, m->ws->ta_list, nullptr, m->ws->ta_cap, lcap, s));
 
   LocalTable ta{}, tb{};
-  tb.keys = m->tb_keys.as<unsigned long long>();
-  tb.count = m->tb_count.as<uint32_t>();
-  tb.lid = m->tb_lid.as<uint32_t>();
-  tb.mask = m->tb_mask.as<unsigned long long>();
-  tb.slot_list = m->tb_list.as<uint32_t>();
+  tb.keys = m->ws->tb_keys.as<unsigned long long>();
+  tb.count = m->ws->tb_count.as<uint32_t>();
+  tb.lid = m->ws->tb_lid.as<uint32_t>();
+  tb.mask = m->ws->tb_mask.as<unsigned long long>();
+  tb.slot_list = m->ws->tb_list.as<uint32_t>();
   tb.n_occ = &ctr->n_occ_b;
-  tb.cap_mask = (uint32_t)(m->tb_cap - 1);
+  tb.cap_mask = (uint32_t)(m->ws->tb_cap - 1);
   if (filters) {
-    ta.keys = m->ta_keys.as<unsigned long long>();
-    ta.count = m->ta_count.as<uint32_t>();
-    ta.lid = m->ta_lid.as<uint32_t>();
+    ta.keys = m->ws->ta_keys.as<unsigned long long>();
+    ta.count = m->ws->ta_count.as<uint32_t>();
+    ta.lid = m->ws->ta_lid.as<uint32_t>();
     ta.mask = nullptr;
-    ta.slot_list = m->ta_list.as<uint32_t>();
+    ta.slot_list = m->ws->ta_list.as<uint32_t>();
     ta.n_occ = &ctr->n_occ_a;
-    ta.cap_mask = (uint32_t)(m->ta_cap - 1);
+    ta.cap_mask = (uint32_t)(m->ws->ta_cap - 1);
   }
 
   // optional exact finite-row filter on the embeddings (second read of the rows)
@@ -808,7 +811,7 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   wa.pts = pts;
   wa.conf = conf;
   wa.emb_ok = emb_ok;
-  wa.pw = m->pw.as<float4>();
+  wa.pw = m->ws->pw.as<float4>();
   wa.n_px = n_px;
   wa.H = p->H;
   wa.W = p->W;
@@ -822,8 +825,8 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   VSM_LAUNCHED();
 
   FilterArgs fa;
-  fa.pw = m->pw.as<float4>();
-  fa.pt_slot = m->pt_slot.as<int32_t>();
+  fa.pw = m->ws->pw.as<float4>();
+  fa.pt_slot = m->ws->pt_slot.as<int32_t>();
   fa.n_px = n_px;
   fa.px_per_frame = px_per_frame;
   fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
@@ -834,7 +837,7 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     float* sel_out;
     VSM_TRY(select_scratch(&sst, &hist, &sel_out));
     SelSrc src;
-    src.base = reinterpret_cast<const float*>(m->pw.p);
+    src.base = reinterpret_cast<const float*>(m->ws->pw.p);
     src.stride = 4;
     src.ncol = 3;
     src.flag_off = 3;
@@ -897,14 +900,14 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
 
   VSM_TRY(map_grow(m, m->n_vox + n_occ, s));
   VSM_TRY(log_grow(m, m->log_n + n_occ, s));
-  VSM_TRY(m->lv_cnt.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  VSM_TRY(m->lv_off.ensure(((size_t)n_occ + 1) * 4, s, 0, 1.25));
-  VSM_TRY(m->lv_cursor.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  VSM_TRY(m->lv_gid.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  local_compact_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, m->lv_cnt.as<uint32_t>());
+  VSM_TRY(m->ws->lv_cnt.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  VSM_TRY(m->ws->lv_off.ensure(((size_t)n_occ + 1) * 4, s, 0, 1.25));
+  VSM_TRY(m->ws->lv_cursor.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  VSM_TRY(m->ws->lv_gid.ensure((size_t)n_occ * 4, s, 0, 1.25));
+  local_compact_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, m->ws->lv_cnt.as<uint32_t>());
   VSM_LAUNCHED();
-  global_merge_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, global_store(m), m->lv_cnt.as<uint32_t>(),
-                                                           m->lv_gid.as<int32_t>(), m->log_gid.as<int32_t>(),
+  global_merge_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, global_store(m), m->ws->lv_cnt.as<uint32_t>(),
+                                                           m->ws->lv_gid.as<int32_t>(), m->log_gid.as<int32_t>(),
                                                            m->log_fuse.as<int32_t>(),
                                                            m->log_mask.as<unsigned long long>(), m->log_n,
                                                            p->submap_id, ctr);
@@ -919,8 +922,8 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     if (p->end_idx < p->S)
       VSM_CUDA(cudaMemsetAsync(point_gid + n_px, 0xFF, (size_t)(p->S - p->end_idx) * px_per_frame * 4, s));
   } else if (pixel_order) {
-    VSM_TRY(m->sorted_gid.ensure((size_t)n_px * 4, s, 0, 1.1));  // reused as the per-pixel id array
-    point_gid = m->sorted_gid.as<int32_t>();
+    VSM_TRY(m->ws->sorted_gid.ensure((size_t)n_px * 4, s, 0, 1.1));  // reused as the per-pixel id array
+    point_gid = m->ws->sorted_gid.as<int32_t>();
   }
 
   AccArgs aa{};
@@ -931,40 +934,42 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   aa.ctr = ctr;
   if (!pixel_order) {
     size_t tmp_bytes = 0;
-    VSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m->lv_cnt.as<uint32_t>(), m->lv_off.as<uint32_t>(),
+    VSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m->ws->lv_cnt.as<uint32_t>(), m->ws->lv_off.as<uint32_t>(),
                                            (int)n_occ, s));
     VSM_TRY(m->cub_tmp.ensure(tmp_bytes, s));
-    VSM_CUDA(cub::DeviceScan::ExclusiveSum(m->cub_tmp.p, tmp_bytes, m->lv_cnt.as<uint32_t>(),
-                                           m->lv_off.as<uint32_t>(), (int)n_occ, s));
+    VSM_CUDA(cub::DeviceScan::ExclusiveSum(m->cub_tmp.p, tmp_bytes, m->ws->lv_cnt.as<uint32_t>(),
+                                           m->ws->lv_off.as<uint32_t>(), (int)n_occ, s));
     ++g_launches;
-    VSM_CUDA(cudaMemsetAsync(m->lv_cursor.p, 0, (size_t)n_occ * 4, s));
-    VSM_TRY(m->sorted_pix.ensure((size_t)n_fused * 4, s, 0, 1.1));
-    VSM_TRY(m->sorted_gid.ensure((size_t)n_fused * 4, s, 0, 1.1));
-    scatter_kernel<<<grid, 256, 0, s>>>(m->pt_slot.as<int32_t>(), n_px, tb, m->lv_off.as<uint32_t>(),
-                                        m->lv_cursor.as<uint32_t>(), m->lv_gid.as<int32_t>(),
-                                        m->sorted_pix.as<uint32_t>(), m->sorted_gid.as<int32_t>(), point_gid);
+    VSM_CUDA(cudaMemsetAsync(m->ws->lv_cursor.p, 0, (size_t)n_occ * 4, s));
+    VSM_TRY(m->ws->sorted_pix.ensure((size_t)n_fused * 4, s, 0, 1.1));
+    VSM_TRY(m->ws->sorted_gid.ensure((size_t)n_fused * 4, s, 0, 1.1));
+    scatter_kernel<<<grid, 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), n_px, tb, m->ws->lv_off.as<uint32_t>(),
+                                        m->ws->lv_cursor.as<uint32_t>(), m->ws->lv_gid.as<int32_t>(),
+                                        m->ws->sorted_pix.as<uint32_t>(), m->ws->sorted_gid.as<int32_t>(), point_gid);
     VSM_LAUNCHED();
     VSM_TRY(cleanup_b());
     aa.emb = emb_dev;
     aa.pix_base = 0;
-    aa.sorted_pix = m->sorted_pix.as<uint32_t>();
-    aa.sorted_gid = m->sorted_gid.as<int32_t>();
+    aa.sorted_pix = m->ws->sorted_pix.as<uint32_t>();
+    aa.sorted_gid = m->ws->sorted_gid.as<int32_t>();
     aa.n = n_fused;
     const bool check = filters && emb_ok == nullptr;
+    if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[1], s));
     VSM_TRY(launch_accumulate(aa, bf16, true, check, s));
+    if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[2], s));
     if (check && (int64_t)hc.n_finite > n_fused) {
       if (bf16)
-        emb_check_kernel<true><<<grid_for(n_px, 256), 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px,
+        emb_check_kernel<true><<<grid_for(n_px, 256), 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px,
                                                                    emb_dev, row_bytes, aa.nvec, ctr);
       else
-        emb_check_kernel<false><<<grid_for(n_px, 256), 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px,
+        emb_check_kernel<false><<<grid_for(n_px, 256), 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px,
                                                                     emb_dev, row_bytes, aa.nvec, ctr);
       VSM_LAUNCHED();
     }
   } else {
     const bool check = filters && emb_ok == nullptr;
-    point_gid_kernel<<<grid, 256, 0, s>>>(m->pt_slot.as<int32_t>(), m->pw.as<float4>(), n_px, tb,
-                                          m->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid);
+    point_gid_kernel<<<grid, 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px, tb,
+                                          m->ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid);
     VSM_LAUNCHED();
     VSM_TRY(cleanup_b());
     aa.point_gid = point_gid;
@@ -972,7 +977,9 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
       aa.emb = emb_dev;
       aa.pix_base = 0;
       aa.n = n_px;
+      if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[1], s));
       VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
+      if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[2], s));
     } else {
       // stream the embeddings frame by frame through two device buffers
       const size_t chunk_bytes = (size_t)px_per_frame * row_bytes;
@@ -1002,6 +1009,17 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   uint32_t n_vox_dev = 0;
   VSM_TRY(read_back(m, &n_vox_dev, m->d_n_vox.p, sizeof(uint32_t), s));
   m->n_vox = (int64_t)n_vox_dev;
+  if (prof) {
+    float t_all = 0.f, t_acc = 0.f;
+    VSM_CUDA(cudaEventElapsedTime(&t_all, m->ev_prof[0], m->ev_prof[2]));
+    VSM_CUDA(cudaEventElapsedTime(&t_acc, m->ev_prof[1], m->ev_prof[2]));
+    m->prof.fuse_ms += t_all;
+    m->prof.accumulate_ms += t_acc;
+    m->prof.fuse_calls += 1;
+    m->prof.accumulate_launches += 1;
+    m->prof.accumulate_bytes += n_fused * row_bytes + (int64_t)n_occ * m->d * 4;
+    m->prof.points_fused += n_fused;
+  }
   m->log_n = rec.log_end;
   m->fuses.push_back(rec);
   st.n_map_voxels = m->n_vox;
@@ -1058,6 +1076,28 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   vsm_fuse_params q = *p;
   q.flags &= ~VSM_FUSE_EMB_PRECHECK;  // not available when streaming from the host
   return fuse_core(m, m->stage_pts.as<float>(), m->stage_conf.as<float>(), nullptr, nullptr, &he, &q, stats_host, s);
+}
+
+extern "C" int vsm_profile_enable(vsm_map* m, int on) {
+  if (!m) {
+    set_error("null map");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  for (int i = 0; i < 3; ++i)
+    if (on && !m->ev_prof[i]) VSM_CUDA(cudaEventCreate(&m->ev_prof[i]));
+  m->profiling = on != 0;
+  m->prof = vsm_profile{};
+  return VSM_OK;
+}
+
+extern "C" int vsm_profile_get(const vsm_map* m, vsm_profile* out_host) {
+  if (!m || !out_host) {
+    set_error("null argument");
+    return VSM_E_INVALID;
+  }
+  *out_host = m->prof;
+  return VSM_OK;
 }
 
 extern "C" int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, const void* emb_dev,

@@ -7,6 +7,7 @@
 //   per-call scratch world points float4[N_px], point->slot i32[N_px], two submap-local hash tables,
 //                   voxel-sorted (pixel, voxel id) lists for the accumulate kernel
 #pragma once
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -70,12 +71,30 @@ struct FuseRecord {
 
 }  // namespace vsm
 
+namespace vsm {
+// Per-device scratch shared by all maps of the process (fuse calls borrow it under the mutex): world points,
+// point -> slot, the two submap-local hash tables (left clean by every call), per-local-voxel arrays and the
+// voxel-sorted point lists.  Kept across maps so that building a new map does not re-allocate ~1 GB.
+struct Workspace {
+  std::mutex mu;
+  DevBuf pw;        // float4[N_px]
+  DevBuf pt_slot;   // int32[N_px]
+  DevBuf ta_keys, ta_count, ta_lid, ta_list;           // coarse table
+  DevBuf tb_keys, tb_count, tb_lid, tb_list, tb_mask;  // fine table
+  uint64_t ta_cap = 0, tb_cap = 0;
+  DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
+  DevBuf sorted_pix, sorted_gid;
+};
+Workspace* workspace_for_device(int device);
+}  // namespace vsm
+
 struct vsm_map {
   vsm_config cfg{};
   int device = 0;
   int d = 0;
   int esize = 4;      // bytes per embedding element
   float vs_f = 0.f;   // (float)voxel_size
+  vsm::Workspace* ws = nullptr;
 
   // global hash + dense store
   uint64_t gcap = 0;
@@ -94,13 +113,6 @@ struct vsm_map {
   vsm::DevBuf ctr;       // FuseCounters
   vsm::DevBuf sel;       // SelectState
   vsm::DevBuf sel_hist;  // histograms
-  vsm::DevBuf pw;        // float4[N_px]
-  vsm::DevBuf pt_slot;   // int32[N_px]
-  vsm::DevBuf ta_keys, ta_count, ta_lid, ta_list;           // coarse table
-  vsm::DevBuf tb_keys, tb_count, tb_lid, tb_list, tb_mask;  // fine table
-  uint64_t ta_cap = 0, tb_cap = 0;
-  vsm::DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
-  vsm::DevBuf sorted_pix, sorted_gid;
   vsm::DevBuf cub_tmp;
   vsm::DevBuf stage_pts, stage_conf, stage_emb[2];  // host-entry staging
   void* pinned = nullptr;                           // pinned host scratch (counters read-back)
@@ -110,6 +122,11 @@ struct vsm_map {
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
+
+  // profiling (vsm_profile_enable)
+  bool profiling = false;
+  cudaEvent_t ev_prof[3] = {nullptr, nullptr, nullptr};
+  vsm_profile prof{};
 
   // finalisation products
   bool finalized = false;

@@ -50,6 +50,11 @@ class FuseStats(C.Structure):
                 "n_bad_emb_rows": self.n_bad_emb_rows, "bbox_lo": list(self.bbox_lo), "bbox_hi": list(self.bbox_hi)}
 
 
+class Profile(C.Structure):
+    _fields_ = [("fuse_ms", C.c_double), ("accumulate_ms", C.c_double), ("fuse_calls", C.c_int64),
+                ("accumulate_launches", C.c_int64), ("accumulate_bytes", C.c_int64), ("points_fused", C.c_int64)]
+
+
 _vp, _i32, _i64, _f32, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _P = C.POINTER
 
@@ -67,6 +72,8 @@ SIGNATURES = {
     "vsm_select_points": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _P(_f64), _vp, _vp, _P(_i64), _vp]),
     "vsm_fuse_submap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _P(FuseParams), _P(FuseStats), _vp]),
     "vsm_fuse_submap_host": (C.c_int, [_vp, _vp, _vp, _vp, _P(FuseParams), _P(FuseStats), _vp]),
+    "vsm_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "vsm_profile_get": (C.c_int, [_vp, _P(Profile)]),
     "vsm_embedding_row_mask": (C.c_int, [_vp, _vp, _vp, _P(FuseParams), _vp, _vp]),
     "vsm_finalize": (C.c_int, [_vp, _vp]),
     "vsm_num_voxels": (C.c_int, [_vp, _P(_i64)]),

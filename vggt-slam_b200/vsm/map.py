@@ -20,6 +20,7 @@ class GraphMap:
     def __init__(self):
         self.submaps = dict()
         self.last_build_stats: List[dict] = []
+        self.last_profile = None
 
     def get_num_submaps(self):
         return len(self.submaps)
@@ -98,7 +99,7 @@ class GraphMap:
     def build_semantic_voxel_map(self, voxel_size: float, stride: int = 1, ignore_loop_closure_frames: bool = True,
                                  deduplicate_contributors: bool = True, use_torch: bool = True,
                                  capacity_hint: Optional[int] = None, host_streaming: Optional[bool] = None,
-                                 exact_coords: bool = False) -> SemanticVoxelMap:
+                                 exact_coords: bool = False, profile: bool = False) -> SemanticVoxelMap:
         """Fuse every submap into one global voxel map on the GPU.
 
         Per submap: confidence mask, float64 world transform, the finite / percentile-box / coarse-cell
@@ -107,6 +108,18 @@ class GraphMap:
         ``host_streaming``: True streams host embeddings frame by frame through pinned buffers
         (vsm_fuse_submap_host); default: used when the embeddings are host arrays.
         """
+        dm, fused, frame_name_maps = self.fuse_into_device_map(voxel_size, stride, ignore_loop_closure_frames,
+                                                               deduplicate_contributors, capacity_hint,
+                                                               host_streaming, profile)
+        if dm is None or dm.num_voxels == 0:
+            return SemanticVoxelMap(_empty_voxels(voxel_size), frame_name_maps=frame_name_maps)
+        dm.finalize()
+        return wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contributors, exact_coords)
+
+    def fuse_into_device_map(self, voxel_size, stride=1, ignore_loop_closure_frames=True,
+                             deduplicate_contributors=True, capacity_hint=None, host_streaming=None, profile=False):
+        """The per-submap loop of build_semantic_voxel_map: returns (DeviceVoxelMap or None, fused-call records,
+        frame_name_maps) before finalisation (the multi-GPU build exchanges voxels at this point)."""
         if voxel_size <= 0.0:
             raise ValueError("voxel_size must be > 0")
         if stride < 1:
@@ -123,12 +136,14 @@ class GraphMap:
             todo.append(submap)
         frame_name_maps: Dict[str, Dict[str, str]] = {}
         self.last_build_stats = []
+        self.last_profile = None
         if not todo:
-            return SemanticVoxelMap(_empty_voxels(voxel_size), frame_name_maps=frame_name_maps)
-
+            return None, [], frame_name_maps
         d = _shape(todo[0].semantic_embeddings)[-1]
         code = todo[0].embedding_dtype_code()
         dm = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=capacity_hint or (1 << 18))
+        if profile:
+            dm.profile_enable(True)
         flags = N.FUSE_FILTERS | (0 if deduplicate_contributors else N.FUSE_KEEP_POINT_INDEX)
         fused: List[dict] = []
         try:
@@ -140,19 +155,13 @@ class GraphMap:
             fused.clear()
             frame_name_maps.clear()
             self.last_build_stats = []
+            if profile:
+                dm.profile_enable(True)
             self._fuse_all(dm, todo, stride, ignore_loop_closure_frames, flags | N.FUSE_EMB_PRECHECK, False, fused,
                            frame_name_maps)
-        if dm.num_voxels == 0:
-            return SemanticVoxelMap(_empty_voxels(voxel_size), frame_name_maps=frame_name_maps)
-        dm.finalize()
-        V = dm.num_voxels
-        _, centers, _, _ = dm.export_geometry(coords=False, centers=True, counts=False, recon=False)
-        if deduplicate_contributors:
-            contributors = _dedup_contributors(dm, fused, V)
-        else:
-            contributors = _per_point_contributors_global(dm, fused, V)
-        vox = SemanticVoxel.lazy(float(voxel_size), centers.cpu().numpy(), dm.features_to_host, contributors)
-        return SemanticVoxelMap(vox, frame_name_maps=frame_name_maps, _device_map=dm, exact_coords=exact_coords)
+        if profile:
+            self.last_profile = dm.profile()
+        return dm, fused, frame_name_maps
 
     def _fuse_all(self, dm, todo, stride, ignore_loop, flags, host_streaming, fused, frame_name_maps):
         for submap in todo:
@@ -163,8 +172,8 @@ class GraphMap:
             if submap.embedding_dtype_code() != dm.emb_dtype or _shape(submap.semantic_embeddings)[-1] != dm.dim:
                 raise ValueError("all submaps must carry embeddings of the same dtype and dimension")
             n_ids = 0 if submap.frame_ids is None else len(submap.frame_ids)
-            conf_dev = submap._device("conf")
             if end_idx > n_ids:
+                conf_dev = submap._device("conf")
                 # upstream builds str(frame_ids[i]) for every kept point (map.py:239-240) and fails on
                 # frames without an id (loop-closure frames)
                 hs = conf_dev[n_ids:end_idx, ::stride, ::stride]
@@ -179,7 +188,7 @@ class GraphMap:
                 pts = submap.pointclouds if isinstance(submap.pointclouds, np.ndarray) else None
                 if pts is None or not isinstance(submap.conf, np.ndarray):
                     pts_h = submap._device("points").cpu().numpy()
-                    conf_h = conf_dev.cpu().numpy()
+                    conf_h = submap._device("conf").cpu().numpy()
                 else:
                     pts_h = np.ascontiguousarray(submap.pointclouds, dtype=np.float32)
                     conf_h = np.ascontiguousarray(submap.conf, dtype=np.float32)
@@ -188,7 +197,8 @@ class GraphMap:
                     emb_h = emb_h.astype(np.float32)
                 stats = dm.fuse_host(pts_h, conf_h, emb_h, params)
             else:
-                stats = dm.fuse(submap._device("points"), conf_dev, submap.embeddings_on_device(), params)
+                stats = dm.fuse(submap._device("points"), submap._device("conf"), submap.embeddings_on_device(),
+                                params)
             stats = dict(stats, submap_id=sid)
             self.last_build_stats.append(stats)
             if stats["n_fused"] == 0:
@@ -197,6 +207,18 @@ class GraphMap:
                           "end_idx": end_idx})
             if getattr(submap, "frame_id_to_name", None) is not None:
                 frame_name_maps[str(sid)] = dict(submap.frame_id_to_name)
+
+
+def wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contributors=True, exact_coords=False):
+    """SemanticVoxelMap over a finalised DeviceVoxelMap: centres now, features / contributors lazily."""
+    V = dm.num_voxels
+    _, centers, _, _ = dm.export_geometry(coords=False, centers=True, counts=False, recon=False)
+    if deduplicate_contributors:
+        contributors = _dedup_contributors(dm, fused, V)
+    else:
+        contributors = _per_point_contributors_global(dm, fused, V)
+    vox = SemanticVoxel.lazy(float(voxel_size), centers.cpu().numpy(), dm.features_to_host, contributors)
+    return SemanticVoxelMap(vox, frame_name_maps=frame_name_maps, _device_map=dm, exact_coords=exact_coords)
 
 
 def _empty_voxels(voxel_size) -> SemanticVoxel:

@@ -141,6 +141,14 @@ class DeviceVoxelMap:
                                              _stream_ptr(self.device)))
         return out
 
+    def profile_enable(self, on: bool = True) -> None:
+        N.check(N.lib.vsm_profile_enable(self._h, int(bool(on))))
+
+    def profile(self) -> dict:
+        p = N.Profile()
+        N.check(N.lib.vsm_profile_get(self._h, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in N.Profile._fields_}
+
     # -- finalisation / export ---------------------------------------------
     def finalize(self) -> None:
         N.check(N.lib.vsm_finalize(self._h, _stream_ptr(self.device)))
