@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "state.cuh"
 
@@ -17,37 +18,67 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// All device memory of the library comes from the device's stream-ordered pool (cudaMallocAsync) with the
+// release threshold lifted, so that re-creating maps and growing scratch buffers costs microseconds after
+// warm-up instead of a cudaMalloc/cudaFree pair (milliseconds, with a device-wide synchronisation).
+// Allocation happens on a private stream that is synchronised right away: the block is then valid on any stream.
+static cudaStream_t alloc_stream_for(int dev) {
+  static cudaStream_t streams[64] = {nullptr};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev]) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(dev);
+    cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaSetDevice(cur);
+  }
+  return streams[dev];
+}
+
 int DevBuf::ensure(size_t need, cudaStream_t s, size_t keep_bytes, double slack) {
   if (need <= bytes && p != nullptr) return VSM_OK;
   if (need == 0) need = 16;
   size_t want = (size_t)((double)need * slack);
   want = (want + 255) & ~(size_t)255;
+  int cur = 0;
+  VSM_CUDA(cudaGetDevice(&cur));
+  cudaStream_t as = alloc_stream_for(cur);
   void* np = nullptr;
-  cudaError_t e = cudaMalloc(&np, want);
+  cudaError_t e = cudaMallocAsync(&np, want, as);
   if (e != cudaSuccess && want > need) {
     cudaGetLastError();
     want = (need + 255) & ~(size_t)255;
-    e = cudaMalloc(&np, want);
+    e = cudaMallocAsync(&np, want, as);
   }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(as);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
     return VSM_E_NOMEM;
   }
   if (p != nullptr) {
-    if (keep_bytes) {
-      VSM_CUDA(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, s));
-      VSM_CUDA(cudaStreamSynchronize(s));
-    }
-    VSM_CUDA(cudaFree(p));  // cudaFree waits for work that may still use the old block
+    if (keep_bytes) VSM_CUDA(cudaMemcpyAsync(np, p, keep_bytes, cudaMemcpyDeviceToDevice, s));
+    VSM_CUDA(cudaStreamSynchronize(s));  // nothing on the caller's stream still uses the old block
+    VSM_CUDA(cudaFreeAsync(p, alloc_stream_for(dev)));
   }
   p = np;
   bytes = want;
+  dev = cur;
   return VSM_OK;
 }
 
 void DevBuf::release() {
-  if (p) cudaFree(p);
+  if (p) {
+    cudaFreeAsync(p, alloc_stream_for(dev));
+    cudaGetLastError();
+  }
   p = nullptr;
   bytes = 0;
 }

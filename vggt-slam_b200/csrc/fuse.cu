@@ -600,7 +600,7 @@ int map_grow(vsm_map* m, int64_t need, cudaStream_t s) {
 
 int log_grow(vsm_map* m, int64_t need, cudaStream_t s) {
   if (need <= m->log_cap) return VSM_OK;
-  const int64_t new_cap = std::max<int64_t>(need, m->log_cap * 2);
+  const int64_t new_cap = std::max<int64_t>(std::max<int64_t>(need, m->log_cap * 2), m->vcap);
   const size_t keep = (size_t)m->log_n;
   VSM_TRY(m->log_gid.ensure((size_t)new_cap * 4, s, keep * 4));
   VSM_TRY(m->log_fuse.ensure((size_t)new_cap * 4, s, keep * 4));

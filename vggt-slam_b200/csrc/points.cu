@@ -131,13 +131,15 @@ extern "C" int vsm_select_points(const float* pts_dev, const float* conf_dev, co
     set_error("vsm_select_points: too many pixels");
     return VSM_E_INVALID;
   }
-  uint32_t *flags = nullptr, *offs = nullptr;
-  void* tmp = nullptr;
-  VSM_CUDA(cudaMalloc(&flags, (size_t)n * 4));
-  VSM_CUDA(cudaMalloc(&offs, ((size_t)n + 1) * 4));
+  DevBuf b_flags, b_offs, b_tmp;
+  VSM_TRY(b_flags.ensure((size_t)n * 4, s));
+  VSM_TRY(b_offs.ensure(((size_t)n + 1) * 4, s));
+  uint32_t* flags = b_flags.as<uint32_t>();
+  uint32_t* offs = b_offs.as<uint32_t>();
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, flags, offs, (int)n, s);
-  VSM_CUDA(cudaMalloc(&tmp, tmp_bytes + 16));
+  VSM_TRY(b_tmp.ensure(tmp_bytes + 16, s));
+  void* tmp = b_tmp.p;
   int status = VSM_OK;
   do {
     select_flags_kernel<<<grid_for(n, 256), 256, 0, s>>>(conf_dev, S, H, W, stride, hs, ws, conf_threshold, flags);
@@ -165,8 +167,9 @@ extern "C" int vsm_select_points(const float* pts_dev, const float* conf_dev, co
     *n_selected_host = (int64_t)last_off + last_flag;
   } while (0);
   if (status != VSM_OK) set_error("vsm_select_points: %s", cudaGetErrorString(cudaGetLastError()));
-  cudaFree(flags);
-  cudaFree(offs);
-  cudaFree(tmp);
+  cudaStreamSynchronize(s);
+  b_flags.release();
+  b_offs.release();
+  b_tmp.release();
   return status;
 }

@@ -18,6 +18,7 @@ namespace vsm {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  int dev = 0;  // device the block lives on
   // grow to at least `need` bytes; old contents are dropped unless keep_bytes > 0
   int ensure(size_t need, cudaStream_t s, size_t keep_bytes = 0, double slack = 1.0);
   void release();
