@@ -332,26 +332,38 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
 // fp32 registers and flushed with vector REDs whenever the voxel id changes.  U rows are in flight.
 template <bool BF16>
 struct RowVec;
+// f32 accumulator += one bf16 half of a 32-bit word: Blackwell's mixed-precision add (PTX add.f32.bf16,
+// SASS FHADD.BF16) takes the half register directly, so widening costs no instruction of its own.
+__device__ __forceinline__ float add_bf16_lo(float acc, uint32_t w) {
+  float d;
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; add.f32.bf16 %0, lo, %1; }" : "=f"(d) : "f"(acc), "r"(w));
+  return d;
+}
+__device__ __forceinline__ float add_bf16_hi(float acc, uint32_t w) {
+  float d;
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %2; add.f32.bf16 %0, hi, %1; }" : "=f"(d) : "f"(acc), "r"(w));
+  return d;
+}
 template <>
 struct RowVec<true> {
   static constexpr int EPV = 8;  // elements per 16-byte vector
   __device__ static __forceinline__ void add(float* acc, const uint4& v) {
-    acc[0] += __uint_as_float(v.x << 16);
-    acc[1] += __uint_as_float(v.x & 0xFFFF0000u);
-    acc[2] += __uint_as_float(v.y << 16);
-    acc[3] += __uint_as_float(v.y & 0xFFFF0000u);
-    acc[4] += __uint_as_float(v.z << 16);
-    acc[5] += __uint_as_float(v.z & 0xFFFF0000u);
-    acc[6] += __uint_as_float(v.w << 16);
-    acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
+    acc[0] = add_bf16_lo(acc[0], v.x);
+    acc[1] = add_bf16_hi(acc[1], v.x);
+    acc[2] = add_bf16_lo(acc[2], v.y);
+    acc[3] = add_bf16_hi(acc[3], v.y);
+    acc[4] = add_bf16_lo(acc[4], v.z);
+    acc[5] = add_bf16_hi(acc[5], v.z);
+    acc[6] = add_bf16_lo(acc[6], v.w);
+    acc[7] = add_bf16_hi(acc[7], v.w);
   }
+  // exponent all ones in either half
   __device__ static __forceinline__ bool nonfinite(const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    bool bad = false;
+    uint32_t bad = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      bad |= ((w[i] & 0x7F800000u) == 0x7F800000u) || ((w[i] & 0x00007F80u) == 0x00007F80u);
-    return bad;
+    for (int i = 0; i < 4; ++i) bad |= ((w[i] & 0x7F807F80u) + 0x00800080u) & 0x80008000u;
+    return bad != 0u;
   }
 };
 template <>
@@ -386,8 +398,12 @@ struct AccArgs {
   FuseCounters* ctr;
 };
 
+// CHECK (optimistic non-finite detection, filters on): a non-finite embedding value makes the fp32 sum of its
+// voxel segment non-finite, so the accumulators are tested once per flush instead of testing every row; rows that
+// are only to be checked (pixel mode, id -2) are tested directly.  Any hit is counted in ctr->n_bad_emb and makes
+// the fuse call fail with VSM_E_NONFINITE_EMB (the caller redoes the build with the exact pre-check).
 template <bool BF16, int VPL, bool SORTED, bool CHECK>
-__global__ void __launch_bounds__(256) accumulate_kernel(AccArgs a) {
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(AccArgs a) {
   constexpr int EPV = RowVec<BF16>::EPV;
   constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
   const int lane = lane_id();
@@ -395,18 +411,22 @@ __global__ void __launch_bounds__(256) accumulate_kernel(AccArgs a) {
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_chunks = (a.n + 31) >> 5;
   unsigned n_bad = 0;
+  bool lane_cols[VPL];
+#pragma unroll
+  for (int v = 0; v < VPL; ++v) lane_cols[v] = (lane + 32 * v) < a.nvec;
+  const uint8_t* emb0 = a.emb - a.pix_base * a.row_bytes + (size_t)lane * 16;
 
   for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
     const int64_t base = chunk << 5;
     const int cnt = (int)min((int64_t)32, a.n - base);
-    int64_t my_pix = 0;
+    uint32_t my_pix = 0;
     int my_gid = -1;
     if (lane < cnt) {
       if (SORTED) {
-        my_pix = (int64_t)a.sorted_pix[base + lane];
+        my_pix = a.sorted_pix[base + lane];
         my_gid = a.sorted_gid[base + lane];
       } else {
-        my_pix = a.pix_base + base + lane;
+        my_pix = (uint32_t)(a.pix_base + base + lane);
         my_gid = a.point_gid[my_pix];
       }
     }
@@ -420,15 +440,25 @@ __global__ void __launch_bounds__(256) accumulate_kernel(AccArgs a) {
 
     auto flush = [&]() {
       if (cur >= 0) {
-        float* dst = a.vsum + (size_t)cur * a.d;
+        bool ok = true;
+        if (CHECK) {
+          float t = 0.f;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = lane + 32 * v;
-          if (c < a.nvec) {
+          for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);  // NaN iff some accumulator is Inf/NaN
+          ok = !__any_sync(0xffffffffu, t != t);
+          if (!ok && lane == 0) ++n_bad;
+        }
+        if (ok) {
+          float* dst = a.vsum + (size_t)cur * a.d;
 #pragma unroll
-            for (int q = 0; q < EPV / 4; ++q)
-              red_add_v4(dst + c * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
-                         acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
+          for (int v = 0; v < VPL; ++v) {
+            if (lane_cols[v]) {
+              const int c = lane + 32 * v;
+#pragma unroll
+              for (int q = 0; q < EPV / 4; ++q)
+                red_add_v4(dst + c * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
+                           acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
+            }
           }
         }
       }
@@ -442,32 +472,28 @@ __global__ void __launch_bounds__(256) accumulate_kernel(AccArgs a) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int src = (j + u) & 31;
-        const int64_t pj = __shfl_sync(0xffffffffu, my_pix, src);
+        const uint32_t pj = __shfl_sync(0xffffffffu, my_pix, src);
         int gj = __shfl_sync(0xffffffffu, my_gid, src);
         if (j + u >= cnt) gj = -1;
         gids[u] = gj;
-        const bool want_row = CHECK ? (gj != -1) : (gj >= 0);
-        const uint8_t* row = a.emb + (pj - a.pix_base) * a.row_bytes;
+        const bool want_row = (!SORTED && CHECK) ? (gj != -1) : (gj >= 0);
+        const uint8_t* row = emb0 + (size_t)pj * a.row_bytes;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          const int c = lane + 32 * v;
-          rows[u][v] = (want_row && c < a.nvec) ? ld_stream_v4(row + (size_t)c * 16) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        for (int v = 0; v < VPL; ++v)
+          rows[u][v] = (want_row && lane_cols[v]) ? ld_stream_v4(row + (size_t)v * 512) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int gj = gids[u];
         if (gj == -1) continue;  // warp-uniform
-        if (CHECK) {
+        if (!SORTED && CHECK && gj == -2) {
           bool bad = false;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(rows[u][v]);
-          if (__any_sync(0xffffffffu, bad)) {
-            if (lane == 0) ++n_bad;
-            continue;
-          }
+          if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+          continue;
         }
-        if (gj < 0) continue;  // -2: checked only
+        if (gj < 0) continue;
         if (gj != cur) {
           flush();
           cur = gj;
