@@ -7,17 +7,21 @@
 //   GraphMap.build_semantic_voxel_map          vggt_slam/map.py:196-291 (per-submap loop, three filters)
 //                                              vggt_slam/map.py:351-362 (global voxelisation, numpy branch)
 //
-// Pipeline of one fuse call (all on one stream):
-//   world_points      px -> (x,y,z,flags) float4; conf mask, stride grid, f64 transform, finite test
-//   [filters]         radix-select percentiles -> bbox; coarse-cell hash count -> isolation filter
+// One fuse call queues all of its kernels back to back on the caller's stream and synchronises once, at the
+// end, to hand the counters back.  Sizes that are only known on the device (survivors, distinct voxels) are
+// read by the kernels from the counter block; buffers are sized by upper bounds; a capacity check on the
+// device aborts the call before anything global is modified if the map has to grow (the host then grows it
+// and repeats the call).
+//   world_points      px -> (x,y,z,flags) float4: conf mask, stride grid, f64 transform, finite test,
+//                     + top-11-bit histograms of the three axes for the percentile select
+//   [filters]         radix-select passes 1,2 -> bbox; coarse-cell hash count -> isolation filter
 //   fine_insert       packed voxel key -> submap-local hash (count + frame mask), point -> slot
-//   local_compact     dense local voxel ids, counts; exclusive scan -> segment offsets
+//   post_insert       capacity check (abort flag), coarse table cleanup
+//   local_compact     dense local voxel ids, counts, segment offsets (warp-aggregated allocation)
 //   global_merge      one thread per DISTINCT voxel inserts into the global hash (V_sub, not N, probes)
-//   scatter           counting sort of the points by local voxel -> (pixel, voxel id) lists
-//   accumulate        warps walk 32-point chunks of the sorted list, sum embedding rows in registers and
-//                     flush with one vector RED burst per voxel boundary (fp32 accumulate)
-#include <cub/device/device_scan.cuh>
-
+//   scatter           counting sort of the points by local voxel -> packed (voxel id, pixel) entries
+//   accumulate        warps walk 32-entry chunks of the sorted list, sum embedding rows in fp32 registers
+//                     (FHADD.BF16) and flush with vector REDs at voxel boundaries
 #include "hash.cuh"
 
 namespace vsm {
@@ -26,26 +30,27 @@ constexpr uint32_t PF_SEL = 1u;     // conf >= thr, on the stride grid, frame < 
 constexpr uint32_t PF_FINITE = 2u;  // world point (and embedding row, if a mask was given) finite
 
 // ---------------------------------------------------------------------------
-// world points
+// world points (+ pass 0 of the percentile select)
 // ---------------------------------------------------------------------------
 struct WorldArgs {
   const float* pts;
   const float* conf;
   const uint8_t* emb_ok;
   float4* pw;
-  int64_t n_px;
-  int H, W, stride;
+  uint32_t n_px;
+  uint32_t H, W, stride;
   float thr;
+  uint32_t* hist0;  // [3][2048] top-11-bit histograms of the finite selected points, or nullptr
 };
 
-__device__ __forceinline__ float4 world_one(const WorldArgs& a, const HMat& Hm, int64_t pix, float px, float py,
+__device__ __forceinline__ float4 world_one(const WorldArgs& a, const HMat& Hm, uint32_t pix, float px, float py,
                                             float pz, float c, uint32_t& flags) {
   flags = 0u;
   float x = 0.f, y = 0.f, z = 0.f;
   bool on_grid = true;
   if (a.stride > 1) {
-    const int w = (int)(pix % a.W);
-    const int h = (int)((pix / a.W) % a.H);
+    const uint32_t w = pix % a.W;
+    const uint32_t h = (pix / a.W) % a.H;
     on_grid = (w % a.stride == 0) && (h % a.stride == 0);
   }
   if (on_grid && c >= a.thr) {
@@ -56,54 +61,71 @@ __device__ __forceinline__ float4 world_one(const WorldArgs& a, const HMat& Hm, 
   return make_float4(x, y, z, __uint_as_float(flags));
 }
 
-// 4 pixels per thread: three 128-bit loads of xyz, one of conf, four 128-bit stores
-__global__ void __launch_bounds__(256) world_points_vec4_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
-  const int64_t n4 = a.n_px >> 2;
-  unsigned n_sel = 0, n_fin = 0;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
-    const float4* p4 = reinterpret_cast<const float4*>(a.pts) + 3 * t;
-    const uint4 r0 = ld_stream_v4(p4), r1 = ld_stream_v4(p4 + 1), r2 = ld_stream_v4(p4 + 2);
-    const uint4 rc = ld_stream_v4(reinterpret_cast<const float4*>(a.conf) + t);
-    const float v[12] = {__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z), __uint_as_float(r0.w),
-                         __uint_as_float(r1.x), __uint_as_float(r1.y), __uint_as_float(r1.z), __uint_as_float(r1.w),
-                         __uint_as_float(r2.x), __uint_as_float(r2.y), __uint_as_float(r2.z), __uint_as_float(r2.w)};
-    const float c[4] = {__uint_as_float(rc.x), __uint_as_float(rc.y), __uint_as_float(rc.z), __uint_as_float(rc.w)};
+// warp-aggregated shared-memory histogram update: neighbouring pixels share their high bits
+__device__ __forceinline__ void hist0_add(uint32_t* sh, const float4& p, bool valid) {
+  const float v[3] = {p.x, p.y, p.z};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t f;
-      const float4 o = world_one(a, Hm, 4 * t + j, v[3 * j], v[3 * j + 1], v[3 * j + 2], c[j], f);
-      a.pw[4 * t + j] = o;
-      n_sel += (f & PF_SEL) ? 1u : 0u;
-      n_fin += (f & PF_FINITE) ? 1u : 0u;
-    }
-  }
-  // tail (n_px % 4) by the first threads of block 0
-  if (blockIdx.x == 0 && threadIdx.x < (a.n_px & 3)) {
-    const int64_t pix = (n4 << 2) + threadIdx.x;
-    uint32_t f;
-    a.pw[pix] = world_one(a, Hm, pix, a.pts[3 * pix], a.pts[3 * pix + 1], a.pts[3 * pix + 2], a.conf[pix], f);
-    n_sel += (f & PF_SEL) ? 1u : 0u;
-    n_fin += (f & PF_FINITE) ? 1u : 0u;
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
-    n_fin += __shfl_xor_sync(0xffffffffu, n_fin, o);
-  }
-  if (lane_id() == 0) {
-    if (n_sel) atomicAdd(&ctr->n_conf, (unsigned long long)n_sel);
-    if (n_fin) atomicAdd(&ctr->n_finite, (unsigned long long)n_fin);
+  for (int c = 0; c < 3; ++c) {
+    const uint32_t bin = valid ? (float_to_ordered(v[c]) >> 21) : 0xFFFFFFFFu;
+    const unsigned grp = __match_any_sync(0xffffffffu, bin);
+    if (valid && lane_id() == __ffs(grp) - 1) atomicAdd(&sh[c * 2048 + bin], (uint32_t)__popc(grp));
   }
 }
 
-// one pixel per thread (unaligned inputs)
-__global__ void __launch_bounds__(256) world_points_scalar_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
+// VEC4: 4 pixels per thread -- three 128-bit loads of xyz, one of conf, four 128-bit stores
+template <bool VEC4, bool HIST>
+__global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
+  __shared__ uint32_t sh[HIST ? 3 * 2048 : 1];
+  if (HIST) {
+    for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x) sh[i] = 0u;
+    __syncthreads();
+  }
   unsigned n_sel = 0, n_fin = 0;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < a.n_px;
-       pix += (int64_t)gridDim.x * blockDim.x) {
-    uint32_t f;
-    a.pw[pix] = world_one(a, Hm, pix, a.pts[3 * pix], a.pts[3 * pix + 1], a.pts[3 * pix + 2], a.conf[pix], f);
-    n_sel += (f & PF_SEL) ? 1u : 0u;
-    n_fin += (f & PF_FINITE) ? 1u : 0u;
+  constexpr uint32_t PPT = VEC4 ? 4u : 1u;
+  const uint32_t n_items = (a.n_px + PPT - 1) / PPT;
+  const uint32_t n_round = (n_items + 31u) & ~31u;  // warp-uniform trip count (match.any inside)
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n_round; t += gridDim.x * blockDim.x) {
+    float4 o[PPT];
+    uint32_t f[PPT];
+#pragma unroll
+    for (uint32_t j = 0; j < PPT; ++j) {
+      o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      f[j] = 0u;
+    }
+    if (t < n_items) {
+      if (VEC4 && 4u * t + 3u < a.n_px) {
+        const float4* p4 = reinterpret_cast<const float4*>(a.pts) + 3 * (size_t)t;
+        const uint4 r0 = ld_stream_v4(p4), r1 = ld_stream_v4(p4 + 1), r2 = ld_stream_v4(p4 + 2);
+        const uint4 rc = ld_stream_v4(reinterpret_cast<const float4*>(a.conf) + t);
+        const float v[12] = {__uint_as_float(r0.x), __uint_as_float(r0.y), __uint_as_float(r0.z),
+                             __uint_as_float(r0.w), __uint_as_float(r1.x), __uint_as_float(r1.y),
+                             __uint_as_float(r1.z), __uint_as_float(r1.w), __uint_as_float(r2.x),
+                             __uint_as_float(r2.y), __uint_as_float(r2.z), __uint_as_float(r2.w)};
+        const float c[4] = {__uint_as_float(rc.x), __uint_as_float(rc.y), __uint_as_float(rc.z),
+                            __uint_as_float(rc.w)};
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+          o[j] = world_one(a, Hm, 4 * t + j, v[3 * j], v[3 * j + 1], v[3 * j + 2], c[j], f[j]);
+          a.pw[4 * (size_t)t + j] = o[j];
+        }
+      } else {
+#pragma unroll
+        for (uint32_t j = 0; j < PPT; ++j) {
+          const uint32_t pix = PPT * t + j;
+          if (pix < a.n_px) {
+            o[j] = world_one(a, Hm, pix, a.pts[3 * (size_t)pix], a.pts[3 * (size_t)pix + 1],
+                             a.pts[3 * (size_t)pix + 2], a.conf[pix], f[j]);
+            a.pw[pix] = o[j];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < PPT; ++j) {
+      n_sel += (f[j] & PF_SEL) ? 1u : 0u;
+      n_fin += (f[j] & PF_FINITE) ? 1u : 0u;
+      if (HIST) hist0_add(sh, o[j], (f[j] & PF_FINITE) != 0u);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
@@ -112,6 +134,11 @@ __global__ void __launch_bounds__(256) world_points_scalar_kernel(WorldArgs a, H
   if (lane_id() == 0) {
     if (n_sel) atomicAdd(&ctr->n_conf, (unsigned long long)n_sel);
     if (n_fin) atomicAdd(&ctr->n_finite, (unsigned long long)n_fin);
+  }
+  if (HIST) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x)
+      if (sh[i]) atomicAdd(&a.hist0[i], sh[i]);
   }
 }
 
@@ -164,9 +191,9 @@ __device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, uns
 struct FilterArgs {
   const float4* pw;
   int32_t* pt_slot;
-  int64_t n_px;
-  int64_t px_per_frame;
-  float cell;      // coarse cell (bbox_coarse) or voxel size (fine)
+  uint32_t n_px;
+  uint32_t px_per_frame;
+  float cell;  // coarse cell (bbox_coarse) or voxel size (fine)
   uint32_t min_pts;
 };
 
@@ -175,9 +202,8 @@ __global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, LocalTab
   const float lx = ctr->bounds[0], hx = ctr->bounds[1], ly = ctr->bounds[2], hy = ctr->bounds[3], lz = ctr->bounds[4],
               hz = ctr->bounds[5];
   unsigned n_in = 0;
-  const int64_t n_round = (a.n_px + 31) & ~(int64_t)31;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
-       pix += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t n_round = (a.n_px + 31u) & ~31u;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
     bool act = false;
     unsigned long long key = kEmptyKey;
     if (pix < a.n_px) {
@@ -204,9 +230,8 @@ __global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, LocalTab
 template <bool FILTERS>
 __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTable ta, LocalTable tb, FuseCounters* ctr) {
   unsigned n_in = 0;
-  const int64_t n_round = (a.n_px + 31) & ~(int64_t)31;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
-       pix += (int64_t)gridDim.x * blockDim.x) {
+  const uint32_t n_round = (a.n_px + 31u) & ~31u;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
     bool act = false;
     unsigned long long key = kEmptyKey;
     int frame = 0;
@@ -233,16 +258,62 @@ __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTab
   if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_fused, (unsigned long long)n_in);
 }
 
-// dense local ids: lid = position in the claim list
-__global__ void local_compact_kernel(LocalTable tb, uint32_t n_occ, uint32_t* __restrict__ lv_cnt) {
-  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
-    const uint32_t slot = tb.slot_list[lid];
-    lv_cnt[lid] = tb.count[slot];
-    tb.lid[slot] = lid;
+// After the inserts: reset the coarse table and decide, on the device, whether the call may go on.  It may not
+// if an error was flagged or if the map / contributor log cannot take this call's voxels: nothing global has
+// been touched yet, so the host can grow the map and simply repeat the call.
+__global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has_ta, FuseCounters* ctr,
+                                                          const uint32_t* __restrict__ n_vox, uint32_t vcap,
+                                                          uint32_t log_free, uint32_t entry_cap) {
+  if (has_ta) {
+    const uint32_t n_occ = *ta.n_occ;
+    for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
+      const uint32_t slot = ta.slot_list[lid];
+      ta.keys[slot] = kEmptyKey;
+      ta.count[slot] = 0u;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const uint32_t n_occ = ctr->n_occ_b;
+    const bool fits = ((unsigned long long)*n_vox + n_occ <= vcap) && (n_occ <= log_free) &&
+                      (ctr->n_finite <= (unsigned long long)entry_cap);
+    if (!fits || ctr->range_err || ctr->internal_err) ctr->abort = 1u;
   }
 }
 
-__global__ void table_cleanup_kernel(LocalTable t, uint32_t n_occ) {
+// dense local ids (= position in the claim list), counts, and a segment of the sorted list per local voxel
+__global__ void __launch_bounds__(256) local_compact_kernel(LocalTable tb, FuseCounters* ctr, uint32_t* __restrict__ lv_cnt,
+                                                            uint32_t* __restrict__ lv_off,
+                                                            uint32_t* __restrict__ lv_cursor) {
+  if (ctr->abort) return;
+  const uint32_t n_occ = ctr->n_occ_b;
+  const uint32_t n_round = (n_occ + 31u) & ~31u;
+  const int lane = lane_id();
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
+    uint32_t cnt = 0, slot = 0;
+    if (lid < n_occ) {
+      slot = tb.slot_list[lid];
+      cnt = tb.count[slot];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(&ctr->seg_total, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (lid < n_occ) {
+      lv_cnt[lid] = cnt;
+      lv_off[lid] = base + incl - cnt;
+      lv_cursor[lid] = 0u;
+      tb.lid[slot] = lid;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) table_cleanup_kernel(LocalTable t) {
+  const uint32_t n_occ = *t.n_occ;
   for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
     const uint32_t slot = t.slot_list[lid];
     t.keys[slot] = kEmptyKey;
@@ -252,7 +323,6 @@ __global__ void table_cleanup_kernel(LocalTable t, uint32_t n_occ) {
       t.mask[(size_t)slot * 2 + 1] = 0ull;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *t.n_occ = 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -274,12 +344,14 @@ __global__ void rehash_kernel(GlobalStore g, uint32_t n) {
 }
 
 // one thread per distinct voxel of this call: global insert, counts, contributor log
-__global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, uint32_t n_occ, GlobalStore g,
+__global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, GlobalStore g,
                                                            const uint32_t* __restrict__ lv_cnt,
                                                            int32_t* __restrict__ lv_gid, int32_t* __restrict__ log_gid,
                                                            int32_t* __restrict__ log_sub,
                                                            unsigned long long* __restrict__ log_mask, int64_t log_base,
                                                            int32_t submap_id, FuseCounters* ctr) {
+  if (ctr->abort) return;
+  const uint32_t n_occ = ctr->n_occ_b;
   for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
     const uint32_t slot = tb.slot_list[lid];
     const unsigned long long key = tb.keys[slot];
@@ -293,33 +365,75 @@ __global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, uint32
   }
 }
 
-// counting sort of the fused points by local voxel.  Lanes with the same voxel claim a block of
-// consecutive positions with one atomic and keep their pixel order inside it.
-__global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict__ pt_slot, int64_t n_px, LocalTable tb,
-                                                      const uint32_t* __restrict__ lv_off,
+// A sorted-list entry packs (voxel id << 32 | pixel).  Ids: >= 0 fused point; -2 = point that passed the
+// confidence and finite tests but was dropped by the bbox / coarse filters: its embedding row is only checked
+// for non-finite values (the reference removes such rows BEFORE the percentiles, map.py:247-258, so the
+// optimistic pass must notice every one of them).
+__device__ __forceinline__ unsigned long long make_entry(int gid, uint32_t pix) {
+  return ((unsigned long long)(uint32_t)gid << 32) | (unsigned long long)pix;
+}
+
+// counting sort of the fused points by local voxel.  Lanes with the same voxel claim a block of consecutive
+// positions with one atomic and keep their pixel order inside it; check-only pixels are appended behind.
+__global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
+                                                      uint32_t n_px, LocalTable tb, const uint32_t* __restrict__ lv_off,
                                                       uint32_t* __restrict__ lv_cursor,
-                                                      const int32_t* __restrict__ lv_gid,
-                                                      uint32_t* __restrict__ sorted_pix,
-                                                      int32_t* __restrict__ sorted_gid, int32_t* __restrict__ point_gid) {
-  const int64_t n_round = (n_px + 31) & ~(int64_t)31;
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_round;
-       pix += (int64_t)gridDim.x * blockDim.x) {
+                                                      const int32_t* __restrict__ lv_gid, int mark_checks,
+                                                      unsigned long long* __restrict__ entries,
+                                                      int32_t* __restrict__ point_gid, FuseCounters* ctr) {
+  if (ctr->abort) return;
+  const uint32_t n_fused = (uint32_t)ctr->n_fused;
+  const uint32_t n_round = (n_px + 31u) & ~31u;
+  const int lane = lane_id();
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
     const int slot = pix < n_px ? pt_slot[pix] : -1;
     const bool act = slot >= 0;
     const uint32_t lid = act ? tb.lid[slot] : 0xFFFFFFFFu;
     const unsigned grp = __match_any_sync(0xffffffffu, lid);
     const int leader = __ffs(grp) - 1;
     uint32_t base = 0;
-    if (act && lane_id() == leader) base = atomicAdd(&lv_cursor[lid], (uint32_t)__popc(grp));
+    if (act && lane == leader) base = atomicAdd(&lv_cursor[lid], (uint32_t)__popc(grp));
     base = __shfl_sync(0xffffffffu, base, leader);
     int gid = -1;
     if (act) {
-      const uint32_t pos = lv_off[lid] + base + (uint32_t)__popc(grp & ((1u << lane_id()) - 1u));
+      const uint32_t pos = lv_off[lid] + base + (uint32_t)__popc(grp & ((1u << lane) - 1u));
       gid = lv_gid[lid];
-      sorted_pix[pos] = (uint32_t)pix;
-      sorted_gid[pos] = gid;
+      entries[pos] = make_entry(gid, pix);
+    }
+    if (mark_checks) {
+      bool chk = false;
+      if (!act && pix < n_px) {
+        const uint32_t f = __float_as_uint(pw[pix].w);
+        chk = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
+      }
+      const unsigned cm = __ballot_sync(0xffffffffu, chk);
+      if (cm) {
+        uint32_t cbase = 0;
+        if (lane == __ffs(cm) - 1) cbase = atomicAdd(&ctr->n_check, (uint32_t)__popc(cm));
+        cbase = __shfl_sync(0xffffffffu, cbase, __ffs(cm) - 1);
+        if (chk) entries[n_fused + cbase + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = make_entry(-2, pix);
+      }
     }
     if (point_gid != nullptr && pix < n_px) point_gid[pix] = gid;
+  }
+}
+
+// pixel -> voxel id without the sorted lists (pixel-order / host-streaming path); -2 marks check-only pixels
+__global__ void __launch_bounds__(256) point_gid_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
+                                                        uint32_t n_px, LocalTable tb, const int32_t* __restrict__ lv_gid,
+                                                        int mark_checks, int32_t* __restrict__ point_gid,
+                                                        const FuseCounters* ctr) {
+  if (ctr->abort) return;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_px; pix += gridDim.x * blockDim.x) {
+    const int slot = pt_slot[pix];
+    int g = -1;
+    if (slot >= 0) {
+      g = lv_gid[tb.lid[slot]];
+    } else if (mark_checks) {
+      const uint32_t f = __float_as_uint(pw[pix].w);
+      if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) g = -2;
+    }
+    point_gid[pix] = g;
   }
 }
 
@@ -328,8 +442,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
 // ---------------------------------------------------------------------------
 // A row is d embedding channels of one pixel (bf16: 2d bytes, f32: 4d bytes), read as 16-byte vectors:
 // lane l of a warp owns vectors l, l+32, ... (VPL of them), i.e. a warp reads 512 contiguous bytes per
-// vector index.  Each warp walks a chunk of 32 entries of a (pixel, voxel id) list; rows are summed in
-// fp32 registers and flushed with vector REDs whenever the voxel id changes.  U rows are in flight.
+// vector index.  Each warp walks a chunk of 32 entries; rows are summed in fp32 registers and flushed with
+// vector REDs whenever the voxel id changes.  U rows are in flight per warp.
 template <bool BF16>
 struct RowVec;
 // f32 accumulator += one bf16 half of a 32-bit word: Blackwell's mixed-precision add (PTX add.f32.bf16,
@@ -388,10 +502,9 @@ struct AccArgs {
   const uint8_t* emb;          // row of pixel p starts at emb + (p - pix_base) * row_bytes
   int64_t pix_base;
   int64_t row_bytes;
-  const uint32_t* sorted_pix;  // SORTED mode: entry lists
-  const int32_t* sorted_gid;
+  const unsigned long long* entries;  // SORTED mode: packed (voxel id << 32 | pixel), n_fused + n_check of them
   const int32_t* point_gid;    // PIXEL mode: voxel id per pixel (-1: skip); entries are pixels [pix_base, pix_base+n)
-  int64_t n;                   // entries
+  int64_t n;                   // PIXEL mode: number of pixels
   float* vsum;
   int d;
   int nvec;                    // 16-byte vectors per row
@@ -409,7 +522,9 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
   const int lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_chunks = (a.n + 31) >> 5;
+  if (a.ctr->abort) return;
+  const int64_t n_entries = SORTED ? (int64_t)a.ctr->n_fused + (int64_t)a.ctr->n_check : a.n;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
   unsigned n_bad = 0;
   bool lane_cols[VPL];
 #pragma unroll
@@ -418,13 +533,14 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
 
   for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
     const int64_t base = chunk << 5;
-    const int cnt = (int)min((int64_t)32, a.n - base);
+    const int cnt = (int)min((int64_t)32, n_entries - base);
     uint32_t my_pix = 0;
     int my_gid = -1;
     if (lane < cnt) {
       if (SORTED) {
-        my_pix = a.sorted_pix[base + lane];
-        my_gid = a.sorted_gid[base + lane];
+        const unsigned long long e = a.entries[base + lane];
+        my_pix = (uint32_t)e;
+        my_gid = (int)(uint32_t)(e >> 32);
       } else {
         my_pix = (uint32_t)(a.pix_base + base + lane);
         my_gid = a.point_gid[my_pix];
@@ -476,7 +592,7 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
         int gj = __shfl_sync(0xffffffffu, my_gid, src);
         if (j + u >= cnt) gj = -1;
         gids[u] = gj;
-        const bool want_row = (!SORTED && CHECK) ? (gj != -1) : (gj >= 0);
+        const bool want_row = CHECK ? (gj != -1) : (gj >= 0);
         const uint8_t* row = emb0 + (size_t)pj * a.row_bytes;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
@@ -486,7 +602,7 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
       for (int u = 0; u < U; ++u) {
         const int gj = gids[u];
         if (gj == -1) continue;  // warp-uniform
-        if (!SORTED && CHECK && gj == -2) {
+        if (CHECK && gj == -2) {
           bool bad = false;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(rows[u][v]);
@@ -510,9 +626,12 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
 template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
   const int block = 256;
-  const int64_t n_chunks = (a.n + 31) >> 5;
-  int grid = (int)std::min<int64_t>(cdiv(n_chunks, block / 32), (int64_t)148 * 8);
-  if (grid < 1) grid = 1;
+  // the sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks
+  int grid = 148 * 6;
+  if (!sorted) {
+    const int64_t n_chunks = (a.n + 31) >> 5;
+    grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)148 * 6);
+  }
   if (sorted) {
     if (check)
       accumulate_kernel<BF16, VPL, true, true><<<grid, block, 0, s>>>(a);
@@ -529,7 +648,7 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
 }
 
 int launch_accumulate(const AccArgs& a, bool bf16, bool sorted, bool check, cudaStream_t s) {
-  if (a.n <= 0) return VSM_OK;
+  if (!sorted && a.n <= 0) return VSM_OK;
   const int vpl = (a.nvec + 31) / 32;
   if (bf16) {
     if (vpl <= 1) return launch_accumulate_t<true, 1>(a, sorted, check, s);
@@ -570,9 +689,7 @@ __global__ void __launch_bounds__(256) emb_row_mask_kernel(const float* __restri
   }
 }
 
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
+
 int map_grow(vsm_map* m, int64_t need, cudaStream_t s) {
   if (need <= m->vcap && m->gcap >= (uint64_t)2 * (uint64_t)std::max<int64_t>(m->vcap, 1)) return VSM_OK;
   if (need >= (int64_t)1 << 31) {
@@ -654,56 +771,6 @@ static int ensure_local_table(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& 
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// pixel -> voxel id without the sorted lists (pixel-order / host-streaming path).  With the filters on, pixels
-// that passed the confidence and finite tests but were dropped by the bbox / coarse filters get -2: their
-// embedding rows are still checked for non-finite values, because the reference removes such rows BEFORE it
-// computes the percentiles (map.py:247-258) and the optimistic pass must notice every one of them.
-__global__ void __launch_bounds__(256) point_gid_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
-                                                        int64_t n_px, LocalTable tb, const int32_t* __restrict__ lv_gid,
-                                                        int mark_checks, int32_t* __restrict__ point_gid) {
-  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_px;
-       pix += (int64_t)gridDim.x * blockDim.x) {
-    const int slot = pt_slot[pix];
-    int g = -1;
-    if (slot >= 0) {
-      g = lv_gid[tb.lid[slot]];
-    } else if (mark_checks) {
-      const uint32_t f = __float_as_uint(pw[pix].w);
-      if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) g = -2;
-    }
-    point_gid[pix] = g;
-  }
-}
-
-// voxel-sorted path: check the rows of the selected-but-filtered pixels (see point_gid_kernel)
-template <bool BF16>
-__global__ void __launch_bounds__(256) emb_check_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
-                                                        int64_t n_px, const uint8_t* __restrict__ emb, int64_t row_bytes,
-                                                        int nvec, FuseCounters* ctr) {
-  const int lane = lane_id();
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  unsigned n_bad = 0;
-  for (int64_t base = warp << 5; base < n_px; base += n_warps << 5) {
-    const int64_t pix = base + lane;
-    bool need = false;
-    if (pix < n_px && pt_slot[pix] < 0) {
-      const uint32_t f = __float_as_uint(pw[pix].w);
-      need = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, need);
-    while (todo) {
-      const int j = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint8_t* row = emb + (base + j) * row_bytes;
-      bool bad = false;
-      for (int c = lane; c < nvec; c += 32) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + (size_t)c * 16));
-      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
-    }
-  }
-  if (n_bad) atomicAdd(&ctr->n_bad_emb, (unsigned long long)n_bad);
-}
-
 static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
   if (!m || !p) {
     set_error("null map or params");
@@ -733,6 +800,9 @@ static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
 }
 
 
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
 struct HostEmb {
   const uint8_t* emb_host = nullptr;  // (S,H,W,d) rows on the host, map dtype
 };
@@ -747,10 +817,25 @@ static int ensure_stream_objects(vsm_map* m, size_t chunk_bytes) {
   return VSM_OK;
 }
 
-// One fuse call.  emb_dev: device embeddings (may be null when host != null: embeddings are then streamed
-// from the host frame by frame and accumulated in pixel order).
-static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
-                     const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s) {
+static LocalTable table_view(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& list, DevBuf* mask, uint64_t cap,
+                             uint32_t* n_occ) {
+  LocalTable t{};
+  t.keys = keys.as<unsigned long long>();
+  t.count = count.as<uint32_t>();
+  t.lid = lid.as<uint32_t>();
+  t.mask = mask ? mask->as<unsigned long long>() : nullptr;
+  t.slot_list = list.as<uint32_t>();
+  t.n_occ = n_occ;
+  t.cap_mask = (uint32_t)(cap - 1);
+  return t;
+}
+
+// One attempt at a fuse call.  *retry is set when the device-side capacity check stopped the call before it
+// modified the map; the caller grows the map by what `hc` reports and calls again.
+static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
+                        const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s,
+                        bool* retry, FuseCounters* hc_out) {
+  Workspace* ws = m->ws;
   const bool filters = (p->flags & VSM_FUSE_FILTERS) != 0;
   const bool keep_index = (p->flags & VSM_FUSE_KEEP_POINT_INDEX) != 0;
   const bool pixel_order = (p->flags & VSM_FUSE_PIXEL_ORDER) != 0 || host != nullptr;
@@ -758,6 +843,7 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   const int64_t n_px = (int64_t)p->end_idx * p->H * p->W;
   const int64_t px_per_frame = (int64_t)p->H * p->W;
   const int64_t row_bytes = (int64_t)m->d * m->esize;
+  *retry = false;
   vsm_fuse_stats st{};
   st.n_map_voxels = m->n_vox;
   for (int i = 0; i < 3; ++i) st.bbox_lo[i] = st.bbox_hi[i] = __builtin_nanf("");
@@ -767,7 +853,6 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters), s));
   m->finalized = false;
   m->ck_built = false;
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
   const bool prof = m->profiling && host == nullptr;
   if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[0], s));
 
@@ -785,35 +870,45 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     return VSM_OK;
   }
 
-  const int64_t hs = cdiv(p->H, p->stride), ws = cdiv(p->W, p->stride);
-  const uint64_t n_sel_max = (uint64_t)p->end_idx * hs * ws;
+  // ---- scratch, sized by upper bounds (the exact sizes only exist on the device) -----------------------
+  const int64_t hs = cdiv(p->H, p->stride), ws_ = cdiv(p->W, p->stride);
+  const uint64_t n_sel_max = (uint64_t)p->end_idx * hs * ws_;
   const uint64_t lcap = std::max<uint64_t>(next_pow2(2 * n_sel_max), 1024);
-  VSM_TRY(m->ws->pw.ensure((size_t)n_px * 16, s));
-  VSM_TRY(m->ws->pt_slot.ensure((size_t)n_px * 4, s));
-  VSM_TRY(ensure_local_table(m->ws->tb_keys, m->ws->tb_count, m->ws->tb_lid, m->ws->tb_list, &m->ws->tb_mask, m->ws->tb_cap, lcap, s));
+  VSM_TRY(ws->pw.ensure((size_t)n_px * 16, s));
+  VSM_TRY(ws->pt_slot.ensure((size_t)n_px * 4, s));
+  VSM_TRY(ensure_local_table(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap, lcap, s));
   if (filters)
-    VSM_TRY(ensure_local_table(m->ws->ta_keys, m->ws->ta_count, m->ws->ta_lid, m->ws->ta_list, nullptr, m->ws->ta_cap, lcap, s));
-
-  LocalTable ta{}, tb{};
-  tb.keys = m->ws->tb_keys.as<unsigned long long>();
-  tb.count = m->ws->tb_count.as<uint32_t>();
-  tb.lid = m->ws->tb_lid.as<uint32_t>();
-  tb.mask = m->ws->tb_mask.as<unsigned long long>();
-  tb.slot_list = m->ws->tb_list.as<uint32_t>();
-  tb.n_occ = &ctr->n_occ_b;
-  tb.cap_mask = (uint32_t)(m->ws->tb_cap - 1);
-  if (filters) {
-    ta.keys = m->ws->ta_keys.as<unsigned long long>();
-    ta.count = m->ws->ta_count.as<uint32_t>();
-    ta.lid = m->ws->ta_lid.as<uint32_t>();
-    ta.mask = nullptr;
-    ta.slot_list = m->ws->ta_list.as<uint32_t>();
-    ta.n_occ = &ctr->n_occ_a;
-    ta.cap_mask = (uint32_t)(m->ws->ta_cap - 1);
+    VSM_TRY(ensure_local_table(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, lcap, s));
+  VSM_TRY(ws->lv_cnt.ensure((size_t)n_sel_max * 4, s));
+  VSM_TRY(ws->lv_off.ensure((size_t)n_sel_max * 4, s));
+  VSM_TRY(ws->lv_cursor.ensure((size_t)n_sel_max * 4, s));
+  VSM_TRY(ws->lv_gid.ensure((size_t)n_sel_max * 4, s));
+  if (!pixel_order) VSM_TRY(ws->sorted_pix.ensure((size_t)n_sel_max * 8, s));  // packed entries
+  // grow ahead of need when the previous call's voxel count suggests it (saves an aborted attempt)
+  {
+    const int64_t guess = m->n_vox + m->last_n_occ + m->last_n_occ / 4 + 1024;
+    if (guess > m->vcap) VSM_TRY(map_grow(m, guess, s));
+    // contributor log: one entry per (call, voxel); keep room for twice the previous call (24 bytes an entry)
+    const int64_t need_free = std::max<int64_t>(2 * m->last_n_occ + 1024, (int64_t)1 << 18);
+    if (m->log_cap - m->log_n < need_free) VSM_TRY(log_grow(m, m->log_n + need_free, s));
   }
+
+  LocalTable tb = table_view(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap,
+                             &ctr->n_occ_b);
+  LocalTable ta{};
+  if (filters)
+    ta = table_view(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, &ctr->n_occ_a);
 
   // optional exact finite-row filter on the embeddings (second read of the rows)
   DevBuf precheck_mask;
+  struct Releaser {
+    DevBuf& b;
+    cudaStream_t s;
+    ~Releaser() {
+      if (b.p) cudaStreamSynchronize(s);
+      b.release();
+    }
+  } releaser{precheck_mask, s};
   if (filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr && emb_dev != nullptr) {
     VSM_TRY(precheck_mask.ensure((size_t)n_px, s));
     const int nvec = (int)(row_bytes / 16);
@@ -826,44 +921,55 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     VSM_LAUNCHED();
     emb_ok = precheck_mask.as<uint8_t>();
   }
-  struct Releaser {
-    DevBuf& b;
-    ~Releaser() { b.release(); }
-  } releaser{precheck_mask};
+  const bool check = filters && emb_ok == nullptr;  // optimistic non-finite detection on the embeddings
 
+  // ---- world points (+ pass 0 of the select) ---------------------------------------------------------
+  SelectState* sst = nullptr;
+  uint32_t* hist = nullptr;
+  float* sel_out = nullptr;
+  if (filters) {
+    VSM_TRY(select_scratch(&sst, &hist, &sel_out));
+    VSM_TRY(select_reset(sst, hist, s));
+  }
   HMat Hm;
   for (int i = 0; i < 16; ++i) Hm.m[i] = p->H_world_map[i];
   WorldArgs wa;
   wa.pts = pts;
   wa.conf = conf;
   wa.emb_ok = emb_ok;
-  wa.pw = m->ws->pw.as<float4>();
-  wa.n_px = n_px;
-  wa.H = p->H;
-  wa.W = p->W;
-  wa.stride = p->stride;
+  wa.pw = ws->pw.as<float4>();
+  wa.n_px = (uint32_t)n_px;
+  wa.H = (uint32_t)p->H;
+  wa.W = (uint32_t)p->W;
+  wa.stride = (uint32_t)p->stride;
   wa.thr = p->conf_threshold;
-  if (aligned16(pts) && aligned16(conf) && n_px >= 4) {
-    world_points_vec4_kernel<<<grid_for(n_px >> 2, 256), 256, 0, s>>>(wa, Hm, ctr);
+  wa.hist0 = hist;
+  const bool vec4 = aligned16(pts) && aligned16(conf) && n_px >= 4;
+  const int wgrid = grid_for(vec4 ? cdiv(n_px, 4) : n_px, 256);
+  if (vec4) {
+    if (filters)
+      world_points_kernel<true, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
+    else
+      world_points_kernel<true, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
   } else {
-    world_points_scalar_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(wa, Hm, ctr);
+    if (filters)
+      world_points_kernel<false, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
+    else
+      world_points_kernel<false, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
   }
   VSM_LAUNCHED();
 
+  // ---- filters and the two submap-local tables -----------------------------------------------------------
   FilterArgs fa;
-  fa.pw = m->ws->pw.as<float4>();
-  fa.pt_slot = m->ws->pt_slot.as<int32_t>();
-  fa.n_px = n_px;
-  fa.px_per_frame = px_per_frame;
+  fa.pw = ws->pw.as<float4>();
+  fa.pt_slot = ws->pt_slot.as<int32_t>();
+  fa.n_px = (uint32_t)n_px;
+  fa.px_per_frame = (uint32_t)px_per_frame;
   fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
   const int grid = grid_for(n_px, 256);
   if (filters) {
-    SelectState* sst;
-    uint32_t* hist;
-    float* sel_out;
-    VSM_TRY(select_scratch(&sst, &hist, &sel_out));
     SelSrc src;
-    src.base = reinterpret_cast<const float*>(m->ws->pw.p);
+    src.base = reinterpret_cast<const float*>(ws->pw.p);
     src.stride = 4;
     src.ncol = 3;
     src.flag_off = 3;
@@ -871,7 +977,7 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     src.n_items = n_px;
     const float q0 = (float)p->bbox_lo_pct / 100.0f;  // numpy: q / float32(100) in float32
     const float q1 = (float)p->bbox_hi_pct / 100.0f;
-    VSM_TRY(run_percentiles(sst, hist, src, 2, q0, q1, ctr->bounds, s));
+    VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
     fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
     bbox_coarse_kernel<<<grid, 256, 0, s>>>(fa, ta, ctr);
     VSM_LAUNCHED();
@@ -883,73 +989,29 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     fine_insert_kernel<false><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
     VSM_LAUNCHED();
   }
-  FuseCounters hc{};
-  VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));
-  st.n_conf = (int64_t)hc.n_conf;
-  st.n_finite = (int64_t)hc.n_finite;
-  st.n_bbox = filters ? (int64_t)hc.n_bbox : (int64_t)hc.n_conf;
-  st.n_fused = (int64_t)hc.n_fused;
-  st.n_submap_voxels = hc.n_occ_b;
-  if (filters)
-    for (int i = 0; i < 3; ++i) {
-      st.bbox_lo[i] = hc.bounds[2 * i];
-      st.bbox_hi[i] = hc.bounds[2 * i + 1];
-    }
-  if (filters && hc.n_occ_a) {
-    table_cleanup_kernel<<<grid_for(hc.n_occ_a, 256), 256, 0, s>>>(ta, hc.n_occ_a);
-    VSM_LAUNCHED();
-  }
-  auto cleanup_b = [&]() -> int {
-    if (hc.n_occ_b) {
-      table_cleanup_kernel<<<grid_for(hc.n_occ_b, 256), 256, 0, s>>>(tb, hc.n_occ_b);
-      VSM_LAUNCHED();
-    }
-    return VSM_OK;
-  };
-  if (hc.internal_err || hc.range_err) {
-    VSM_TRY(cleanup_b());
-    if (stats) *stats = st;
-    if (hc.internal_err) {
-      set_error("internal: local hash probe limit hit (%u)", hc.internal_err);
-      return VSM_E_INTERNAL;
-    }
-    set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", hc.range_err);
-    return VSM_E_COORD_RANGE;
-  }
-  const uint32_t n_occ = hc.n_occ_b;
-  const int64_t n_fused = (int64_t)hc.n_fused;
-  if (n_occ == 0) {
-    m->fuses.push_back(rec);
-    if (stats) *stats = st;
-    return VSM_OK;
-  }
+  const uint32_t log_free = (uint32_t)std::min<int64_t>(m->log_cap - m->log_n, 0xFFFFFFFFll);
+  post_insert_kernel<<<148 * 2, 256, 0, s>>>(ta, filters ? 1 : 0, ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
+                                             log_free, (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
+  VSM_LAUNCHED();
 
-  VSM_TRY(map_grow(m, m->n_vox + n_occ, s));
-  VSM_TRY(log_grow(m, m->log_n + n_occ, s));
-  VSM_TRY(m->ws->lv_cnt.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  VSM_TRY(m->ws->lv_off.ensure(((size_t)n_occ + 1) * 4, s, 0, 1.25));
-  VSM_TRY(m->ws->lv_cursor.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  VSM_TRY(m->ws->lv_gid.ensure((size_t)n_occ * 4, s, 0, 1.25));
-  local_compact_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, m->ws->lv_cnt.as<uint32_t>());
+  // ---- distinct voxels -> global map; points -> sorted entries ---------------------------------------------
+  const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)148 * 8 * 256), 256, 148 * 8);
+  local_compact_kernel<<<vgrid, 256, 0, s>>>(tb, ctr, ws->lv_cnt.as<uint32_t>(), ws->lv_off.as<uint32_t>(),
+                                             ws->lv_cursor.as<uint32_t>());
   VSM_LAUNCHED();
-  global_merge_kernel<<<grid_for(n_occ, 256), 256, 0, s>>>(tb, n_occ, global_store(m), m->ws->lv_cnt.as<uint32_t>(),
-                                                           m->ws->lv_gid.as<int32_t>(), m->log_gid.as<int32_t>(),
-                                                           m->log_fuse.as<int32_t>(),
-                                                           m->log_mask.as<unsigned long long>(), m->log_n,
-                                                           p->submap_id, ctr);
+  global_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ws->lv_cnt.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
+                                            m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
+                                            m->log_mask.as<unsigned long long>(), m->log_n, p->submap_id, ctr);
   VSM_LAUNCHED();
-  rec.log_end = m->log_n + n_occ;
-  rec.n_fused = n_fused;
 
   int32_t* point_gid = nullptr;
   if (keep_index) {
     VSM_TRY(rec.point_gid.ensure((size_t)p->S * px_per_frame * 4, s));
     point_gid = rec.point_gid.as<int32_t>();
-    if (p->end_idx < p->S)
-      VSM_CUDA(cudaMemsetAsync(point_gid + n_px, 0xFF, (size_t)(p->S - p->end_idx) * px_per_frame * 4, s));
+    VSM_CUDA(cudaMemsetAsync(point_gid, 0xFF, (size_t)p->S * px_per_frame * 4, s));
   } else if (pixel_order) {
-    VSM_TRY(m->ws->sorted_gid.ensure((size_t)n_px * 4, s, 0, 1.1));  // reused as the per-pixel id array
-    point_gid = m->ws->sorted_gid.as<int32_t>();
+    VSM_TRY(ws->sorted_gid.ensure((size_t)n_px * 4, s, 0, 1.1));  // per-pixel voxel ids
+    point_gid = ws->sorted_gid.as<int32_t>();
   }
 
   AccArgs aa{};
@@ -959,45 +1021,25 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
   aa.nvec = (int)(row_bytes / 16);
   aa.ctr = ctr;
   if (!pixel_order) {
-    size_t tmp_bytes = 0;
-    VSM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m->ws->lv_cnt.as<uint32_t>(), m->ws->lv_off.as<uint32_t>(),
-                                           (int)n_occ, s));
-    VSM_TRY(m->cub_tmp.ensure(tmp_bytes, s));
-    VSM_CUDA(cub::DeviceScan::ExclusiveSum(m->cub_tmp.p, tmp_bytes, m->ws->lv_cnt.as<uint32_t>(),
-                                           m->ws->lv_off.as<uint32_t>(), (int)n_occ, s));
-    ++g_launches;
-    VSM_CUDA(cudaMemsetAsync(m->ws->lv_cursor.p, 0, (size_t)n_occ * 4, s));
-    VSM_TRY(m->ws->sorted_pix.ensure((size_t)n_fused * 4, s, 0, 1.1));
-    VSM_TRY(m->ws->sorted_gid.ensure((size_t)n_fused * 4, s, 0, 1.1));
-    scatter_kernel<<<grid, 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), n_px, tb, m->ws->lv_off.as<uint32_t>(),
-                                        m->ws->lv_cursor.as<uint32_t>(), m->ws->lv_gid.as<int32_t>(),
-                                        m->ws->sorted_pix.as<uint32_t>(), m->ws->sorted_gid.as<int32_t>(), point_gid);
+    scatter_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
+                                        ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
+                                        ws->lv_gid.as<int32_t>(), check ? 1 : 0,
+                                        ws->sorted_pix.as<unsigned long long>(), point_gid, ctr);
     VSM_LAUNCHED();
-    VSM_TRY(cleanup_b());
+    table_cleanup_kernel<<<vgrid, 256, 0, s>>>(tb);
+    VSM_LAUNCHED();
     aa.emb = emb_dev;
     aa.pix_base = 0;
-    aa.sorted_pix = m->ws->sorted_pix.as<uint32_t>();
-    aa.sorted_gid = m->ws->sorted_gid.as<int32_t>();
-    aa.n = n_fused;
-    const bool check = filters && emb_ok == nullptr;
+    aa.entries = ws->sorted_pix.as<unsigned long long>();
     if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[1], s));
     VSM_TRY(launch_accumulate(aa, bf16, true, check, s));
     if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[2], s));
-    if (check && (int64_t)hc.n_finite > n_fused) {
-      if (bf16)
-        emb_check_kernel<true><<<grid_for(n_px, 256), 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px,
-                                                                   emb_dev, row_bytes, aa.nvec, ctr);
-      else
-        emb_check_kernel<false><<<grid_for(n_px, 256), 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px,
-                                                                    emb_dev, row_bytes, aa.nvec, ctr);
-      VSM_LAUNCHED();
-    }
   } else {
-    const bool check = filters && emb_ok == nullptr;
-    point_gid_kernel<<<grid, 256, 0, s>>>(m->ws->pt_slot.as<int32_t>(), m->ws->pw.as<float4>(), n_px, tb,
-                                          m->ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid);
+    point_gid_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
+                                          ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
     VSM_LAUNCHED();
-    VSM_TRY(cleanup_b());
+    table_cleanup_kernel<<<vgrid, 256, 0, s>>>(tb);
+    VSM_LAUNCHED();
     aa.point_gid = point_gid;
     if (host == nullptr) {
       aa.emb = emb_dev;
@@ -1026,16 +1068,44 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     }
   }
 
-  struct Tail {
-    unsigned long long n_bad;
-    uint32_t internal_err;
-    uint32_t n_vox;
-  };
+  // ---- the one synchronisation of the call ----------------------------------------------------------------
+  FuseCounters hc{};
   VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));
+  *hc_out = hc;
+  st.n_conf = (int64_t)hc.n_conf;
+  st.n_finite = (int64_t)hc.n_finite;
+  st.n_bbox = filters ? (int64_t)hc.n_bbox : (int64_t)hc.n_conf;
+  st.n_fused = (int64_t)hc.n_fused;
+  st.n_submap_voxels = hc.n_occ_b;
+  if (filters)
+    for (int i = 0; i < 3; ++i) {
+      st.bbox_lo[i] = hc.bounds[2 * i];
+      st.bbox_hi[i] = hc.bounds[2 * i + 1];
+    }
+  if (stats) *stats = st;
+  if (hc.internal_err && !hc.abort) {
+    set_error("internal: hash overflow (%u)", hc.internal_err);
+    return VSM_E_INTERNAL;
+  }
+  if (hc.abort) {
+    rec.point_gid.release();
+    if (hc.internal_err) {
+      set_error("internal: local hash probe limit hit (%u)", hc.internal_err);
+      return VSM_E_INTERNAL;
+    }
+    if (hc.range_err) {
+      set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", hc.range_err);
+      return VSM_E_COORD_RANGE;
+    }
+    *retry = true;  // the map has to grow first; nothing was modified
+    return VSM_OK;
+  }
   uint32_t n_vox_dev = 0;
   VSM_TRY(read_back(m, &n_vox_dev, m->d_n_vox.p, sizeof(uint32_t), s));
   m->n_vox = (int64_t)n_vox_dev;
-  if (prof) {
+  m->last_n_occ = hc.n_occ_b;
+  const int64_t n_fused = (int64_t)hc.n_fused;
+  if (prof && n_fused > 0) {
     float t_all = 0.f, t_acc = 0.f;
     VSM_CUDA(cudaEventElapsedTime(&t_all, m->ev_prof[0], m->ev_prof[2]));
     VSM_CUDA(cudaEventElapsedTime(&t_acc, m->ev_prof[1], m->ev_prof[2]));
@@ -1043,25 +1113,39 @@ static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint
     m->prof.accumulate_ms += t_acc;
     m->prof.fuse_calls += 1;
     m->prof.accumulate_launches += 1;
-    m->prof.accumulate_bytes += n_fused * row_bytes + (int64_t)n_occ * m->d * 4;
+    m->prof.accumulate_bytes += n_fused * row_bytes + (int64_t)hc.n_occ_b * m->d * 4;
     m->prof.points_fused += n_fused;
   }
+  rec.log_end = m->log_n + hc.n_occ_b;
+  rec.n_fused = n_fused;
   m->log_n = rec.log_end;
   m->fuses.push_back(rec);
   st.n_map_voxels = m->n_vox;
   st.n_bad_emb_rows = (int64_t)hc.n_bad_emb;
   if (stats) *stats = st;
-  if (hc.internal_err) {
-    set_error("internal: global hash overflow (%u)", hc.internal_err);
-    return VSM_E_INTERNAL;
-  }
   if (hc.n_bad_emb) {
-    set_error("%llu non-finite embedding rows met in the optimistic filter pass; clear the map and fuse again with "
-              "VSM_FUSE_EMB_PRECHECK",
+    set_error("%llu non-finite embedding rows / voxel sums met in the optimistic filter pass; clear the map and "
+              "fuse again with VSM_FUSE_EMB_PRECHECK",
               (unsigned long long)hc.n_bad_emb);
     return VSM_E_NONFINITE_EMB;
   }
   return VSM_OK;
+}
+
+static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
+                     const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s) {
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    bool retry = false;
+    FuseCounters hc{};
+    VSM_TRY(fuse_attempt(m, pts, conf, emb_dev, emb_ok, host, p, stats, s, &retry, &hc));
+    if (!retry) return VSM_OK;
+    VSM_TRY(map_grow(m, m->n_vox + (int64_t)hc.n_occ_b, s));
+    VSM_TRY(log_grow(m, m->log_n + (int64_t)hc.n_occ_b, s));
+    m->last_n_occ = hc.n_occ_b;
+  }
+  set_error("internal: fuse call kept aborting after the map was grown");
+  return VSM_E_INTERNAL;
 }
 
 }  // namespace vsm

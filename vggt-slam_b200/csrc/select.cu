@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(256) sel_hist0_kernel(SelSrc src, uint32_t* __
 }
 
 // turn percentiles into ranks:  pcts are q/100 as float32 (host computes f32(q)/f32(100))
-__global__ void sel_plan_kernel(SelectState* st, int ncol, int npct, float q0, float q1) {
+__global__ void sel_plan_kernel(SelectState* st, int ncol, int npct, float q0, float q1,
+                                const unsigned long long* n_dev) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (n_dev) st->n = *n_dev;
   const unsigned long long n = st->n;
   st->n_targets = ncol * npct * 2;
   st->targets_per_col = npct * 2;
@@ -198,7 +200,41 @@ int run_percentiles(SelectState* st, uint32_t* h0, const SelSrc& src, int npct, 
   const int grid = grid_for(src.n_items, 256, 148 * 8);
   sel_hist0_kernel<<<grid, 256, 0, s>>>(src, h0, st, 1);
   VSM_LAUNCHED();
-  sel_plan_kernel<<<1, 32, 0, s>>>(st, src.ncol, npct, q0, q1);
+  sel_plan_kernel<<<1, 32, 0, s>>>(st, src.ncol, npct, q0, q1, nullptr);
+  VSM_LAUNCHED();
+  sel_pick_kernel<<<nt, 32, 0, s>>>(st, h0, 2048, 11, 1);
+  VSM_LAUNCHED();
+  sel_histn_kernel<<<grid, 256, 0, s>>>(src, h1, st, 21, 10, 2047u);
+  VSM_LAUNCHED();
+  sel_pick_kernel<<<nt, 32, 0, s>>>(st, h1, 2048, 11, 0);
+  VSM_LAUNCHED();
+  sel_histn_kernel<<<grid, 256, 0, s>>>(src, h2, st, 10, 0, 1023u);
+  VSM_LAUNCHED();
+  sel_pick_kernel<<<nt, 32, 0, s>>>(st, h2, 1024, 10, 0);
+  VSM_LAUNCHED();
+  sel_finish_kernel<<<1, 32, 0, s>>>(st, out_dev, src.ncol * npct);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
+
+int select_reset(SelectState* st, uint32_t* hist, cudaStream_t s) {
+  VSM_CUDA(cudaMemsetAsync(st, 0, sizeof(SelectState), s));
+  VSM_CUDA(cudaMemsetAsync(hist, 0, kSelHistWords * sizeof(uint32_t), s));
+  return VSM_OK;
+}
+
+int run_percentiles_after_hist0(SelectState* st, uint32_t* h0, const SelSrc& src, int npct, float q0, float q1,
+                                float* out_dev, const unsigned long long* n_dev, cudaStream_t s) {
+  if (src.ncol < 1 || src.ncol > 3 || npct < 1 || npct > 2) {
+    set_error("run_percentiles: unsupported shape");
+    return VSM_E_INVALID;
+  }
+  const int nt = src.ncol * npct * 2;
+  uint32_t* h1 = h0 + 3 * 2048;
+  uint32_t* h2 = h1 + kSelMaxTargets * 2048;
+  const int grid = grid_for(src.n_items, 256, 148 * 8);
+  sel_plan_kernel<<<1, 32, 0, s>>>(st, src.ncol, npct, q0, q1, n_dev);
   VSM_LAUNCHED();
   sel_pick_kernel<<<nt, 32, 0, s>>>(st, h0, 2048, 11, 1);
   VSM_LAUNCHED();

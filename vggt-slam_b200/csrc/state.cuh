@@ -44,8 +44,11 @@ struct FuseCounters {
   unsigned long long n_conf, n_finite, n_bbox, n_fused, n_bad_emb;
   uint32_t n_occ_a, n_occ_b;
   uint32_t range_err, internal_err;
-  uint32_t n_new_voxels, pad;
-  float bounds[6];  // bbox filter bounds laid out [axis][lo,hi]
+  uint32_t abort;      // set on the device when the call must stop before touching the global map
+  uint32_t seg_total;  // running allocation of sorted-list positions
+  uint32_t n_check;    // check-only entries appended behind the fused ones
+  uint32_t pad;
+  float bounds[6];     // bbox filter bounds laid out [axis][lo,hi]
 };
 
 // radix-select state (device)
@@ -102,6 +105,7 @@ struct vsm_map {
   vsm::DevBuf gkeys, gids;
   int64_t vcap = 0;
   int64_t n_vox = 0;  // host mirror of *d_n_vox
+  int64_t last_n_occ = 0;  // distinct voxels of the previous fuse call (growth heuristic)
   vsm::DevBuf vkey, vcount, vsum;
   vsm::DevBuf d_n_vox;  // uint32 voxel counter on device
 
@@ -158,6 +162,11 @@ struct SelSrc {
 // out_dev receives ncol*npct floats laid out [col][pct]; valid elements are counted in pass 0.
 int run_percentiles(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1, float* out_dev,
                     cudaStream_t s);
+// the same, for a caller that has already filled pass 0 (hist[0..3*2048), after select_reset) and knows the
+// element count on the device (n_dev)
+int select_reset(SelectState* st, uint32_t* hist, cudaStream_t s);
+int run_percentiles_after_hist0(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1,
+                                float* out_dev, const unsigned long long* n_dev, cudaStream_t s);
 // process-wide scratch per device: select state, histograms, 16 result floats
 int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);
