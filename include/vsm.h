@@ -143,6 +143,16 @@ VSM_API int vsm_select_points(const float* pts_dev, const float* conf_dev, const
 VSM_API int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* conf_dev, const void* emb_dev,
                     const uint8_t* emb_ok_dev, const vsm_fuse_params* p, vsm_fuse_stats* stats_host, void* stream);
 
+/* The two halves of vsm_fuse_submap.  _async queues the call's kernels on `stream` and returns without waiting
+ * (the inputs must stay valid until the call is collected); _collect synchronises once for all queued calls,
+ * repeats the ones the device stopped for lack of room (after growing the map), writes up to max_stats stats
+ * in call order, the number of collected calls to n_stats_host, and returns the first failing call's status.
+ * vsm_finalize and the exchange calls collect implicitly. */
+VSM_API int vsm_fuse_submap_async(vsm_map* m, const float* pts_dev, const float* conf_dev, const void* emb_dev,
+                                  const uint8_t* emb_ok_dev, const vsm_fuse_params* p, void* stream);
+VSM_API int vsm_fuse_collect(vsm_map* m, vsm_fuse_stats* stats_host, int32_t max_stats, int32_t* n_stats_host,
+                             void* stream);
+
 /* Same call with HOST arrays (pinned or pageable): stages geometry first, then
  * streams the embeddings frame by frame through pinned double buffers while
  * the pixel-order accumulate kernel consumes them.  This is the end-to-end

@@ -158,8 +158,8 @@ extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
     set_error("device ordinal %d not supported", dev);
     return VSM_E_INVALID;
   }
-  int st = m->d_n_vox.ensure(sizeof(uint32_t), nullptr);
-  if (st == VSM_OK) st = cudaMemset(m->d_n_vox.p, 0, sizeof(uint32_t)) == cudaSuccess ? VSM_OK : VSM_E_CUDA;
+  int st = m->d_n_vox.ensure(2 * sizeof(uint32_t), nullptr);
+  if (st == VSM_OK) st = cudaMemset(m->d_n_vox.p, 0, 2 * sizeof(uint32_t)) == cudaSuccess ? VSM_OK : VSM_E_CUDA;
   if (st == VSM_OK) st = map_grow(m, std::max<int64_t>(cfg->voxel_capacity, 1024), nullptr);
   if (st != VSM_OK) {
     vsm_map_destroy(m);
@@ -175,7 +175,7 @@ extern "C" int vsm_map_destroy(vsm_map* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   vsm::DevBuf* bufs[] = {&m->gkeys,     &m->gids,      &m->vkey,       &m->vcount,    &m->vsum,       &m->d_n_vox,
-                         &m->log_gid,   &m->log_fuse,  &m->log_mask,   &m->ctr,       &m->sel,        &m->sel_hist,
+                         &m->log_gid,   &m->log_fuse,  &m->log_mask,   &m->ctr, &m->ctr_ring,      &m->sel,        &m->sel_hist,
                          &m->cub_tmp,
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
@@ -191,6 +191,10 @@ extern "C" int vsm_map_destroy(vsm_map* m) {
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   for (int i = 0; i < 3; ++i)
     if (m->ev_prof[i]) cudaEventDestroy(m->ev_prof[i]);
+  for (auto& c : m->pending) c.precheck_mask.release();
+  for (int r = 0; r < vsm::kCallRing; ++r)
+    for (int i = 0; i < 3; ++i)
+      if (m->ev_ring[r][i]) cudaEventDestroy(m->ev_ring[r][i]);
   cudaGetLastError();
   delete m;
   return VSM_OK;
@@ -203,14 +207,18 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_CUDA(cudaStreamSynchronize(s));  // queued fuse calls are dropped with the contents
   VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, m->gcap * 8, s));
   VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, m->gcap * 4, s));
   VSM_CUDA(cudaMemsetAsync(m->vcount.p, 0, (size_t)m->vcap * 4, s));
   VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, (size_t)m->vcap * m->d * 4, s));
-  VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, sizeof(uint32_t), s));
+  VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, 2 * sizeof(uint32_t), s));
+  for (auto& c : m->pending) c.precheck_mask.release();
+  m->pending.clear();
   VSM_CUDA(cudaStreamSynchronize(s));
   m->n_vox = 0;
   m->log_n = 0;
+  m->last_n_occ = 0;
   for (auto& f : m->fuses) f.point_gid.release();
   m->fuses.clear();
   m->finalized = false;

@@ -169,6 +169,7 @@ extern "C" int vsm_partials_pack(vsm_map* m, int32_t world, uint64_t* keys_dev, 
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
   const uint32_t V = (uint32_t)m->n_vox;
   for (int o = 0; o < world; ++o) owner_counts_host[o] = 0;
   if (V == 0) return VSM_OK;
@@ -208,6 +209,7 @@ extern "C" int vsm_partials_merge(vsm_map* m, const uint64_t* keys_dev, const ui
   if (n == 0) return VSM_OK;
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
   m->finalized = false;
   m->ck_built = false;
   VSM_TRY(map_grow(m, m->n_vox + n, s));
@@ -241,6 +243,7 @@ extern "C" int vsm_contrib_pack(vsm_map* m, int32_t world, uint64_t* keys_dev, i
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
   const int64_t M = m->log_n;
   for (int o = 0; o < world; ++o) owner_counts_host[o] = 0;
   if (M == 0) return VSM_OK;
@@ -273,6 +276,7 @@ extern "C" int vsm_contrib_merge(vsm_map* m, const uint64_t* keys_dev, const int
   if (n == 0) return VSM_OK;
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
   m->finalized = false;
   VSM_TRY(log_grow(m, m->log_n + n, s));
   contrib_merge_kernel<<<grid_for(n, 256), 256, 0, s>>>(global_store(m), reinterpret_cast<const unsigned long long*>(keys_dev),
@@ -281,5 +285,8 @@ extern "C" int vsm_contrib_merge(vsm_map* m, const uint64_t* keys_dev, const int
                                                         m->log_mask.as<unsigned long long>());
   VSM_LAUNCHED();
   m->log_n += n;
+  const uint32_t log_n32 = (uint32_t)m->log_n;
+  VSM_CUDA(cudaMemcpyAsync(m->d_n_vox.as<uint32_t>() + 1, &log_n32, 4, cudaMemcpyHostToDevice, s));
+  VSM_CUDA(cudaStreamSynchronize(s));
   return VSM_OK;
 }

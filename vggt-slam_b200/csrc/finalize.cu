@@ -210,6 +210,7 @@ extern "C" int vsm_finalize(vsm_map* m, void* stream) {
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
   const uint32_t V = (uint32_t)m->n_vox;
   m->ck_built = false;
   VSM_TRY(m->id_of_rank.ensure(std::max<size_t>((size_t)V * 4, 16), s));

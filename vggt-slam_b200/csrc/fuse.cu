@@ -258,12 +258,36 @@ __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTab
   if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_fused, (unsigned long long)n_in);
 }
 
+// how many of this call's distinct voxels are not in the global map yet (read-only probe): the exact number the
+// capacity check needs, so that a call is only stopped when the map really has to grow
+__global__ void __launch_bounds__(256) count_new_kernel(LocalTable tb, GlobalStore g, FuseCounters* ctr) {
+  const uint32_t n_occ = ctr->n_occ_b;
+  unsigned n_new = 0;
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
+    const unsigned long long key = tb.keys[tb.slot_list[lid]];
+    uint64_t h = mix64(key) & g.gmask;
+    bool found = false;
+    for (uint64_t probes = 0; probes <= g.gmask; ++probes) {
+      const unsigned long long cur = g.gkeys[h];
+      if (cur == key) {
+        found = true;
+        break;
+      }
+      if (cur == kEmptyKey) break;
+      h = (h + 1) & g.gmask;
+    }
+    n_new += found ? 0u : 1u;
+  }
+  for (int o = 16; o > 0; o >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
+  if (lane_id() == 0 && n_new) atomicAdd(&ctr->n_new, n_new);
+}
+
 // After the inserts: reset the coarse table and decide, on the device, whether the call may go on.  It may not
 // if an error was flagged or if the map / contributor log cannot take this call's voxels: nothing global has
 // been touched yet, so the host can grow the map and simply repeat the call.
 __global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has_ta, FuseCounters* ctr,
-                                                          const uint32_t* __restrict__ n_vox, uint32_t vcap,
-                                                          uint32_t log_free, uint32_t entry_cap) {
+                                                          uint32_t* __restrict__ map_state /* [0] voxels, [1] log */,
+                                                          uint32_t vcap, uint32_t log_cap, uint32_t entry_cap) {
   if (has_ta) {
     const uint32_t n_occ = *ta.n_occ;
     for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
@@ -274,9 +298,16 @@ __global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const uint32_t n_occ = ctr->n_occ_b;
-    const bool fits = ((unsigned long long)*n_vox + n_occ <= vcap) && (n_occ <= log_free) &&
-                      (ctr->n_finite <= (unsigned long long)entry_cap);
-    if (!fits || ctr->range_err || ctr->internal_err) ctr->abort = 1u;
+    const uint32_t log_n = map_state[1];
+    const bool fits = ((unsigned long long)map_state[0] + ctr->n_new <= vcap) &&
+                      ((unsigned long long)log_n + n_occ <= log_cap) &&
+                      (ctr->n_finite <= (unsigned long long)entry_cap || ctr->n_fused <= (unsigned long long)entry_cap);
+    if (!fits || ctr->range_err || ctr->internal_err) {
+      ctr->abort = 1u;
+    } else {
+      ctr->log_base = log_n;  // calls on one stream run one after the other: plain read-modify-write
+      map_state[1] = log_n + n_occ;
+    }
   }
 }
 
@@ -348,10 +379,11 @@ __global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, Global
                                                            const uint32_t* __restrict__ lv_cnt,
                                                            int32_t* __restrict__ lv_gid, int32_t* __restrict__ log_gid,
                                                            int32_t* __restrict__ log_sub,
-                                                           unsigned long long* __restrict__ log_mask, int64_t log_base,
-                                                           int32_t submap_id, FuseCounters* ctr) {
+                                                           unsigned long long* __restrict__ log_mask, int32_t submap_id,
+                                                           FuseCounters* ctr) {
   if (ctr->abort) return;
   const uint32_t n_occ = ctr->n_occ_b;
+  const size_t log_base = ctr->log_base;
   for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
     const uint32_t slot = tb.slot_list[lid];
     const unsigned long long key = tb.keys[slot];
@@ -512,24 +544,27 @@ struct AccArgs {
 };
 
 // CHECK (optimistic non-finite detection, filters on): a non-finite embedding value makes the fp32 sum of its
-// voxel segment non-finite, so the accumulators are tested once per flush instead of testing every row; rows that
-// are only to be checked (pixel mode, id -2) are tested directly.  Any hit is counted in ctr->n_bad_emb and makes
-// the fuse call fail with VSM_E_NONFINITE_EMB (the caller redoes the build with the exact pre-check).
-template <bool BF16, int VPL, bool SORTED, bool CHECK>
+// voxel segment non-finite, so the accumulators are tested once per flush instead of testing every row; entries
+// that are only to be checked (id -2: behind the fused entries in the sorted list, anywhere in pixel mode) are
+// tested directly.  Any hit is counted in ctr->n_bad_emb and makes the fuse call fail with VSM_E_NONFINITE_EMB
+// (the caller redoes the build with the exact pre-check).
+// FULL: every lane owns VPL vectors (nvec == 32*VPL, e.g. d=512): no per-lane predicates in the hot loop.
+template <bool BF16, int VPL, bool SORTED, bool CHECK, bool FULL>
 __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(AccArgs a) {
   constexpr int EPV = RowVec<BF16>::EPV;
   constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
+  if (a.ctr->abort) return;
   const int lane = lane_id();
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  if (a.ctr->abort) return;
-  const int64_t n_entries = SORTED ? (int64_t)a.ctr->n_fused + (int64_t)a.ctr->n_check : a.n;
+  const int64_t n_entries = SORTED ? (int64_t)a.ctr->n_fused : a.n;
   const int64_t n_chunks = (n_entries + 31) >> 5;
-  unsigned n_bad = 0;
-  bool lane_cols[VPL];
-#pragma unroll
-  for (int v = 0; v < VPL; ++v) lane_cols[v] = (lane + 32 * v) < a.nvec;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const int nvec = a.nvec;
   const uint8_t* emb0 = a.emb - a.pix_base * a.row_bytes + (size_t)lane * 16;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  unsigned n_bad = 0;
 
   for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
     const int64_t base = chunk << 5;
@@ -565,14 +600,13 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
           if (!ok && lane == 0) ++n_bad;
         }
         if (ok) {
-          float* dst = a.vsum + (size_t)cur * a.d;
+          float* dst = vsum0 + (size_t)cur * d;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
-            if (lane_cols[v]) {
-              const int c = lane + 32 * v;
+            if (FULL || lane + 32 * v < nvec) {
 #pragma unroll
               for (int q = 0; q < EPV / 4; ++q)
-                red_add_v4(dst + c * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
+                red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
                            acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
             }
           }
@@ -582,7 +616,44 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
       for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
     };
 
-    for (int j = 0; j < cnt; j += U) {
+    int j = 0;
+    if (SORTED && FULL) {
+      // hot loop: U rows in flight, every entry is a fused point, every lane owns VPL vectors
+      for (; j + U <= cnt; j += U) {
+        uint4 rows[U][VPL];
+        int gids[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t pj = __shfl_sync(0xffffffffu, my_pix, j + u);
+          gids[u] = __shfl_sync(0xffffffffu, my_gid, j + u);
+          const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) rows[u][v] = ld_stream_v4(row + v * 512);
+        }
+        bool same = true;
+#pragma unroll
+        for (int u = 0; u < U; ++u) same &= (gids[u] == cur);
+        if (same) {
+          // common case (tens of points per voxel): straight-line adds, no boundary inside the batch
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (gids[u] != cur) {
+              flush();
+              cur = gids[u];
+            }
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+          }
+        }
+      }
+    }
+    // generic loop: tails, partial rows (small d), pixel mode with its skipped / check-only pixels
+    for (; j < cnt; j += U) {
       uint4 rows[U][VPL];
       int gids[U];
 #pragma unroll
@@ -593,10 +664,11 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
         if (j + u >= cnt) gj = -1;
         gids[u] = gj;
         const bool want_row = CHECK ? (gj != -1) : (gj >= 0);
-        const uint8_t* row = emb0 + (size_t)pj * a.row_bytes;
+        const uint8_t* row = emb0 + (unsigned long long)pj * rb;
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
-          rows[u][v] = (want_row && lane_cols[v]) ? ld_stream_v4(row + (size_t)v * 512) : make_uint4(0u, 0u, 0u, 0u);
+          rows[u][v] = (want_row && (FULL || lane + 32 * v < nvec)) ? ld_stream_v4(row + v * 512)
+                                                                   : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -620,6 +692,20 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
     }
     flush();
   }
+
+  if (SORTED && CHECK) {
+    // check-only entries sit behind the fused ones: one warp per row, test the raw values
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        if (FULL || lane + 32 * v < nvec) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+  }
   if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
 }
 
@@ -632,17 +718,26 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
     const int64_t n_chunks = (a.n + 31) >> 5;
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)148 * 6);
   }
+  const bool full = a.nvec == 32 * VPL;
+#define VSM_ACC(SORTED_, CHECK_)                                                      \
+  do {                                                                                \
+    if (full)                                                                         \
+      accumulate_kernel<BF16, VPL, SORTED_, CHECK_, true><<<grid, block, 0, s>>>(a);  \
+    else                                                                              \
+      accumulate_kernel<BF16, VPL, SORTED_, CHECK_, false><<<grid, block, 0, s>>>(a); \
+  } while (0)
   if (sorted) {
     if (check)
-      accumulate_kernel<BF16, VPL, true, true><<<grid, block, 0, s>>>(a);
+      VSM_ACC(true, true);
     else
-      accumulate_kernel<BF16, VPL, true, false><<<grid, block, 0, s>>>(a);
+      VSM_ACC(true, false);
   } else {
     if (check)
-      accumulate_kernel<BF16, VPL, false, true><<<grid, block, 0, s>>>(a);
+      VSM_ACC(false, true);
     else
-      accumulate_kernel<BF16, VPL, false, false><<<grid, block, 0, s>>>(a);
+      VSM_ACC(false, false);
   }
+#undef VSM_ACC
   VSM_LAUNCHED();
   return VSM_OK;
 }
@@ -803,6 +898,10 @@ static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// A fuse call is ENQUEUED (all kernels queued on the caller's stream, nothing read back) and later COLLECTED
+// (one stream synchronisation for any number of queued calls; counters read, aborted calls repeated after the
+// map has grown).  vsm_fuse_submap = enqueue + collect; vsm_fuse_submap_async / vsm_fuse_collect expose the
+// two halves so that a whole build runs without the host ever waiting on the device between submaps.
 struct HostEmb {
   const uint8_t* emb_host = nullptr;  // (S,H,W,d) rows on the host, map dtype
 };
@@ -830,12 +929,12 @@ static LocalTable table_view(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& l
   return t;
 }
 
-// One attempt at a fuse call.  *retry is set when the device-side capacity check stopped the call before it
-// modified the map; the caller grows the map by what `hc` reports and calls again.
-static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
-                        const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s,
-                        bool* retry, FuseCounters* hc_out) {
+static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_stats>* out);
+
+// Queue one fuse call.  Needs the workspace lock.  `host` != null: embeddings are streamed from the host.
+static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cudaStream_t s) {
   Workspace* ws = m->ws;
+  const vsm_fuse_params* p = &call.p;
   const bool filters = (p->flags & VSM_FUSE_FILTERS) != 0;
   const bool keep_index = (p->flags & VSM_FUSE_KEEP_POINT_INDEX) != 0;
   const bool pixel_order = (p->flags & VSM_FUSE_PIXEL_ORDER) != 0 || host != nullptr;
@@ -843,34 +942,27 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
   const int64_t n_px = (int64_t)p->end_idx * p->H * p->W;
   const int64_t px_per_frame = (int64_t)p->H * p->W;
   const int64_t row_bytes = (int64_t)m->d * m->esize;
-  *retry = false;
-  vsm_fuse_stats st{};
-  st.n_map_voxels = m->n_vox;
-  for (int i = 0; i < 3; ++i) st.bbox_lo[i] = st.bbox_hi[i] = __builtin_nanf("");
+  const float* pts = call.pts;
+  const float* conf = call.conf;
+  const uint8_t* emb_dev = call.emb;
+  const uint8_t* emb_ok = call.emb_ok;
 
-  VSM_TRY(m->ctr.ensure(sizeof(FuseCounters), s));
-  FuseCounters* ctr = m->ctr.as<FuseCounters>();
+  VSM_TRY(m->ctr_ring.ensure(sizeof(FuseCounters) * kCallRing, s));
+  FuseCounters* ctr = m->ctr_ring.as<FuseCounters>() + call.slot;
   VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters), s));
   m->finalized = false;
   m->ck_built = false;
-  const bool prof = m->profiling && host == nullptr;
-  if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[0], s));
-
-  FuseRecord rec{};
-  rec.submap_id = p->submap_id;
-  rec.S = p->S;
-  rec.H = p->H;
-  rec.W = p->W;
-  rec.end_idx = p->end_idx;
-  rec.stride = p->stride;
-  rec.log_begin = rec.log_end = m->log_n;
-  if (n_px == 0) {
-    m->fuses.push_back(rec);
-    if (stats) *stats = st;
-    return VSM_OK;
+  call.profiled = m->profiling && host == nullptr;
+  cudaEvent_t* ev = m->ev_ring[call.slot];
+  if (call.profiled) {
+    for (int i = 0; i < 3; ++i)
+      if (!ev[i]) VSM_CUDA(cudaEventCreate(&ev[i]));
+    VSM_CUDA(cudaEventRecord(ev[0], s));
   }
+  if (n_px == 0) return VSM_OK;
 
   // ---- scratch, sized by upper bounds (the exact sizes only exist on the device) -----------------------
+  // DevBuf::ensure synchronises the stream before it replaces a block, so queued calls never lose a buffer.
   const int64_t hs = cdiv(p->H, p->stride), ws_ = cdiv(p->W, p->stride);
   const uint64_t n_sel_max = (uint64_t)p->end_idx * hs * ws_;
   const uint64_t lcap = std::max<uint64_t>(next_pow2(2 * n_sel_max), 1024);
@@ -884,14 +976,6 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
   VSM_TRY(ws->lv_cursor.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_gid.ensure((size_t)n_sel_max * 4, s));
   if (!pixel_order) VSM_TRY(ws->sorted_pix.ensure((size_t)n_sel_max * 8, s));  // packed entries
-  // grow ahead of need when the previous call's voxel count suggests it (saves an aborted attempt)
-  {
-    const int64_t guess = m->n_vox + m->last_n_occ + m->last_n_occ / 4 + 1024;
-    if (guess > m->vcap) VSM_TRY(map_grow(m, guess, s));
-    // contributor log: one entry per (call, voxel); keep room for twice the previous call (24 bytes an entry)
-    const int64_t need_free = std::max<int64_t>(2 * m->last_n_occ + 1024, (int64_t)1 << 18);
-    if (m->log_cap - m->log_n < need_free) VSM_TRY(log_grow(m, m->log_n + need_free, s));
-  }
 
   LocalTable tb = table_view(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap,
                              &ctr->n_occ_b);
@@ -900,26 +984,17 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
     ta = table_view(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, &ctr->n_occ_a);
 
   // optional exact finite-row filter on the embeddings (second read of the rows)
-  DevBuf precheck_mask;
-  struct Releaser {
-    DevBuf& b;
-    cudaStream_t s;
-    ~Releaser() {
-      if (b.p) cudaStreamSynchronize(s);
-      b.release();
-    }
-  } releaser{precheck_mask, s};
   if (filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr && emb_dev != nullptr) {
-    VSM_TRY(precheck_mask.ensure((size_t)n_px, s));
+    VSM_TRY(call.precheck_mask.ensure((size_t)n_px, s));
     const int nvec = (int)(row_bytes / 16);
     if (bf16)
       emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
-                                                        p->conf_threshold, precheck_mask.as<uint8_t>());
+                                                        p->conf_threshold, call.precheck_mask.as<uint8_t>());
     else
       emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
-                                                         p->conf_threshold, precheck_mask.as<uint8_t>());
+                                                         p->conf_threshold, call.precheck_mask.as<uint8_t>());
     VSM_LAUNCHED();
-    emb_ok = precheck_mask.as<uint8_t>();
+    emb_ok = call.precheck_mask.as<uint8_t>();
   }
   const bool check = filters && emb_ok == nullptr;  // optimistic non-finite detection on the embeddings
 
@@ -989,21 +1064,24 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
     fine_insert_kernel<false><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
     VSM_LAUNCHED();
   }
-  const uint32_t log_free = (uint32_t)std::min<int64_t>(m->log_cap - m->log_n, 0xFFFFFFFFll);
+  const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)148 * 8 * 256), 256, 148 * 8);
+  count_new_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr);
+  VSM_LAUNCHED();
   post_insert_kernel<<<148 * 2, 256, 0, s>>>(ta, filters ? 1 : 0, ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
-                                             log_free, (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
+                                             (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
+                                             (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
   VSM_LAUNCHED();
 
   // ---- distinct voxels -> global map; points -> sorted entries ---------------------------------------------
-  const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)148 * 8 * 256), 256, 148 * 8);
   local_compact_kernel<<<vgrid, 256, 0, s>>>(tb, ctr, ws->lv_cnt.as<uint32_t>(), ws->lv_off.as<uint32_t>(),
                                              ws->lv_cursor.as<uint32_t>());
   VSM_LAUNCHED();
   global_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ws->lv_cnt.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
                                             m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
-                                            m->log_mask.as<unsigned long long>(), m->log_n, p->submap_id, ctr);
+                                            m->log_mask.as<unsigned long long>(), p->submap_id, ctr);
   VSM_LAUNCHED();
 
+  FuseRecord& rec = m->fuses[call.fuse_index];
   int32_t* point_gid = nullptr;
   if (keep_index) {
     VSM_TRY(rec.point_gid.ensure((size_t)p->S * px_per_frame * 4, s));
@@ -1031,9 +1109,9 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
     aa.emb = emb_dev;
     aa.pix_base = 0;
     aa.entries = ws->sorted_pix.as<unsigned long long>();
-    if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[1], s));
+    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], s));
     VSM_TRY(launch_accumulate(aa, bf16, true, check, s));
-    if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[2], s));
+    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], s));
   } else {
     point_gid_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
                                           ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
@@ -1045,9 +1123,9 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
       aa.emb = emb_dev;
       aa.pix_base = 0;
       aa.n = n_px;
-      if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[1], s));
+      if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], s));
       VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
-      if (prof) VSM_CUDA(cudaEventRecord(m->ev_prof[2], s));
+      if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], s));
     } else {
       // stream the embeddings frame by frame through two device buffers
       const size_t chunk_bytes = (size_t)px_per_frame * row_bytes;
@@ -1067,90 +1145,193 @@ static int fuse_attempt(vsm_map* m, const float* pts, const float* conf, const u
       }
     }
   }
+  return VSM_OK;
+}
 
-  // ---- the one synchronisation of the call ----------------------------------------------------------------
-  FuseCounters hc{};
-  VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));
-  *hc_out = hc;
-  st.n_conf = (int64_t)hc.n_conf;
-  st.n_finite = (int64_t)hc.n_finite;
-  st.n_bbox = filters ? (int64_t)hc.n_bbox : (int64_t)hc.n_conf;
-  st.n_fused = (int64_t)hc.n_fused;
-  st.n_submap_voxels = hc.n_occ_b;
-  if (filters)
-    for (int i = 0; i < 3; ++i) {
-      st.bbox_lo[i] = hc.bounds[2 * i];
-      st.bbox_hi[i] = hc.bounds[2 * i + 1];
-    }
-  if (stats) *stats = st;
-  if (hc.internal_err && !hc.abort) {
-    set_error("internal: hash overflow (%u)", hc.internal_err);
-    return VSM_E_INTERNAL;
-  }
-  if (hc.abort) {
-    rec.point_gid.release();
-    if (hc.internal_err) {
-      set_error("internal: local hash probe limit hit (%u)", hc.internal_err);
-      return VSM_E_INTERNAL;
-    }
-    if (hc.range_err) {
-      set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", hc.range_err);
-      return VSM_E_COORD_RANGE;
-    }
-    *retry = true;  // the map has to grow first; nothing was modified
-    return VSM_OK;
-  }
-  uint32_t n_vox_dev = 0;
-  VSM_TRY(read_back(m, &n_vox_dev, m->d_n_vox.p, sizeof(uint32_t), s));
-  m->n_vox = (int64_t)n_vox_dev;
-  m->last_n_occ = hc.n_occ_b;
-  const int64_t n_fused = (int64_t)hc.n_fused;
-  if (prof && n_fused > 0) {
-    float t_all = 0.f, t_acc = 0.f;
-    VSM_CUDA(cudaEventElapsedTime(&t_all, m->ev_prof[0], m->ev_prof[2]));
-    VSM_CUDA(cudaEventElapsedTime(&t_acc, m->ev_prof[1], m->ev_prof[2]));
-    m->prof.fuse_ms += t_all;
-    m->prof.accumulate_ms += t_acc;
-    m->prof.fuse_calls += 1;
-    m->prof.accumulate_launches += 1;
-    m->prof.accumulate_bytes += n_fused * row_bytes + (int64_t)hc.n_occ_b * m->d * 4;
-    m->prof.points_fused += n_fused;
-  }
-  rec.log_end = m->log_n + hc.n_occ_b;
-  rec.n_fused = n_fused;
-  m->log_n = rec.log_end;
-  m->fuses.push_back(rec);
-  st.n_map_voxels = m->n_vox;
-  st.n_bad_emb_rows = (int64_t)hc.n_bad_emb;
-  if (stats) *stats = st;
-  if (hc.n_bad_emb) {
-    set_error("%llu non-finite embedding rows / voxel sums met in the optimistic filter pass; clear the map and "
-              "fuse again with VSM_FUSE_EMB_PRECHECK",
-              (unsigned long long)hc.n_bad_emb);
-    return VSM_E_NONFINITE_EMB;
+// Make room before queueing a call.  The device aborts a call that does not fit (and the collect repeats it after
+// growing), so this is only a heuristic that keeps aborts rare: voxel capacity is raised while nothing is queued;
+// the contributor log (exactly one entry per call and voxel) is reserved many calls ahead, sized by the last
+// call's voxel count on this map or, for a fresh map, on this device.
+static int pregrow(vsm_map* m, cudaStream_t s) {
+  const int64_t occ = std::max<int64_t>(m->last_n_occ, m->ws->hint_n_occ);
+  const int64_t per_call = occ + occ / 4 + 1024;
+  if (m->pending.empty() && m->n_vox + per_call > m->vcap) VSM_TRY(map_grow(m, m->n_vox + 2 * per_call, s));
+  const int64_t in_flight = (int64_t)m->pending.size() + 1;
+  if (m->log_n + in_flight * 2 * per_call > m->log_cap) {
+    if (!m->pending.empty()) VSM_TRY(fuse_collect_locked(m, s, nullptr));
+    VSM_TRY(log_grow(m, m->log_n + 32 * 2 * per_call, s));
   }
   return VSM_OK;
 }
 
-static int fuse_core(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb_dev, const uint8_t* emb_ok,
-                     const HostEmb* host, const vsm_fuse_params* p, vsm_fuse_stats* stats, cudaStream_t s) {
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    bool retry = false;
-    FuseCounters hc{};
-    VSM_TRY(fuse_attempt(m, pts, conf, emb_dev, emb_ok, host, p, stats, s, &retry, &hc));
-    if (!retry) return VSM_OK;
-    VSM_TRY(map_grow(m, m->n_vox + (int64_t)hc.n_occ_b, s));
-    VSM_TRY(log_grow(m, m->log_n + (int64_t)hc.n_occ_b, s));
-    m->last_n_occ = hc.n_occ_b;
+static int fuse_submit_locked(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb, const uint8_t* emb_ok,
+                              const HostEmb* host, const vsm_fuse_params* p, cudaStream_t s) {
+  if ((int)m->pending.size() >= kCallRing) VSM_TRY(fuse_collect_locked(m, s, nullptr));
+  VSM_TRY(pregrow(m, s));
+  FuseRecord rec{};
+  rec.submap_id = p->submap_id;
+  rec.S = p->S;
+  rec.H = p->H;
+  rec.W = p->W;
+  rec.end_idx = p->end_idx;
+  rec.stride = p->stride;
+  m->fuses.push_back(rec);
+  PendingCall call{};
+  call.p = *p;
+  call.pts = pts;
+  call.conf = conf;
+  call.emb = emb;
+  call.emb_ok = emb_ok;
+  call.slot = (int)m->pending.size();
+  call.fuse_index = (int)m->fuses.size() - 1;
+  m->pending.push_back(call);
+  const int st = fuse_enqueue(m, m->pending.back(), host, s);
+  if (st != VSM_OK) {
+    cudaStreamSynchronize(s);
+    m->pending.back().precheck_mask.release();
+    m->pending.pop_back();
+    m->fuses.back().point_gid.release();
+    m->fuses.pop_back();
   }
-  set_error("internal: fuse call kept aborting after the map was grown");
-  return VSM_E_INTERNAL;
+  return st;
+}
+
+// Synchronise once, read every queued call's counters, repeat the calls the device aborted for lack of room.
+// Stats are appended to `out` in call order.  The first failing call's status is returned (after all calls
+// have been accounted for); m->last_stats holds the stats of the last call.
+static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_stats>* out) {
+  if (m->pending.empty()) return VSM_OK;
+  const size_t n_calls = m->pending.size();
+  std::vector<FuseCounters> hc(kCallRing);
+  VSM_TRY(read_back(m, hc.data(), m->ctr_ring.p, sizeof(FuseCounters) * n_calls, s));
+  std::vector<PendingCall> calls;
+  calls.swap(m->pending);
+  int first_error = VSM_OK;
+  char first_msg[512] = "";
+  for (size_t k = 0; k < n_calls; ++k) {
+    PendingCall& call = calls[k];
+    FuseCounters c = hc[k];
+    const bool filters = (call.p.flags & VSM_FUSE_FILTERS) != 0;
+    int status = VSM_OK;
+    for (int attempt = 0; c.abort && !c.internal_err && !c.range_err; ++attempt) {
+      // nothing was modified: grow and run the call again, alone
+      if (attempt >= 3) {
+        set_error("internal: fuse call kept aborting after the map was grown");
+        status = VSM_E_INTERNAL;
+        break;
+      }
+      uint32_t state[2] = {0, 0};
+      VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
+      m->n_vox = state[0];
+      m->log_n = state[1];
+      VSM_TRY(map_grow(m, m->n_vox + (int64_t)c.n_new, s));
+      VSM_TRY(log_grow(m, m->log_n + (int64_t)c.n_occ_b, s));
+      call.slot = 0;
+      m->fuses[call.fuse_index].point_gid.release();
+      VSM_TRY(fuse_enqueue(m, call, nullptr, s));
+      VSM_TRY(read_back(m, &c, m->ctr_ring.p, sizeof(FuseCounters), s));
+    }
+    call.precheck_mask.release();
+    vsm_fuse_stats st{};
+    st.n_conf = (int64_t)c.n_conf;
+    st.n_finite = (int64_t)c.n_finite;
+    st.n_bbox = filters ? (int64_t)c.n_bbox : (int64_t)c.n_conf;
+    st.n_fused = (int64_t)c.n_fused;
+    st.n_submap_voxels = c.n_occ_b;
+    st.n_bad_emb_rows = (int64_t)c.n_bad_emb;
+    for (int i = 0; i < 3; ++i) {
+      st.bbox_lo[i] = filters ? c.bounds[2 * i] : __builtin_nanf("");
+      st.bbox_hi[i] = filters ? c.bounds[2 * i + 1] : __builtin_nanf("");
+    }
+    if (status == VSM_OK) {
+      if (c.internal_err) {
+        set_error("internal: hash probe limit / overflow (%u)", c.internal_err);
+        status = VSM_E_INTERNAL;
+      } else if (c.range_err) {
+        set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", c.range_err);
+        status = VSM_E_COORD_RANGE;
+      } else if (c.n_bad_emb) {
+        set_error("%llu non-finite embedding rows / voxel sums met in the optimistic filter pass; clear the map "
+                  "and fuse again with VSM_FUSE_EMB_PRECHECK", (unsigned long long)c.n_bad_emb);
+        status = VSM_E_NONFINITE_EMB;
+      }
+    }
+    if (status == VSM_OK || status == VSM_E_NONFINITE_EMB) {
+      m->last_n_occ = c.n_occ_b;
+      m->ws->hint_n_occ = c.n_occ_b;
+      m->fuses[call.fuse_index].n_fused = (int64_t)c.n_fused;
+      if (call.profiled && c.n_fused > 0 && !hc[k].abort) {
+        float t_all = 0.f, t_acc = 0.f;
+        cudaEvent_t* ev = m->ev_ring[call.slot];
+        VSM_CUDA(cudaEventElapsedTime(&t_all, ev[0], ev[2]));
+        VSM_CUDA(cudaEventElapsedTime(&t_acc, ev[1], ev[2]));
+        m->prof.fuse_ms += t_all;
+        m->prof.accumulate_ms += t_acc;
+        m->prof.fuse_calls += 1;
+        m->prof.accumulate_launches += 1;
+        m->prof.accumulate_bytes += (int64_t)c.n_fused * m->d * m->esize + (int64_t)c.n_occ_b * m->d * 4;
+        m->prof.points_fused += (int64_t)c.n_fused;
+      }
+    }
+    if (status != VSM_OK && first_error == VSM_OK) {
+      first_error = status;
+      snprintf(first_msg, sizeof(first_msg), "%s", vsm_last_error());
+    }
+    m->last_stats = st;
+    if (out) out->push_back(st);
+  }
+  uint32_t state[2] = {0, 0};
+  VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
+  m->n_vox = state[0];
+  m->log_n = state[1];
+  m->last_stats.n_map_voxels = m->n_vox;
+  if (out && !out->empty()) out->back().n_map_voxels = m->n_vox;
+  if (first_error != VSM_OK) set_error("%s", first_msg);
+  return first_error;
+}
+
+int fuse_collect_pending(vsm_map* m, cudaStream_t s) {
+  if (m->pending.empty()) return VSM_OK;
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  return fuse_collect_locked(m, s, nullptr);
 }
 
 }  // namespace vsm
 
 using namespace vsm;
+
+extern "C" int vsm_fuse_submap_async(vsm_map* m, const float* pts_dev, const float* conf_dev, const void* emb_dev,
+                                     const uint8_t* emb_ok_dev, const vsm_fuse_params* p, void* stream) {
+  VSM_TRY(validate_params(m, p));
+  if (!pts_dev || !conf_dev || !emb_dev) {
+    set_error("null device pointer");
+    return VSM_E_INVALID;
+  }
+  if (p->flags & VSM_FUSE_KEEP_POINT_INDEX) {
+    // keeps a per-call array alive in the record: fine, but nothing to gain from queueing
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  return fuse_submit_locked(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int vsm_fuse_collect(vsm_map* m, vsm_fuse_stats* stats_host, int32_t max_stats, int32_t* n_stats_host,
+                                void* stream) {
+  if (!m) {
+    set_error("null map");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  std::vector<vsm_fuse_stats> out;
+  const int st = fuse_collect_locked(m, (cudaStream_t)stream, &out);
+  const int n = (int)std::min<size_t>(out.size(), (size_t)std::max(max_stats, 0));
+  if (stats_host)
+    for (int i = 0; i < n; ++i) stats_host[i] = out[i];
+  if (n_stats_host) *n_stats_host = (int32_t)out.size();
+  return st;
+}
 
 extern "C" int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* conf_dev, const void* emb_dev,
                                const uint8_t* emb_ok_dev, const vsm_fuse_params* p, vsm_fuse_stats* stats_host,
@@ -1161,8 +1342,13 @@ extern "C" int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* co
     return VSM_E_INVALID;
   }
   VSM_CUDA(cudaSetDevice(m->device));
-  return fuse_core(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p, stats_host,
-                   (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  VSM_TRY(fuse_collect_locked(m, s, nullptr));
+  VSM_TRY(fuse_submit_locked(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p, s));
+  const int st = fuse_collect_locked(m, s, nullptr);
+  if (stats_host) *stats_host = m->last_stats;
+  return st;
 }
 
 extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const float* conf_host, const void* emb_host,
@@ -1174,6 +1360,8 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  VSM_TRY(fuse_collect_locked(m, s, nullptr));
   const size_t n_px = (size_t)p->end_idx * p->H * p->W;
   VSM_TRY(m->stage_pts.ensure(std::max<size_t>(n_px * 12, 16), s));
   VSM_TRY(m->stage_conf.ensure(std::max<size_t>(n_px * 4, 16), s));
@@ -1185,7 +1373,47 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   he.emb_host = (const uint8_t*)emb_host;
   vsm_fuse_params q = *p;
   q.flags &= ~VSM_FUSE_EMB_PRECHECK;  // not available when streaming from the host
-  return fuse_core(m, m->stage_pts.as<float>(), m->stage_conf.as<float>(), nullptr, nullptr, &he, &q, stats_host, s);
+  // a call the device aborts for lack of room is repeated by the collect with device-resident inputs only, which
+  // a host-streamed call does not have: make room up front instead (worst case: every selected pixel a new voxel
+  // is far too pessimistic, so use the same guess as the device path and fall back to an explicit retry here)
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    VSM_TRY(pregrow(m, s));
+    FuseRecord rec{};
+    rec.submap_id = q.submap_id;
+    rec.S = q.S;
+    rec.H = q.H;
+    rec.W = q.W;
+    rec.end_idx = q.end_idx;
+    rec.stride = q.stride;
+    m->fuses.push_back(rec);
+    PendingCall call{};
+    call.p = q;
+    call.pts = m->stage_pts.as<float>();
+    call.conf = m->stage_conf.as<float>();
+    call.slot = 0;
+    call.fuse_index = (int)m->fuses.size() - 1;
+    VSM_TRY(fuse_enqueue(m, call, &he, s));
+    FuseCounters c{};
+    VSM_TRY(read_back(m, &c, m->ctr_ring.p, sizeof(FuseCounters), s));
+    if (c.abort && !c.internal_err && !c.range_err) {
+      m->fuses.back().point_gid.release();
+      m->fuses.pop_back();
+      uint32_t state[2] = {0, 0};
+      VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
+      VSM_TRY(map_grow(m, (int64_t)state[0] + (int64_t)c.n_new, s));
+      VSM_TRY(log_grow(m, (int64_t)state[1] + (int64_t)c.n_occ_b, s));
+      m->last_n_occ = c.n_occ_b;
+      continue;
+    }
+    // account for it through the common path
+    m->pending.push_back(call);
+    // counters are already on the host; collect re-reads them (cheap) and fills stats / errors
+    const int st = fuse_collect_locked(m, s, nullptr);
+    if (stats_host) *stats_host = m->last_stats;
+    return st;
+  }
+  set_error("internal: host-streamed fuse call kept aborting after the map was grown");
+  return VSM_E_INTERNAL;
 }
 
 extern "C" int vsm_profile_enable(vsm_map* m, int on) {
@@ -1193,9 +1421,6 @@ extern "C" int vsm_profile_enable(vsm_map* m, int on) {
     set_error("null map");
     return VSM_E_INVALID;
   }
-  VSM_CUDA(cudaSetDevice(m->device));
-  for (int i = 0; i < 3; ++i)
-    if (on && !m->ev_prof[i]) VSM_CUDA(cudaEventCreate(&m->ev_prof[i]));
   m->profiling = on != 0;
   m->prof = vsm_profile{};
   return VSM_OK;

@@ -43,11 +43,12 @@ struct LocalTable {
 struct FuseCounters {
   unsigned long long n_conf, n_finite, n_bbox, n_fused, n_bad_emb;
   uint32_t n_occ_a, n_occ_b;
+  uint32_t n_new, pad0;  // this call's distinct voxels that are new to the map
   uint32_t range_err, internal_err;
   uint32_t abort;      // set on the device when the call must stop before touching the global map
   uint32_t seg_total;  // running allocation of sorted-list positions
   uint32_t n_check;    // check-only entries appended behind the fused ones
-  uint32_t pad;
+  uint32_t log_base;   // first contributor-log entry of this call (allocated on the device)
   float bounds[6];     // bbox filter bounds laid out [axis][lo,hi]
 };
 
@@ -64,6 +65,21 @@ struct SelectState {
   int n_targets;
   int targets_per_col;
 };
+
+// a fuse call that has been queued on the stream and not yet collected
+struct PendingCall {
+  vsm_fuse_params p;
+  const float* pts;
+  const float* conf;
+  const uint8_t* emb;
+  const uint8_t* emb_ok;
+  int slot;             // index into the counter / event rings
+  int fuse_index;       // index into vsm_map::fuses
+  bool profiled;
+  DevBuf precheck_mask; // row mask computed for VSM_FUSE_EMB_PRECHECK, alive until the call is collected
+};
+
+constexpr int kCallRing = 64;  // fuse calls in flight per map
 
 struct FuseRecord {
   int32_t submap_id;
@@ -88,6 +104,7 @@ struct Workspace {
   uint64_t ta_cap = 0, tb_cap = 0;
   DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
   DevBuf sorted_pix, sorted_gid;
+  int64_t hint_n_occ = 0;  // distinct voxels of the last collected fuse call on this device
 };
 Workspace* workspace_for_device(int device);
 }  // namespace vsm
@@ -107,7 +124,11 @@ struct vsm_map {
   int64_t n_vox = 0;  // host mirror of *d_n_vox
   int64_t last_n_occ = 0;  // distinct voxels of the previous fuse call (growth heuristic)
   vsm::DevBuf vkey, vcount, vsum;
-  vsm::DevBuf d_n_vox;  // uint32 voxel counter on device
+  vsm::DevBuf d_n_vox;  // device-side map state: uint32 [0] voxel count, [1] contributor-log entries
+  vsm::DevBuf ctr_ring;  // kCallRing x FuseCounters, one slot per queued fuse call
+  std::vector<vsm::PendingCall> pending;
+  cudaEvent_t ev_ring[vsm::kCallRing][3] = {};
+  vsm_fuse_stats last_stats{};
 
   // contributor log
   int64_t log_n = 0, log_cap = 0;
@@ -171,5 +192,6 @@ int run_percentiles_after_hist0(SelectState* st, uint32_t* hist, const SelSrc& s
 int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);
 int log_grow(vsm_map* m, int64_t need_entries, cudaStream_t s);
+int fuse_collect_pending(vsm_map* m, cudaStream_t s);  // collect queued fuse calls (no-op if none)
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
 }  // namespace vsm

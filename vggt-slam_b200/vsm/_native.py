@@ -71,6 +71,8 @@ SIGNATURES = {
     "vsm_transform_points": (C.c_int, [_vp, _i64, _P(_f64), _vp, C.c_int, _vp]),
     "vsm_select_points": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _P(_f64), _vp, _vp, _P(_i64), _vp]),
     "vsm_fuse_submap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _P(FuseParams), _P(FuseStats), _vp]),
+    "vsm_fuse_submap_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _P(FuseParams), _vp]),
+    "vsm_fuse_collect": (C.c_int, [_vp, _P(FuseStats), _i32, _P(_i32), _vp]),
     "vsm_fuse_submap_host": (C.c_int, [_vp, _vp, _vp, _vp, _P(FuseParams), _P(FuseStats), _vp]),
     "vsm_profile_enable": (C.c_int, [_vp, C.c_int]),
     "vsm_profile_get": (C.c_int, [_vp, _P(Profile)]),

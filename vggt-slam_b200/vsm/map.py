@@ -164,6 +164,17 @@ class GraphMap:
         return dm, fused, frame_name_maps
 
     def _fuse_all(self, dm, todo, stride, ignore_loop, flags, host_streaming, fused, frame_name_maps):
+        queued = []
+
+        def flush():
+            waiting = [i for i, (st, _) in enumerate(queued) if st is None]
+            if not waiting:
+                return
+            got = dm.collect()
+            assert len(got) == len(waiting), (len(got), len(waiting))
+            for i, st in zip(waiting, got):
+                queued[i] = (st, queued[i][1])
+
         for submap in todo:
             S, H, W = _shape(submap.pointclouds)[:3]
             end_idx = S
@@ -195,18 +206,26 @@ class GraphMap:
                 emb_h = emb if isinstance(emb, torch.Tensor) else np.ascontiguousarray(emb)
                 if isinstance(emb_h, np.ndarray) and emb_h.dtype not in (np.float32, np.uint16):
                     emb_h = emb_h.astype(np.float32)
+                flush()  # the host-streamed call synchronises: take the queued calls' stats first
                 stats = dm.fuse_host(pts_h, conf_h, emb_h, params)
             else:
-                stats = dm.fuse(submap._device("points"), submap._device("conf"), submap.embeddings_on_device(),
-                                params)
-            stats = dict(stats, submap_id=sid)
+                # device-resident inputs: queue the call, collect all of them with one synchronisation below
+                dm.fuse_async(submap._device("points"), submap._device("conf"), submap.embeddings_on_device(), params)
+                stats = None
+            queued.append((stats, {"fuse_index": dm.fuse_calls - 1, "submap": submap, "S": S, "H": H, "W": W,
+                                   "end_idx": end_idx, "sid": sid}))
+        flush()
+        for stats, rec in queued:
+            stats = dict(stats, submap_id=rec["sid"])
             self.last_build_stats.append(stats)
             if stats["n_fused"] == 0:
                 continue
-            fused.append({"fuse_index": dm.fuse_calls - 1, "submap": submap, "S": S, "H": H, "W": W,
-                          "end_idx": end_idx})
+            fused.append(rec)
+            submap = rec["submap"]
             if getattr(submap, "frame_id_to_name", None) is not None:
-                frame_name_maps[str(sid)] = dict(submap.frame_id_to_name)
+                frame_name_maps[str(rec["sid"])] = dict(submap.frame_id_to_name)
+        if self.last_build_stats:
+            self.last_build_stats[-1]["n_map_voxels"] = dm.num_voxels
 
 
 def wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contributors=True, exact_coords=False):

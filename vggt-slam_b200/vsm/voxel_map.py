@@ -68,6 +68,7 @@ class DeviceVoxelMap:
         N.check(N.lib.vsm_map_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.fuse_calls = 0
+        self._inflight = []
 
     # -- life cycle -------------------------------------------------------
     def close(self) -> None:
@@ -121,6 +122,32 @@ class DeviceVoxelMap:
         N.check(rc)
         self.fuse_calls += 1
         return self.last_stats
+
+    def fuse_async(self, points: torch.Tensor, conf: torch.Tensor, emb: torch.Tensor, params: N.FuseParams,
+                   emb_ok: Optional[torch.Tensor] = None) -> None:
+        """vsm_fuse_submap_async: queue the call on the current stream and return; `collect` gets the stats.
+        The tensors are kept alive here until then."""
+        assert points.is_cuda and conf.is_cuda and emb.is_cuda
+        assert points.dtype == torch.float32 and conf.dtype == torch.float32
+        assert points.is_contiguous() and conf.is_contiguous() and emb.is_contiguous()
+        assert emb_dtype_code(emb) == self.emb_dtype and emb.shape[-1] == self.dim
+        N.check(N.lib.vsm_fuse_submap_async(self._h, _ptr(points), _ptr(conf), _ptr(emb), _ptr(emb_ok),
+                                            C.byref(params), _stream_ptr(self.device)))
+        self._inflight.append((points, conf, emb, emb_ok))
+        self.fuse_calls += 1
+
+    def collect(self) -> list:
+        """vsm_fuse_collect: one synchronisation for all queued calls; list of stats dicts in call order."""
+        n_max = max(len(self._inflight), 1) + 64
+        arr = (N.FuseStats * n_max)()
+        n = C.c_int32(0)
+        rc = N.lib.vsm_fuse_collect(self._h, arr, n_max, C.byref(n), _stream_ptr(self.device))
+        self._inflight.clear()
+        out = [arr[i].as_dict() for i in range(min(int(n.value), n_max))]
+        if out:
+            self.last_stats = out[-1]
+        N.check(rc)
+        return out
 
     def fuse_host(self, points: np.ndarray, conf: np.ndarray, emb, params: N.FuseParams) -> dict:
         """vsm_fuse_submap_host on HOST arrays (numpy, or CPU torch tensors for bf16)."""
