@@ -66,7 +66,7 @@ class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py):
     polling `nvidia-smi -lms` from a subprocess takes driver locks often enough to stall kernel launches."""
 
-    def __init__(self, index: int, period_s: float = 0.05):
+    def __init__(self, index: int, period_s: float = 0.01):
         self.index = index
         self.period = period_s
         self.samples = []

@@ -87,7 +87,7 @@ typedef struct vsm_fuse_params {
   double bbox_hi_pct;       /* 99.5 (map.py:258) */
   double coarse_factor;     /* 3.0  (map.py:271) */
   int32_t coarse_min_points;/* 10   (map.py:272) */
-  int32_t reserved;
+  int32_t frame_base;       /* index, inside its submap, of this call's frame 0 (per-frame streaming: S = 1 calls) */
 } vsm_fuse_params;
 
 typedef struct vsm_fuse_stats {

@@ -4,6 +4,7 @@
 Bars: voxel key sets (== centres), per-voxel counts, point->voxel indices, top-k indices: bit-exact;
 features and scores: 1e-3 relative (fp32 accumulate), tolerance written at each assert."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -386,3 +387,91 @@ def test_persistence_round_trip(vsm_mod, tmp_path):
     assert lm2.query_with_embedding(q, top_k=5)[0] == m.query_with_embedding(q, top_k=5)[0]
     name, sid, fid = lm2.get_latest_frame_at_voxel(3)
     assert (name, sid, fid) == m.get_latest_frame_at_voxel(3)
+
+
+# ---------------------------------------------------------------------------
+# a16-a18: evaluators, evaluation manager, query CLI
+# ---------------------------------------------------------------------------
+def _saved_map(vsm, tmp_path):
+    z = gio.load("case_c_global_sl4.npz")
+    gm = graph_from(vsm, gio.inputs(z))
+    m = gm.build_semantic_voxel_map(0.05)
+    d = tmp_path / "voxels"
+    m.save_to_directory(str(d))
+    return m, str(d)
+
+
+def test_evaluators_and_manager(vsm_mod, tmp_path):
+    from vsm import voxel_evaluation_manager as mgr
+    from vsm import voxel_evaluators as ev
+
+    m, vdir = _saved_map(vsm_mod, tmp_path)
+    d = m.get_features().shape[1]
+    rng = np.random.default_rng(7)
+    table = {}
+
+    def encoder(texts):  # stands in for the CLIP text tower (weights are not available offline)
+        out = []
+        for t in texts:
+            if t not in table:
+                table[t] = rng.normal(size=d).astype(np.float32) * 3.0
+            out.append(table[t])
+        return np.stack(out)
+
+    # the frame the map retrieves for "chair" is annotated as a chair (valid) but not as a "lamp"
+    q = encoder(["chair"])[0]
+    q = q / np.linalg.norm(q)
+    idx, _, sims = m.query_with_embedding(q, top_k=3)
+    frame, sid, fid = m.get_latest_frame_at_voxel(idx[0])
+    ts = ev.get_ts(frame)
+    assert ts is not None
+    ann = tmp_path / "annotations.json"
+    ann.write_text(json.dumps({"images": [{"file_name": frame, "label": "office chair"},
+                                          {"timestamp": ts + 10**12, "label": "floor lamp"}]}))
+    sve = ev.SearchValidityEvaluator(str(ann), text_encoder=encoder)
+    res = sve.evaluate(m, {"queries": ["chair", "lamp"], "top_k": 3})
+    assert res[0]["found"] and res[0]["valid"] and res[0]["retrieved_voxel_index"] == idx[0]
+    assert res[0]["retrieved_img"] == frame and res[0]["retrieved_submap_id"] == sid and res[0]["retrieved_frame_id"] == fid
+    assert abs(res[0]["score"] - sims[0]) <= 1e-6 * max(1.0, abs(sims[0])) and res[0]["time_diff_ns"] == 0.0
+    assert res[1]["found"] and not res[1]["valid"] and res[1]["closest_gt_label"] == "floor lamp"
+    assert sve.evaluate(m, {}) is None
+    cnt = ev.get_evaluator("voxel_count_metric", {}).evaluate(m, {})
+    assert cnt == {"num_voxels": len(m.get_centers_world()), "feature_dim": d, "voxel_size": 0.05}
+    perf = ev.get_evaluator("performance_metric", {}).evaluate(m, {})
+    assert perf["status"] == "ok" and perf["queries"]["1"]["ms"] > 0
+    with pytest.raises(NotImplementedError):
+        ev.get_evaluator("navigability_metric", {}).evaluate(m, {})
+
+    config = {"experiment_name": "unit test!", "datasets": [{"path": str(tmp_path), "annotation_file": str(ann),
+                                                            "voxel_map_dir": vdir + " "}],
+              "hyperparameters": [{"queries": ["chair", "lamp"], "top_k": 2}, {"queries": "chair"}],
+              "eval_functions": ["search_validity_metric", "voxel_count_metric", "navigability_metric"]}
+    out_file, runs = mgr.run(config, workers=1, out_dir=str(tmp_path / "results"), text_encoder=encoder)
+    assert os.path.basename(out_file) == "unittest.json" and len(runs) == 2
+    saved = json.loads(open(out_file).read())
+    assert saved["experiment_meta"]["experiment_name"] == "unit test!" and len(saved["runs"]) == 2
+    run0 = saved["runs"][0]
+    assert run0["status"] == "success" and run0["history"][0]["voxel_map"] == "voxels"
+    met = run0["history"][0]["metrics"]
+    assert met["search_validity_metric"][0]["valid"] is True and met["voxel_count_metric"]["feature_dim"] == d
+    assert "error" in met["navigability_metric"]  # BaseEvaluator.evaluate raises; the manager records it
+    assert saved["runs"][1]["history"][0]["metrics"]["search_validity_metric"][0]["query"] == "chair"
+    missing = mgr.run_experiment({"dataset_path": "x", "annotation_path": "y", "voxel_dir": str(tmp_path / "nope"),
+                                  "params": {}, "eval_funcs": []})
+    assert missing["status"] == "failed"
+
+
+def test_query_cli(vsm_mod, tmp_path, capsys):
+    from vsm import query_voxelmap as cli
+
+    m, vdir = _saved_map(vsm_mod, tmp_path)
+    d = m.get_features().shape[1]
+    q = np.random.default_rng(3).normal(size=d).astype(np.float32)
+    np.save(tmp_path / "q.npy", q)
+    res = cli.main(["--voxel_map_dir", vdir, "--query_prompt", "a red chair", "--top_k", "2", "--embedding",
+                    str(tmp_path / "q.npy"), "--output_dir", str(tmp_path / "out")])
+    widx, wsims, _ = vo.query(m.get_features(), q / np.linalg.norm(q), 2)
+    assert [r["voxel_index"] for r in res] == widx
+    np.testing.assert_allclose([r["similarity"] for r in res], wsims, rtol=RTOL, atol=1e-6)
+    assert os.path.exists(tmp_path / "out" / "a_red_chair" / "retrieval_results.json")
+    assert "Top 1 retrieval result" in capsys.readouterr().out

@@ -193,6 +193,7 @@ struct FilterArgs {
   int32_t* pt_slot;
   uint32_t n_px;
   uint32_t px_per_frame;
+  uint32_t frame_base;
   float cell;  // coarse cell (bbox_coarse) or voxel size (fine)
   uint32_t min_pts;
 };
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTab
         bool rerr = false;
         key = pack_key(p.x, p.y, p.z, a.cell, rerr);
         if (rerr) atomicAdd(&ctr->range_err, 1u);
-        frame = (int)(pix / a.px_per_frame);
+        frame = (int)(a.frame_base + pix / a.px_per_frame);
       }
     }
     const int slot = warp_insert(tb, act, key, frame, ctr);
@@ -879,8 +880,8 @@ static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
     set_error("stride must be >= 1");  // map.py:187-188
     return VSM_E_INVALID;
   }
-  if (p->end_idx > VSM_MAX_FRAMES) {
-    set_error("%d frames in one submap, max %d", p->end_idx, VSM_MAX_FRAMES);
+  if (p->frame_base < 0 || p->end_idx + p->frame_base > VSM_MAX_FRAMES) {
+    set_error("%d frames in one submap, max %d", p->end_idx + p->frame_base, VSM_MAX_FRAMES);
     return VSM_E_TOO_MANY_FRAMES;
   }
   if ((int64_t)p->end_idx * p->H * p->W >= ((int64_t)1 << 32)) {
@@ -1040,6 +1041,7 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   fa.pt_slot = ws->pt_slot.as<int32_t>();
   fa.n_px = (uint32_t)n_px;
   fa.px_per_frame = (uint32_t)px_per_frame;
+  fa.frame_base = (uint32_t)p->frame_base;
   fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
   const int grid = grid_for(n_px, 256);
   if (filters) {

@@ -96,7 +96,8 @@ class DeviceVoxelMap:
         return int(out.value)
 
     # -- fusion -----------------------------------------------------------
-    def make_params(self, S, H, W, end_idx, stride, conf_threshold, H_world_map, submap_id, flags) -> N.FuseParams:
+    def make_params(self, S, H, W, end_idx, stride, conf_threshold, H_world_map, submap_id, flags,
+                    frame_base: int = 0) -> N.FuseParams:
         p = N.FuseParams()
         p.S, p.H, p.W, p.end_idx, p.stride = int(S), int(H), int(W), int(end_idx), int(stride)
         p.conf_threshold = float(conf_threshold)
@@ -106,6 +107,7 @@ class DeviceVoxelMap:
         p.submap_id = int(submap_id)
         p.flags = int(flags)
         p.bbox_lo_pct, p.bbox_hi_pct, p.coarse_factor, p.coarse_min_points = 0.5, 99.5, 3.0, 10
+        p.frame_base = int(frame_base)
         return p
 
     def fuse(self, points: torch.Tensor, conf: torch.Tensor, emb: torch.Tensor, params: N.FuseParams,
