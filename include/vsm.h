@@ -212,6 +212,10 @@ VSM_API int vsm_lookup(vsm_map* m, const float* pos_dev, int64_t M, int64_t* idx
 VSM_API int vsm_query(vsm_map* m, const float* q_dev, int32_t P, int32_t k, int normalize, int engine, int64_t* idx_dev,
               float* score_dev, void* stream);
 
+/* engine-2 diagnostics: longest candidate list of the last tensor-core query, and how many engine-2 queries were
+ * answered by engine 1 because a candidate list overflowed */
+VSM_API int vsm_query_stats(const vsm_map* m, int64_t* last_candidates_host, int64_t* fallbacks_host);
+
 /* ---- multi-GPU exchange (no reference counterpart) ------------- *
  * Voxels are owned by mix64(key) % world.  pack: groups this map's voxels by owner and writes
  * keys uint64[V], counts uint32[V], sums float[V*d] in owner-major order, per-owner counts to counts_host[world].

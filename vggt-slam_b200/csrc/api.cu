@@ -179,7 +179,8 @@ extern "C" int vsm_map_destroy(vsm_map* m) {
                          &m->cub_tmp,
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
-                         &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm};
+                         &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm,
+                         &m->q_tc,      &m->q_tc_cand};
   for (auto* b : bufs) b->release();
   for (auto& f : m->fuses) f.point_gid.release();
   if (m->pinned) cudaFreeHost(m->pinned);
@@ -222,6 +223,7 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
   for (auto& f : m->fuses) f.point_gid.release();
   m->fuses.clear();
   m->finalized = false;
+  m->norms_valid = false;
   m->dense_loaded = false;
   m->ck_built = false;
   m->csr_entries = 0;

@@ -213,6 +213,7 @@ extern "C" int vsm_finalize(vsm_map* m, void* stream) {
   VSM_TRY(fuse_collect_pending(m, s));
   const uint32_t V = (uint32_t)m->n_vox;
   m->ck_built = false;
+  m->norms_valid = false;
   VSM_TRY(m->id_of_rank.ensure(std::max<size_t>((size_t)V * 4, 16), s));
   VSM_TRY(m->rank_of_id.ensure(std::max<size_t>((size_t)V * 4, 16), s));
   VSM_TRY(m->sorted_keys.ensure(std::max<size_t>((size_t)V * 8, 16), s));

@@ -1,9 +1,495 @@
-// query_tc.cu -- tensor-core (tcgen05) engine of vsm_query.  Placeholder until the kernel lands: fails loudly.
+// query_tc.cu -- tensor-core engine of vsm_query (engine 2): the (voxels x 512) x (512 x prompts) contraction on
+// Blackwell's 5th-generation tensor cores, hand-written for sm_100a:
+//   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128-voxel x 32-channel fp32 tiles of the voxel sums into
+//     shared memory through a 4-stage mbarrier pipeline; the prompt block (<= 64 prompts x d) is loaded once per
+//     CTA and stays resident;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8 per instruction) with the fp32
+//     accumulators in tensor memory (two 64-column accumulators: the epilogue of tile t overlaps the MMAs of t+1);
+//   * four epilogue warps read the accumulators back with tcgen05.ld, scale by 1/count (or the cosine
+//     normaliser) and compare with a per-prompt threshold; survivors are appended to per-prompt candidate lists.
+// TF32 drops mantissa bits, so the tensor-core scores only SELECT candidates, conservatively:
+//   1. thresholds: the exact fp32 engine scores a strided sample of the voxels; the k-th best sample score T_p is
+//      a lower bound of the k-th best score overall;
+//   2. the tensor-core pass keeps voxel v for prompt p if  a(v,p) + 3*eps(v,p) >= T_p  with
+//      eps = 2^-8 * ||f_v|| * ||q_p||  (>= the TF32 product error summed over d channels, Cauchy-Schwarz);
+//   3. the candidates are re-scored exactly in fp32 and the top-k taken with the same keys as engine 1.
+// The result is therefore identical to engine 1 (vggt_slam/semantic_voxel.py:97-116 semantics).  If a candidate
+// list overflows, the call falls back to engine 1.
+#include <cuda.h>
+
 #include "state.cuh"
 
 namespace vsm {
-int query_tc(vsm_map*, const float*, int, int, int, int64_t*, float*, cudaStream_t) {
-  set_error("vsm_query: engine 2 (tcgen05) is not built in this version");
-  return VSM_E_STATE;
+
+int query_exact_rows(vsm_map* m, const float* q_dev, int P, int k, int normalize, uint32_t row_stride, uint32_t n_rows,
+                     int64_t* idx_dev, float* score_dev, cudaStream_t s);  // query.cu
+int query_exact(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_t* idx_dev, float* score_dev,
+                cudaStream_t s);
+int query_select_from_keys(vsm_map* m, const unsigned long long* keys, const uint32_t* counts, int P, int cap, int k,
+                           int64_t* idx_dev, float* score_dev, cudaStream_t s);
+
+namespace tc {
+
+constexpr int kTileM = 128;      // voxels per tile (MMA M)
+constexpr int kTileN = 64;       // prompts per pass (MMA N)
+constexpr int kChunkK = 32;      // fp32 channels per pipeline stage: 128 bytes = one swizzle row
+constexpr int kStages = 4;
+constexpr int kThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 epilogue
+constexpr uint32_t kABytes = kTileM * kChunkK * 4;  // 16 KB per stage
+constexpr uint32_t kBChunkBytes = kTileN * kChunkK * 4;  // 8 KB per K chunk of the prompt block
+constexpr int kTmemCols = 128;   // 2 accumulators x 64 columns
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate; issued by one thread for the CTA
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier when all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B (8-row x 128-byte atoms, 1024 bytes apart along M/N)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)0 << 16;                        // leading byte offset (unused: one swizzle atom along K)
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
+__host__ __device__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+struct TcArgs {
+  const uint32_t* vcount;
+  const float* vnorm;    // ||sum_v||_2 per voxel id
+  const float* thr;      // per prompt of this pass: sample threshold T_p (already in the scored units)
+  const float* qnorm;    // per prompt of this pass: ||q_p||_2
+  uint32_t V;
+  int pb;                // prompts in this pass (<= kTileN)
+  int p0;                // first prompt of the pass
+  int normalize;
+  uint32_t* cand;        // [P][cap] voxel ids
+  uint32_t* cand_cnt;    // [P]
+  uint32_t cap;
+  int n_kchunks;         // d / 32
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout: [B: n_kchunks x 8 KB][A: kStages x 16 KB][barriers]
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + (size_t)a.n_kchunks * kBChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * kABytes);
+  uint64_t* full = bars;                   // [kStages] TMA -> MMA
+  uint64_t* empty = bars + kStages;        // [kStages] MMA -> TMA
+  uint64_t* tfull = bars + 2 * kStages;    // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;            // [2] epilogue -> MMA
+  uint64_t* bfull = tempty + 2;            // [1] prompt block resident
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bfull + 1);
+  __shared__ float s_thr[kTileN], s_qn[kTileN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n_tiles = (a.V + kTileM - 1) / kTileM;
+
+  if (threadIdx.x < kTileN) {
+    s_thr[threadIdx.x] = threadIdx.x < a.pb ? a.thr[threadIdx.x] : __int_as_float(0x7f800000);
+    s_qn[threadIdx.x] = threadIdx.x < a.pb ? a.qnorm[threadIdx.x] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+    }
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    mbar_expect_tx(bfull, (uint32_t)a.n_kchunks * kBChunkBytes);
+    for (int kc = 0; kc < a.n_kchunks; ++kc) tma_load_2d(smem_b + (size_t)kc * kBChunkBytes, &map_b, bfull, kc * kChunkK, 0);
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], kABytes);
+        tma_load_2d(smem_a + (size_t)stage * kABytes, &map_a, &full[stage], kc * kChunkK, (int)(tile * kTileM));
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc();
+    mbar_wait(bfull, 0);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kTileN;
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)stage * kABytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)kc * kBChunkBytes));
+#pragma unroll
+        for (int k = 0; k < kChunkK / 8; ++k)  // K = 8 tf32 (32 bytes) per instruction: advance 32 bytes inside the atom
+          mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        mma_commit(&empty[stage]);  // frees the smem stage when these MMAs are done
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      mma_commit(&tfull[acc]);  // accumulator complete
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> threshold test -> candidate lists =====
+    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const uint32_t id = tile * kTileM + ew * 32 + lane;
+      float inv = 0.f, fn = 0.f;
+      const bool valid = id < a.V;
+      if (valid) {
+        const float cnt = (float)a.vcount[id];
+        const float nrm = a.vnorm[id];
+        fn = __fdiv_rn(nrm, cnt);  // ||f_v||
+        inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
+        if (a.normalize) fn = 1.0f;  // scored quantity is f/||f||: unit norm
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      uint32_t r[kTileN];
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kTileN;
+      tmem_ld32(taddr, r);
+      tmem_ld32(taddr + 32, r + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (valid) {
+        const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
+#pragma unroll 8
+        for (int p = 0; p < kTileN; ++p) {
+          const float sc = __uint_as_float(r[p]) * inv;
+          // !(x < t) also keeps NaN scores (they rank first in torch.topk)
+          if (p < a.pb && !(sc + margin * s_qn[p] < s_thr[p])) {
+            const uint32_t pos = atomicAdd(&a.cand_cnt[a.p0 + p], 1u);
+            if (pos < a.cap) a.cand[(size_t)(a.p0 + p) * a.cap + pos] = id;
+          }
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---- helpers ---------------------------------------------------------------------------------------------------
+// ||sum_v||_2 per voxel id (one warp per row)
+__global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ vsum, uint32_t V, int d, float* __restrict__ out) {
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t id = warp; id < V; id += n_warps) {
+    float ss = 0.f;
+    for (int c = lane; c < d / 4; c += 32) {
+      const uint4 u = ld_stream_v4(vsum + (size_t)id * d + 4 * c);
+      const float x = __uint_as_float(u.x), y = __uint_as_float(u.y), z = __uint_as_float(u.z), w = __uint_as_float(u.w);
+      ss = fmaf(x, x, fmaf(y, y, fmaf(z, z, fmaf(w, w, ss))));
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) out[id] = sqrtf(ss);
+  }
+}
+
+// per prompt: ||q_p|| and the threshold T_p = k-th best sample score (or -inf if the sample has fewer than k rows)
+__global__ void prompt_prep_kernel(const float* __restrict__ q, int P, int d, const float* __restrict__ sample_scores, int k,
+                                   int have_sample, float* __restrict__ qnorm, float* __restrict__ thr) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float ss = 0.f;
+  for (int c = 0; c < d; ++c) ss = fmaf(q[(size_t)p * d + c], q[(size_t)p * d + c], ss);
+  qnorm[p] = sqrtf(ss);
+  float t = __int_as_float(0xff800000);  // -inf
+  if (have_sample) {
+    const float s = sample_scores[(size_t)p * k + (k - 1)];
+    if (s == s) t = s;  // NaN (fewer than k sample rows, or NaN scores) -> keep everything
+  }
+  thr[p] = t;
+}
+
+// zero-padded copy of the prompts of one pass: [kTileN][d]
+__global__ void pad_prompts_kernel(const float* __restrict__ q, int p0, int pb, int d, float* __restrict__ out) {
+  const int total = kTileN * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i / d;
+    out[i] = p < pb ? q[(size_t)(p0 + p) * d + (i % d)] : 0.f;
+  }
+}
+
+// exact fp32 re-scoring of the candidates: one warp per candidate, key = (ordered(score) << 32 | ~rank)
+__global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ vsum, const uint32_t* __restrict__ vcount,
+                                                      const uint32_t* __restrict__ rank_of_id, const float* __restrict__ q,
+                                                      int d, int normalize, const uint32_t* __restrict__ cand,
+                                                      const uint32_t* __restrict__ cand_cnt, uint32_t cap, int P,
+                                                      unsigned long long* __restrict__ keys) {
+  const int lane = lane_id();
+  const int p = blockIdx.y;
+  const uint32_t n = min(cand_cnt[p], cap);
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float* qp = q + (size_t)p * d;
+  for (int64_t i = warp; i < n; i += n_warps) {
+    const uint32_t id = cand[(size_t)p * cap + i];
+    float dot = 0.f, ss = 0.f;
+    for (int c = lane; c < d / 4; c += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(vsum + (size_t)id * d + 4 * c);
+      const float4 w = *reinterpret_cast<const float4*>(qp + 4 * c);
+      ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+      dot = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, dot))));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if (lane == 0) {
+      const float cnt = (float)vcount[id];
+      float inv = 1.0f;
+      if (normalize) inv = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(sqrtf(ss), cnt), 1e-12f));
+      const float sc = __fmul_rn(__fdiv_rn(dot, cnt), inv);
+      keys[(size_t)p * cap + i] =
+          ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - rank_of_id[id]);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p) {
+      cudaGetLastError();
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return VSM_E_CUDA;
+    }
+    fn = (EncodeTiledFn)p;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)kChunkK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d", (int)r);
+    return VSM_E_CUDA;
+  }
+  return VSM_OK;
+}
+
+}  // namespace tc
+
+int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_t* idx_dev, float* score_dev,
+             cudaStream_t s) {
+  using namespace tc;
+  const uint32_t V = (uint32_t)m->n_vox;
+  const int d = m->d;
+  if (d % kChunkK != 0 || d > 1024) {
+    set_error("vsm_query engine 2 needs d to be a multiple of 32 and <= 1024 (d=%d)", d);
+    return VSM_E_INVALID;
+  }
+  const int n_kchunks = d / kChunkK;
+  const size_t smem = (size_t)n_kchunks * kBChunkBytes + (size_t)kStages * kABytes + 256;
+  if (smem > 227 * 1024) {
+    set_error("vsm_query engine 2: d=%d needs %zu bytes of shared memory", d, smem);
+    return VSM_E_INVALID;
+  }
+  // ---- scratch: norms (cached per finalisation), thresholds, candidates ------------------------------------
+  const uint32_t cap = 1u << 16;
+  VSM_TRY(m->q_norm.ensure((size_t)std::max<uint32_t>(V, 1) * 4, s));
+  if (!m->norms_valid) {
+    row_norm_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), V, d, m->q_norm.as<float>());
+    VSM_LAUNCHED();
+    m->norms_valid = true;
+  }
+  // layout of q_tc: [qnorm P][thr P][padded prompts kTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P]
+  const size_t off_qn = 0, off_thr = off_qn + (size_t)P * 4, off_pad = (off_thr + (size_t)P * 4 + 255) & ~(size_t)255;
+  const size_t off_sidx = (off_pad + (size_t)kTileN * d * 4 + 255) & ~(size_t)255;
+  const size_t off_ssc = off_sidx + (size_t)P * k * 8, off_cnt = (off_ssc + (size_t)P * k * 4 + 255) & ~(size_t)255;
+  const size_t small_bytes = off_cnt + (size_t)P * 4;
+  VSM_TRY(m->q_tc.ensure(small_bytes, s));
+  VSM_TRY(m->q_tc_cand.ensure((size_t)P * cap * 12, s));  // ids (u32) + keys (u64)
+  uint8_t* base = m->q_tc.as<uint8_t>();
+  float* qnorm = (float*)(base + off_qn);
+  float* thr = (float*)(base + off_thr);
+  float* qpad = (float*)(base + off_pad);
+  int64_t* sidx = (int64_t*)(base + off_sidx);
+  float* ssc = (float*)(base + off_ssc);
+  uint32_t* cand_cnt = (uint32_t*)(base + off_cnt);
+  uint32_t* cand = m->q_tc_cand.as<uint32_t>();
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(m->q_tc_cand.as<uint8_t>() + (size_t)P * cap * 4);
+
+  // ---- 1. thresholds from an exactly scored strided sample -----------------------------------------------------
+  const uint32_t stride = std::max<uint32_t>(1, V / std::max<uint32_t>(65536u, V / 256));
+  const uint32_t n_sample = (V + stride - 1) / stride;
+  const int have_sample = n_sample >= (uint32_t)k ? 1 : 0;
+  if (have_sample) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride, n_sample, sidx, ssc, s));
+  prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, ssc, k, have_sample, qnorm, thr);
+  VSM_LAUNCHED();
+  VSM_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)P * 4, s));
+
+  // ---- 2. tensor-core pass(es): 64 prompts at a time ------------------------------------------------------------
+  CUtensorMap map_a, map_b;
+  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)m->vcap, (uint64_t)d, kTileM));
+  VSM_TRY(make_map_2d(&map_b, qpad, (uint64_t)kTileN, (uint64_t)d, kTileN));
+  VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const uint32_t n_tiles = (V + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
+  for (int p0 = 0; p0 < P; p0 += kTileN) {
+    const int pb = std::min(kTileN, P - p0);
+    pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, qpad);
+    VSM_LAUNCHED();
+    TcArgs a;
+    a.vcount = m->vcount.as<uint32_t>();
+    a.vnorm = m->q_norm.as<float>();
+    a.thr = thr + p0;
+    a.qnorm = qnorm + p0;
+    a.V = V;
+    a.pb = pb;
+    a.p0 = p0;
+    a.normalize = normalize;
+    a.cand = cand;
+    a.cand_cnt = cand_cnt;
+    a.cap = cap;
+    a.n_kchunks = n_kchunks;
+    query_tc_kernel<<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+    VSM_LAUNCHED();
+  }
+  // ---- 3. exact re-scoring + top-k ----------------------------------------------------------------------------------
+  std::vector<uint32_t> h_cnt(P);
+  VSM_TRY(read_back(m, h_cnt.data(), cand_cnt, (size_t)P * 4, s));
+  uint32_t mx = 0;
+  for (int p = 0; p < P; ++p) mx = std::max(mx, h_cnt[p]);
+  m->tc_last_candidates = mx;
+  if (mx > cap || mx < (uint32_t)k) {
+    // a list overflowed (dense ties) -- or, impossibly, lost candidates: answer with the exact engine
+    m->tc_fallbacks += 1;
+    return query_exact(m, q_dev, P, k, normalize, idx_dev, score_dev, s);
+  }
+  dim3 rgrid((unsigned)std::min<uint32_t>((mx + 7) / 8, 148u * 4u), (unsigned)P);
+  rescore_kernel<<<rgrid, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
+                                       normalize, cand, cand_cnt, cap, P, keys);
+  VSM_LAUNCHED();
+  return query_select_from_keys(m, keys, cand_cnt, P, (int)cap, k, idx_dev, score_dev, s);
+}
+
 }  // namespace vsm

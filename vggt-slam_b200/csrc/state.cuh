@@ -167,6 +167,10 @@ struct vsm_map {
   bool ck_built = false;
   // query scratch
   vsm::DevBuf q_cand, q_tmp, q_norm;
+  vsm::DevBuf q_tc, q_tc_cand;     // tensor-core engine: thresholds / padded prompts; candidate ids + keys
+  bool norms_valid = false;        // q_norm holds ||sum_v|| for the current contents
+  uint32_t tc_last_candidates = 0; // longest candidate list of the last engine-2 query
+  int64_t tc_fallbacks = 0;        // engine-2 queries answered by engine 1 (candidate overflow)
 };
 
 namespace vsm {

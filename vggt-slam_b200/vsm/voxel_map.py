@@ -269,6 +269,11 @@ class DeviceVoxelMap:
                                 _ptr(sc), _stream_ptr(self.device)))
         return idx, sc
 
+    def query_stats(self) -> dict:
+        a, b = C.c_int64(), C.c_int64()
+        N.check(N.lib.vsm_query_stats(self._h, C.byref(a), C.byref(b)))
+        return {"last_candidates": int(a.value), "fallbacks": int(b.value)}
+
     # -- multi-GPU partials ---------------------------------------------------
     def partials_counts(self, world: int) -> np.ndarray:
         cnt = (C.c_int64 * world)()
