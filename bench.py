@@ -33,6 +33,11 @@ for p in (ROOT, os.path.join(ROOT, "vggt-slam_b200"), os.path.join(ROOT, "tests"
 
 import numpy as np  # noqa: E402
 
+# accumulate_kernel DRAM traffic per launch from the committed `ncu --set full` capture of this workload's submap shape
+# (mean of 3 launches: 3.861 GB read + 0.072 GB written against 3.73 GB algorithmic)
+NCU_ACC_TRAFFIC_BYTES = 3.932e9
+NCU_ACC_TRAFFIC_SRC = "profiles/r01_accumulate_ncu_full_summary.txt"
+
 METRIC = "points fused/sec"
 UNIT = "points/s"
 
@@ -325,10 +330,14 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     acc_gbs = prof["accumulate_bytes"] / max(prof["accumulate_ms"], 1e-9) * 1e-6
+    default_shape = (args.frames, args.height, args.width, args.dim, args.emb_dtype, args.voxel_size) == (32, 294, 518, 512, "bf16", 0.05)
     px_total = args.submaps * args.frames * args.height * args.width
     fuse_bytes_step = px_total * 16 + n_fused_step * args.dim * esize + sum(s["n_submap_voxels"] for s in stats) * (4 * args.dim + 16)
     roofline = {"bound": "hbm", "kernel": "vsm::accumulate_kernel", "achieved": acc_gbs, "peak": peak, "unit": "GB/s",
-                "frac": acc_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": acc_gbs / peak, "traffic": NCU_ACC_TRAFFIC_BYTES if default_shape else None,
+                "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), " + NCU_ACC_TRAFFIC_SRC,
+                "algorithmic_bytes_per_launch": prof["accumulate_bytes"] / max(prof["accumulate_launches"], 1),
+                "peak_source": peak_src,
                 "accumulate_ms_per_launch": prof["accumulate_ms"] / max(prof["accumulate_launches"], 1),
                 "accumulate_share_of_step": prof["accumulate_ms"] * (1.0 if world == 1 else 1.0) / max(elapsed_ms, 1e-9),
                 "fuse_calls_GBps": fuse_bytes_step * args.steps / max(prof["fuse_ms"], 1e-9) * 1e-6,
@@ -359,6 +368,21 @@ def main():
     e2e = None
     if not args.no_e2e:
         n_e2e = args.submaps if args.e2e_submaps < 0 else min(args.e2e_submaps, args.submaps)
+        # the e2e arm pins its inputs in host memory (5 GB per submap): never more than 60 % of what the box has free,
+        # shared by the ranks of this node
+        try:
+            import psutil
+
+            per_submap = args.frames * args.height * args.width * (16 + args.dim * esize)
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            budget = 0.6 * psutil.virtual_memory().available / max(local_world, 1)
+            n_e2e = max(1, min(n_e2e, int(budget // per_submap)))
+        except Exception:
+            pass
+        if world > 1:  # every rank must run the same number of collective builds with the same shapes
+            t_n = torch.tensor([n_e2e], dtype=torch.int64, device=dev)
+            dist.all_reduce(t_n, op=dist.ReduceOp.MIN)
+            n_e2e = int(t_n.item())
         gmh = vsm.GraphMap()
         h2d = 0
         for d in datas[:n_e2e]:

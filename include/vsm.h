@@ -110,7 +110,11 @@ VSM_API int64_t vsm_launch_count(void);
 /* ---- map life cycle ---------------------------------------------------- */
 /* replaces: the python containers built at the end of map.py:375-381 / submap.py:306-311 */
 VSM_API int vsm_map_create(const vsm_config* cfg, vsm_map** out);
+/* A destroyed map of up to 8 GB is cleared and parked (at most 4 per process); the next vsm_map_create with the same
+ * device, dim and embedding type takes it over, so that building map after map allocates nothing.
+ * vsm_map_cache_release frees the parked maps of every device. */
 VSM_API int vsm_map_destroy(vsm_map* m);
+VSM_API int vsm_map_cache_release(void);
 VSM_API int vsm_map_clear(vsm_map* m, void* stream);
 VSM_API int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream);
 

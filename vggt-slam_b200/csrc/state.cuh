@@ -127,6 +127,7 @@ struct vsm_map {
   vsm::DevBuf d_n_vox;  // device-side map state: uint32 [0] voxel count, [1] contributor-log entries
   vsm::DevBuf ctr_ring;  // kCallRing x FuseCounters, one slot per queued fuse call
   std::vector<vsm::PendingCall> pending;
+  std::vector<vsm_fuse_stats> stats_backlog;  // stats of queued calls collected internally, handed out by vsm_fuse_collect
   cudaEvent_t ev_ring[vsm::kCallRing][3] = {};
   vsm_fuse_stats last_stats{};
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vsm_launch_count": (_i64, []),
     "vsm_map_create": (C.c_int, [_P(Config), _P(_vp)]),
     "vsm_map_destroy": (C.c_int, [_vp]),
+    "vsm_map_cache_release": (C.c_int, []),
     "vsm_map_clear": (C.c_int, [_vp, _vp]),
     "vsm_map_reserve": (C.c_int, [_vp, _i64, _vp]),
     "vsm_conf_threshold": (C.c_int, [_vp, _i64, _f64, _P(_f32), _vp]),
