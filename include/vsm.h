@@ -233,6 +233,26 @@ VSM_API int vsm_contrib_pack(vsm_map* m, int32_t world, uint64_t* keys_dev, int3
                      int64_t* owner_counts_host, void* stream);
 VSM_API int vsm_contrib_merge(vsm_map* m, const uint64_t* keys_dev, const int32_t* submap_ids_dev, const uint64_t* masks_dev,
                       int64_t n, void* stream);
+
+/* ---- one-sided exchange over NVLink peer memory (csrc/peer.cu) ------------- *
+ * Every rank owns an inbox (vsm_peer_alloc: cudaMalloc + CUDA IPC handle) that its peers map (vsm_peer_open).
+ * vsm_partials_push: ONE pass groups this map's voxels and contributor entries by owner and stores the records
+ * straight into the owners' inboxes (remote slot reservation + 16-byte peer stores), then signals every owner.
+ * inbox_ptrs_host[world]: device pointers of all inboxes as seen from this process (own inbox included).
+ * vsm_partials_drain: waits on the device for `world` signals (bounded by timeout_s), inserts the received records
+ * into this map and resets the inbox half.  Exchanges alternate halves: pass epoch = 0, 1, 2, ... on every rank.
+ * Returns VSM_E_NOMEM if the inbox was too small (n_rows_host / n_contrib_host tell the sizes needed), VSM_E_STATE on
+ * timeout.  flags_host: 1 row overflow, 2 contributor overflow, 4 timeout, 8 hash error. */
+VSM_API int vsm_inbox_bytes(int32_t dim, int64_t cap_rows, int64_t cap_contrib, int64_t* bytes_host);
+VSM_API int vsm_peer_alloc(int32_t device, int64_t bytes, void** ptr_out, void* ipc_handle_out /* 64 bytes or NULL */);
+VSM_API int vsm_peer_open(int32_t device, const void* ipc_handle /* 64 bytes */, void** ptr_out);
+VSM_API int vsm_peer_close(int32_t device, void* ptr);
+VSM_API int vsm_peer_free(int32_t device, void* ptr);
+VSM_API int vsm_partials_push(vsm_map* m, int32_t world, void* const* inbox_ptrs_host, int64_t cap_rows, int64_t cap_contrib,
+                      int64_t epoch, void* stream);
+VSM_API int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib, int64_t epoch,
+                       double timeout_s, int64_t* n_rows_host, int64_t* n_contrib_host, uint32_t* flags_host, void* stream);
+
 /* sorted packed keys of this map's voxels (uint64[V]); pack/unpack helpers for global ranking across owners */
 VSM_API int vsm_export_packed_keys(const vsm_map* m, uint64_t* keys_dev, void* stream);
 

@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 subs = [synth_device.to_submap(synth_device.make_submap_device(1234, i), host=False) for i in range(n)]
 torch.cuda.synchronize()
 hint = 1 << 18
-for rep in range(8):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 8):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     dm = vm.DeviceVoxelMap(0.05, 512, N.BF16, capacity=hint)
     dm.profile_enable(True)

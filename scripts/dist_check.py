@@ -27,7 +27,9 @@ subs = [synth.make_submap(71, i, S=4, H=56, W=84, d=64, mode="sl4", room=(2.4, 1
 gm = vsm.GraphMap()
 for s in subs[rank::world]:
     gm.add_submap(to_submap(vsm, s, device_inputs=True))
-sh, stats = vdist.build_sharded(gm, 0.05)
+transport = sys.argv[1] if len(sys.argv) > 1 else "peer"
+for _ in range(3):  # repeated exchanges alternate the inbox halves
+    sh, stats = vdist.build_sharded(gm, 0.05, transport=transport)
 keys = sh._dm.export_packed_keys().cpu().numpy()
 coords, _, counts, _ = sh._dm.export_geometry()
 feats = sh._dm.features_to_host()
@@ -59,6 +61,10 @@ if rank == 0:
     si, _, ss = single.query_with_embeddings(Q, top_k=7)
     np.testing.assert_array_equal(qi, si)
     np.testing.assert_allclose(qs, ss, rtol=1e-3, atol=1e-6)
-    print(f"dist_check ok: world={world} voxels={V} shards={[len(p[0]) for p in parts]}")
+    print(f"dist_check ok: transport={transport} world={world} voxels={V} shards={[len(p[0]) for p in parts]}")
 dist.barrier()
+if transport == "peer":
+    from vsm import peer
+
+    peer.close_all()
 dist.destroy_process_group()

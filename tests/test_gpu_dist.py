@@ -74,3 +74,86 @@ def test_pack_route_merge_equals_single_map():
         contribs += m.get_contributors().tolist()
     contribs = [contribs[i] for i in order]
     assert contribs == single.get_contributors().tolist()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_push_drain_equals_single_map(world):
+    """The one-sided exchange (csrc/peer.cu) with every 'rank' on this GPU: inboxes are plain device blocks, the
+    maps of all ranks push into them, each owner drains its own.  Two exchanges back to back use both halves."""
+    import torch
+    import vsm
+    from vsm import peer
+    from vsm import voxel_map as vm
+    from vsm.map import wrap_device_map
+
+    dev = torch.device("cuda", 0)
+    subs = [synth.make_submap(67, i, S=4, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
+                              first_frame_number=4 * i) for i in range(6)]
+    single = _local_map(vsm, subs, 0.05).build_semantic_voxel_map(0.05)
+    s_coords, _, s_counts, _ = single._dm.export_geometry()
+    s_keys = single._dm.export_packed_keys().cpu().numpy()
+    cap_rows, cap_contrib = len(s_keys) + 8, 6 * len(s_keys)
+    inboxes = [peer.Inbox(dev, 64, cap_rows, cap_contrib, shared=False) for _ in range(world)]
+    ptrs = [b.ptr for b in inboxes]
+    for epoch in range(3):
+        fused_all, names = [], {}
+        for r in range(world):
+            gm = _local_map(vsm, subs[r::world], 0.05)
+            dm, fused, nm = gm.fuse_into_device_map(0.05)
+            peer.push(dm, ptrs, cap_rows, cap_contrib, epoch)
+            fused_all += fused
+            names.update(nm)
+            dm.close()
+        owners = []
+        n_rows_total = 0
+        for o in range(world):
+            om = vm.DeviceVoxelMap(0.05, 64, 0, capacity=1024)
+            n_rows, n_contrib = peer.drain(om, ptrs[o], world, cap_rows, cap_contrib, epoch, timeout_s=5.0)
+            n_rows_total += n_rows
+            om.finalize()
+            owners.append(om)
+        all_keys = np.concatenate([o.export_packed_keys().cpu().numpy() for o in owners])
+        assert len(np.unique(all_keys)) == len(all_keys) == len(s_keys)
+        assert n_rows_total >= len(s_keys)  # voxels seen by several ranks arrive once per rank
+        order = np.argsort(all_keys.view(np.uint64), kind="stable")
+        np.testing.assert_array_equal(all_keys[order], s_keys)
+        coords = np.concatenate([o.export_geometry()[0].cpu().numpy() for o in owners])[order]
+        counts = np.concatenate([o.export_geometry()[2].cpu().numpy() for o in owners])[order]
+        feats = np.concatenate([o.features_to_host() for o in owners])[order]
+        np.testing.assert_array_equal(coords, s_coords.cpu().numpy())
+        np.testing.assert_array_equal(counts, s_counts.cpu().numpy())
+        np.testing.assert_allclose(feats, single.get_features(), rtol=1e-3, atol=1e-5)
+        contribs = []
+        for o in owners:
+            contribs += wrap_device_map(o, fused_all, names, 0.05).get_contributors().tolist()
+        assert [contribs[i] for i in order] == single.get_contributors().tolist()
+        for o in owners:
+            o.close()
+    for b in inboxes:
+        b.free()
+
+
+def test_peer_inbox_overflow_and_timeout_are_reported():
+    import torch
+    import vsm
+    from vsm import peer
+    from vsm import voxel_map as vm
+
+    dev = torch.device("cuda", 0)
+    subs = [synth.make_submap(71, 0, S=3, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2))]
+    gm = _local_map(vsm, subs, 0.05)
+    dm, _, _ = gm.fuse_into_device_map(0.05)
+    V = dm.num_voxels
+    assert V > 64
+    small = peer.Inbox(dev, 64, 16, 16, shared=False)
+    peer.push(dm, [small.ptr], 16, 16, 0)
+    om = vm.DeviceVoxelMap(0.05, 64, 0, capacity=1024)
+    with pytest.raises(MemoryError, match="inbox too small"):
+        peer.drain(om, small.ptr, 1, 16, 16, 0, timeout_s=5.0)
+    # the half was reset by the drain: nobody pushes now, so waiting for a sender must time out, not hang
+    om.clear()
+    with pytest.raises(RuntimeError, match="timed out"):
+        peer.drain(om, small.ptr, 1, 16, 16, 0, timeout_s=0.05)
+    om.close()
+    dm.close()
+    small.free()

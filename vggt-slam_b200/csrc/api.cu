@@ -93,6 +93,17 @@ Workspace* workspace_for_device(int device) {
   return table[device];
 }
 
+void prefer_max_smem(const void* kernel) {
+  static std::mutex mu;
+  static std::vector<const void*> done;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const void* k : done)
+    if (k == kernel) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  done.push_back(kernel);
+}
+
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
   if (m->pinned_bytes < bytes) {
     if (m->pinned) cudaFreeHost(m->pinned);
@@ -269,6 +280,7 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (m->ws) VSM_TRY(vsm::join_accumulates(m->ws, s));
   VSM_CUDA(cudaStreamSynchronize(s));  // queued fuse calls are dropped with the contents
   VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, m->gcap * 8, s));
   VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, m->gcap * 4, s));

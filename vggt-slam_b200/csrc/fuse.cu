@@ -713,8 +713,11 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
 template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
   const int block = 256;
-  // the sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks
-  int grid = 148 * 6;
+  // The sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks.  Two CTAs
+  // per SM (16 warps x 4 rows of 1 KB in flight) already saturate HBM (measured: same time as 3 or 6 per SM) and
+  // leave 24 K registers and 1536 threads per SM to the NEXT call's preparation kernels, which run concurrently
+  // on the caller's stream (fuse_enqueue).
+  int grid = 148 * 2;
   if (!sorted) {
     const int64_t n_chunks = (a.n + 31) >> 5;
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)148 * 6);
@@ -722,10 +725,13 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
   const bool full = a.nvec == 32 * VPL;
 #define VSM_ACC(SORTED_, CHECK_)                                                      \
   do {                                                                                \
-    if (full)                                                                         \
+    if (full) {                                                                       \
+      VSM_SHARE_SM((accumulate_kernel<BF16, VPL, SORTED_, CHECK_, true>));            \
       accumulate_kernel<BF16, VPL, SORTED_, CHECK_, true><<<grid, block, 0, s>>>(a);  \
-    else                                                                              \
+    } else {                                                                          \
+      VSM_SHARE_SM((accumulate_kernel<BF16, VPL, SORTED_, CHECK_, false>));           \
       accumulate_kernel<BF16, VPL, SORTED_, CHECK_, false><<<grid, block, 0, s>>>(a); \
+    }                                                                                 \
   } while (0)
   if (sorted) {
     if (check)
@@ -932,6 +938,24 @@ static LocalTable table_view(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& l
 
 static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_stats>* out);
 
+static int ensure_acc_stream(Workspace* ws) {
+  if (ws->acc_stream) return VSM_OK;
+  const char* e = getenv("VSM_NO_OVERLAP");
+  ws->overlap = !(e && e[0] == '1');
+  VSM_CUDA(cudaStreamCreateWithFlags(&ws->acc_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_prep_done[b], cudaEventDisableTiming));
+    VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_acc_done[b], cudaEventDisableTiming));
+  }
+  return VSM_OK;
+}
+
+int join_accumulates(Workspace* ws, cudaStream_t s) {
+  for (int b = 0; b < 2; ++b)
+    if (ws->acc_used[b]) VSM_CUDA(cudaStreamWaitEvent(s, ws->ev_acc_done[b], 0));
+  return VSM_OK;
+}
+
 // Queue one fuse call.  Needs the workspace lock.  `host` != null: embeddings are streamed from the host.
 static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cudaStream_t s) {
   Workspace* ws = m->ws;
@@ -976,7 +1000,13 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   VSM_TRY(ws->lv_off.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_cursor.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_gid.ensure((size_t)n_sel_max * 4, s));
-  if (!pixel_order) VSM_TRY(ws->sorted_pix.ensure((size_t)n_sel_max * 8, s));  // packed entries
+  VSM_TRY(ensure_acc_stream(ws));
+  const int ab = ws->acc_parity;  // which sorted list this call fills
+  if (!pixel_order) {
+    // the accumulate kernel that last read this list (two calls ago) must be done before it is replaced or refilled
+    if (ws->acc_used[ab]) VSM_CUDA(cudaStreamWaitEvent(s, ws->ev_acc_done[ab], 0));
+    VSM_TRY(ws->sorted_pix[ab].ensure((size_t)n_sel_max * 8, s));  // packed entries
+  }
 
   LocalTable tb = table_view(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap,
                              &ctr->n_occ_b);
@@ -1104,16 +1134,27 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     scatter_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
                                         ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
                                         ws->lv_gid.as<int32_t>(), check ? 1 : 0,
-                                        ws->sorted_pix.as<unsigned long long>(), point_gid, ctr);
+                                        ws->sorted_pix[ab].as<unsigned long long>(), point_gid, ctr);
     VSM_LAUNCHED();
     table_cleanup_kernel<<<vgrid, 256, 0, s>>>(tb);
     VSM_LAUNCHED();
     aa.emb = emb_dev;
     aa.pix_base = 0;
-    aa.entries = ws->sorted_pix.as<unsigned long long>();
-    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], s));
-    VSM_TRY(launch_accumulate(aa, bf16, true, check, s));
-    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], s));
+    aa.entries = ws->sorted_pix[ab].as<unsigned long long>();
+    // the accumulate kernel goes to the side stream: the caller's stream is free for the next call's preparation
+    cudaStream_t sa = ws->overlap ? ws->acc_stream : s;
+    if (ws->overlap) {
+      VSM_CUDA(cudaEventRecord(ws->ev_prep_done[ab], s));
+      VSM_CUDA(cudaStreamWaitEvent(sa, ws->ev_prep_done[ab], 0));
+    }
+    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], sa));
+    VSM_TRY(launch_accumulate(aa, bf16, true, check, sa));
+    if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], sa));
+    if (ws->overlap) {
+      VSM_CUDA(cudaEventRecord(ws->ev_acc_done[ab], sa));
+      ws->acc_used[ab] = true;
+      ws->acc_parity ^= 1;
+    }
   } else {
     point_gid_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
                                           ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
@@ -1204,12 +1245,18 @@ static int fuse_submit_locked(vsm_map* m, const float* pts, const float* conf, c
 static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_stats>* out) {
   if (m->pending.empty()) return VSM_OK;
   const size_t n_calls = m->pending.size();
+  VSM_TRY(join_accumulates(m->ws, s));
   std::vector<FuseCounters> hc(kCallRing);
   VSM_TRY(read_back(m, hc.data(), m->ctr_ring.p, sizeof(FuseCounters) * n_calls, s));
   std::vector<PendingCall> calls;
   calls.swap(m->pending);
   int first_error = VSM_OK;
   char first_msg[512] = "";
+  // profiling: calls overlap (accumulate of call i runs beside the preparation of call i+1), so the time of the
+  // batch is the span from the first call's start to the last call's end, not a sum over calls
+  cudaEvent_t span_begin = nullptr, span_end = nullptr;
+  bool any_abort = false;
+  for (size_t k = 0; k < n_calls; ++k) any_abort |= hc[k].abort != 0;
   for (size_t k = 0; k < n_calls; ++k) {
     PendingCall& call = calls[k];
     FuseCounters c = hc[k];
@@ -1231,6 +1278,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
       call.slot = 0;
       m->fuses[call.fuse_index].point_gid.release();
       VSM_TRY(fuse_enqueue(m, call, nullptr, s));
+      VSM_TRY(join_accumulates(m->ws, s));
       VSM_TRY(read_back(m, &c, m->ctr_ring.p, sizeof(FuseCounters), s));
     }
     call.precheck_mask.release();
@@ -1263,11 +1311,18 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
       m->ws->hint_n_occ = c.n_occ_b;
       m->fuses[call.fuse_index].n_fused = (int64_t)c.n_fused;
       if (call.profiled && c.n_fused > 0 && !hc[k].abort) {
-        float t_all = 0.f, t_acc = 0.f;
+        float t_acc = 0.f;
         cudaEvent_t* ev = m->ev_ring[call.slot];
-        VSM_CUDA(cudaEventElapsedTime(&t_all, ev[0], ev[2]));
         VSM_CUDA(cudaEventElapsedTime(&t_acc, ev[1], ev[2]));
-        m->prof.fuse_ms += t_all;
+        if (!span_begin) span_begin = ev[0];
+        span_end = ev[2];
+        if (getenv("VSM_TRACE")) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+          cudaEventElapsedTime(&a0, span_begin, ev[0]);
+          cudaEventElapsedTime(&a1, span_begin, ev[1]);
+          cudaEventElapsedTime(&a2, span_begin, ev[2]);
+          fprintf(stderr, "[vsm trace] call %zu: start %.3f  acc %.3f .. %.3f ms\n", k, a0, a1, a2);
+        }
         m->prof.accumulate_ms += t_acc;
         m->prof.fuse_calls += 1;
         m->prof.accumulate_launches += 1;
@@ -1281,6 +1336,11 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     }
     m->last_stats = st;
     if (out) out->push_back(st);
+  }
+  if (span_begin && span_end && !any_abort) {
+    float t_all = 0.f;
+    VSM_CUDA(cudaEventElapsedTime(&t_all, span_begin, span_end));
+    m->prof.fuse_ms += t_all;
   }
   uint32_t state[2] = {0, 0};
   VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));

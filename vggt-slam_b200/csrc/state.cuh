@@ -103,8 +103,17 @@ struct Workspace {
   DevBuf tb_keys, tb_count, tb_lid, tb_list, tb_mask;  // fine table
   uint64_t ta_cap = 0, tb_cap = 0;
   DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
-  DevBuf sorted_pix, sorted_gid;
+  DevBuf sorted_pix[2], sorted_gid;
   int64_t hint_n_occ = 0;  // distinct voxels of the last collected fuse call on this device
+  // The accumulate kernel of a (voxel-sorted, device-resident) fuse call runs on this side stream, so that the
+  // preparation kernels of the NEXT call -- queued on the caller's stream -- overlap it.  The sorted entry lists
+  // are double-buffered; ev_acc_done[b] marks the end of the last accumulate that read sorted_pix[b].
+  cudaStream_t acc_stream = nullptr;
+  cudaEvent_t ev_prep_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_acc_done[2] = {nullptr, nullptr};
+  bool acc_used[2] = {false, false};
+  int acc_parity = 0;
+  bool overlap = true;  // VSM_NO_OVERLAP=1 keeps everything on the caller's stream (profiling, A/B timing)
 };
 Workspace* workspace_for_device(int device);
 }  // namespace vsm
@@ -198,5 +207,6 @@ int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);
 int log_grow(vsm_map* m, int64_t need_entries, cudaStream_t s);
 int fuse_collect_pending(vsm_map* m, cudaStream_t s);  // collect queued fuse calls (no-op if none)
+int join_accumulates(Workspace* ws, cudaStream_t s);    // make s wait for the accumulate kernels queued on the side stream
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
 }  // namespace vsm

@@ -93,6 +93,13 @@ SIGNATURES = {
     "vsm_partials_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "vsm_contrib_pack": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _P(_i64), _vp]),
     "vsm_contrib_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "vsm_inbox_bytes": (C.c_int, [_i32, _i64, _i64, _P(_i64)]),
+    "vsm_peer_alloc": (C.c_int, [_i32, _i64, _P(_vp), _vp]),
+    "vsm_peer_open": (C.c_int, [_i32, _vp, _P(_vp)]),
+    "vsm_peer_close": (C.c_int, [_i32, _vp]),
+    "vsm_peer_free": (C.c_int, [_i32, _vp]),
+    "vsm_partials_push": (C.c_int, [_vp, _i32, _P(_vp), _i64, _i64, _i64, _vp]),
+    "vsm_partials_drain": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _f64, _P(_i64), _P(_i64), _P(C.c_uint32), _vp]),
     "vsm_export_packed_keys": (C.c_int, [_vp, _vp, _vp]),
 }
 

@@ -104,10 +104,23 @@ class ShardedVoxelMap:
         return bi.cpu().numpy(), bs.cpu().numpy()
 
 
+def _sizes_all(values, group, device) -> np.ndarray:
+    """all-gather of a few int64 per rank -> (world, len(values))"""
+    world = dist.get_world_size(group)
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return torch.stack(out).cpu().numpy()
+
+
 def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_closure_frames: bool = True,
                   capacity_hint: Optional[int] = None, host_streaming: Optional[bool] = None, profile: bool = False,
-                  group=None):
-    """Collective multi-GPU build.  Returns (ShardedVoxelMap, this rank's per-submap fuse stats)."""
+                  group=None, transport: str = "peer"):
+    """Collective multi-GPU build.  Returns (ShardedVoxelMap, this rank's per-submap fuse stats).
+
+    transport "peer" (default): voxel partials and contributor entries are pushed straight into the owners' inboxes
+    over NVLink peer memory by one kernel pass (vsm/peer.py, csrc/peer.cu); "collective": pack on the device, one
+    torch.distributed all-to-all per array, merge (works with any backend)."""
     from . import voxel_map as vm
     from .map import wrap_device_map
 
@@ -118,25 +131,43 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
     if dm is None:
         raise RuntimeError("build_sharded: this rank has no submap to fuse")
     dev = dm.device
-    # ---- voxels -> owners ------------------------------------------------------
-    keys, counts, sums, send = dm.partials_pack(world)
-    recv = exchange_counts(send.tolist(), group, dev)
-    r_keys = exchange_rows(keys, send.tolist(), recv, group)
-    r_counts = exchange_rows(counts, send.tolist(), recv, group)
-    r_sums = exchange_rows(sums, send.tolist(), recv, group)
-    ckeys, csubs, cmasks, csend = dm.contrib_pack(world)
-    crecv = exchange_counts(csend.tolist(), group, dev)
-    rc_keys = exchange_rows(ckeys, csend.tolist(), crecv, group)
-    rc_subs = exchange_rows(csubs, csend.tolist(), crecv, group)
-    rc_masks = exchange_rows(cmasks, csend.tolist(), crecv, group)
     d, code = dm.dim, dm.emb_dtype
-    del keys, counts, sums, ckeys, csubs, cmasks
-    dm.close()
-    # ---- owner merge --------------------------------------------------------------
-    owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=max(int(sum(recv)), 1024), device=dev)
-    owner.partials_merge(r_keys, r_counts, r_sums)
-    owner.contrib_merge(rc_keys, rc_subs, rc_masks)
-    del r_keys, r_counts, r_sums
+    if transport == "peer":
+        from . import peer
+
+        # the inboxes must hold what the owners receive: a hash spreads sum(V_r) voxels evenly over the owners;
+        # 25 % + 64 K slots of slack, never more than everything
+        n_log = int(sum(s["n_submap_voxels"] for s in stats))
+        sizes = _sizes_all([dm.num_voxels, n_log], group, dev)
+        tot_v, tot_c = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+        need_rows = min(tot_v, int(1.25 * tot_v / world) + (1 << 16)) + 1
+        need_contrib = min(tot_c, int(1.25 * tot_c / world) + (1 << 16)) + 1
+        ex = peer.exchange_for(dev, d, need_rows, need_contrib, group)
+        ex.push(dm)
+        owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=ex.cap_rows, device=dev)
+        ex.drain(owner)
+        dm.close()
+    elif transport == "collective":
+        # ---- voxels -> owners ------------------------------------------------------
+        keys, counts, sums, send = dm.partials_pack(world)
+        recv = exchange_counts(send.tolist(), group, dev)
+        r_keys = exchange_rows(keys, send.tolist(), recv, group)
+        r_counts = exchange_rows(counts, send.tolist(), recv, group)
+        r_sums = exchange_rows(sums, send.tolist(), recv, group)
+        ckeys, csubs, cmasks, csend = dm.contrib_pack(world)
+        crecv = exchange_counts(csend.tolist(), group, dev)
+        rc_keys = exchange_rows(ckeys, csend.tolist(), crecv, group)
+        rc_subs = exchange_rows(csubs, csend.tolist(), crecv, group)
+        rc_masks = exchange_rows(cmasks, csend.tolist(), crecv, group)
+        del keys, counts, sums, ckeys, csubs, cmasks
+        dm.close()
+        # ---- owner merge --------------------------------------------------------------
+        owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=max(int(sum(recv)), 1024), device=dev)
+        owner.partials_merge(r_keys, r_counts, r_sums)
+        owner.contrib_merge(rc_keys, rc_subs, rc_masks)
+        del r_keys, r_counts, r_sums
+    else:
+        raise ValueError(f"unknown transport {transport!r}")
     owner.finalize()
     # frame ids of every submap, from every rank (contributor lists name frames of remote submaps too)
     mine = {int(f["submap"].get_id()): (list(f["submap"].frame_ids), dict(f["submap"].frame_id_to_name or {}))
