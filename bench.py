@@ -61,75 +61,98 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--query", action="store_true", help="also report query latency on the built map")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the two secondary measurements (text-query latency at 10 M voxels, per-frame streaming latency)")
+    ap.add_argument("--query-voxels", type=float, default=10e6)
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------
+_CLOCK_CHILD = r"""
+import sys, time
+import pynvml as nv
+bus, period = sys.argv[1], float(sys.argv[2])
+nv.nvmlInit()
+h = None
+for i in range(nv.nvmlDeviceGetCount()):
+    hi = nv.nvmlDeviceGetHandleByIndex(i)
+    b = nv.nvmlDeviceGetPciInfo(hi).busId
+    b = b.decode() if isinstance(b, bytes) else b
+    if bus == "" or b.lower().endswith(bus.lower()):
+        h = hi
+        break
+if h is None:
+    h = nv.nvmlDeviceGetHandleByIndex(0)
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+    except Exception:
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    print("s", time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), r, flush=True)
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py):
-    polling `nvidia-smi -lms` from a subprocess takes driver locks often enough to stall kernel launches."""
+    """SM clock and throttle reasons sampled DURING the timed region through NVML, from a CHILD process, so that the
+    thread that queues ~300 kernel launches per step never shares the interpreter lock with a poller."""
+
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index: int, period_s: float = 0.01):
-        self.index = index
-        self.period = period_s
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
-        self.err = None
-        self._stop = threading.Event()
-        self.thread = None
+        self.index, self.period = index, period_s
+        self.proc, self.err, self.max_mhz = None, None, None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Spawns the child and waits until it is sampling (call before the barrier that opens the timed region)."""
         try:
-            import pynvml
-
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            # CUDA_VISIBLE_DEVICES may remap ordinals: resolve through the PCI bus id of the torch device
             import torch
 
-            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
-                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            if bus is not None:
-                for i in range(pynvml.nvmlDeviceGetCount()):
-                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
-                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
-                        self.h = h
-                        break
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._run, daemon=True)
-            self.thread.start()
+            props = torch.cuda.get_device_properties(self.index)
+            bus = ""
+            if hasattr(props, "pci_bus_id"):
+                bus = f"{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0"
+            self.proc = subprocess.Popen([sys.executable, "-c", _CLOCK_CHILD, bus, str(self.period)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()
+            if len(first) == 2 and first[0] == "max":
+                self.max_mhz = float(first[1])
+            else:
+                self.err = f"clock child said {first!r}"
         except Exception as e:  # no NVML: report it rather than fail the benchmark
             self.err = repr(e)
 
-    def _run(self):
-        nv = self.nv
-        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception as e:
-                self.err = repr(e)
-                break
-            self._stop.wait(self.period)
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
-        self._stop.set()
-        if self.thread is not None:
-            self.thread.join(timeout=2)
-        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(self.samples), "source": "NVML, sampled during the timed region"}
+        samples, reasons = [], set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                for line in out.splitlines():
+                    f = line.split()
+                    if len(f) == 4 and f[0] == "s":
+                        t = float(f[1])
+                        if self.t0 is not None and (t < self.t0 or (self.t1 is not None and t > self.t1)):
+                            continue
+                        samples.append(float(f[2]))
+                        for name, bit in self.BITS.items():
+                            if int(f[3]) & bit:
+                                reasons.add(name)
+            except Exception as e:
+                self.err = repr(e)
+        out = {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(reasons), "samples": len(samples),
+               "source": "NVML polled by a child process; samples inside the timed region only"}
         if self.err:
             out["error"] = self.err
         return out
@@ -222,6 +245,96 @@ def workload_config(args, world):
 
 
 # ---------------------------------------------------------------------------
+# secondary measurements
+# ---------------------------------------------------------------------------
+def query_latency(args, dev):
+    """BASELINE configs[3]: V voxels x P prompts, top-10, whole vsm_query call (tensor-core engine + exact
+    re-scoring), CUDA events, 5 calls after 2 warm-ups.  The V x 512 fp32 sums (20 GB at 10 M) are far larger than L2."""
+    import torch
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    V, d, k = int(args.query_voxels), args.dim, 10
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    feats = torch.empty((V, d), dtype=torch.float32, device=dev)
+    for r0 in range(0, V, 1 << 20):
+        r1 = min(V, r0 + (1 << 20))
+        x = torch.randn((r1 - r0, d), dtype=torch.float32, device=dev, generator=g)
+        feats[r0:r1] = x / x.norm(dim=1, keepdim=True) * (0.3 + 0.7 * torch.rand((r1 - r0, 1), device=dev, generator=g))
+    centers = torch.rand((V, 3), dtype=torch.float32, device=dev, generator=g) * 1000.0
+    dm = vm.DeviceVoxelMap(0.05, d, N.F32, capacity=V)
+    dm.load_dense(centers, feats)
+    del feats, centers
+    torch.cuda.empty_cache()
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"voxels": V, "dim": d, "top_k": k, "bytes_per_call": V * d * 4, "points": []}
+    rng = np.random.default_rng(0)
+    for P in (1, 64, 256):
+        q = rng.normal(size=(P, d)).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        qt = torch.from_numpy(q).to(dev)
+        for _ in range(2):
+            dm.query(qt, top_k=k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dm.query(qt, top_k=k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        gbs = V * d * 4 / ms * 1e-6
+        out["points"].append({"prompts": P, "ms": ms, "hbm_GBps": gbs, "hbm_frac": gbs / hbm,
+                              "TFLOPs_tf32": 2.0 * V * d * P / ms * 1e-9})
+    dm.close()
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    return out
+
+
+def frame_stream_latency(args, dev):
+    """BASELINE configs[4]: Sim(3) mode, one 518x518 frame at a time (what 1600x1600 MetaCam images become after VGGT's
+    preprocessing) fused into a growing map with the submap's frame offset; latency per frame of the synchronous
+    vsm_fuse_submap call (device-resident frame), median and max over 64 frames."""
+    import torch
+    from vsm import _native as N
+    from vsm import synth_device
+    from vsm import voxel_map as vm
+
+    S, H, W = 64, 518, 518
+    d = synth_device.make_submap_device(4321, 0, S=S, H=H, W=W, d=args.dim, mode="sim3", room=(6.0, 4.0, 3.0),
+                                        emb_dtype=torch.bfloat16)
+    thr = vm.conf_threshold(d.conf, 25.0)
+    dm = vm.DeviceVoxelMap(args.voxel_size, args.dim, N.BF16, capacity=1 << 19)
+    times = []
+    for rep in range(2):  # the first sweep warms the pool and the map
+        dm.clear()
+        times = []
+        for f in range(S):
+            p = dm.make_params(1, H, W, 1, 1, thr, d.H_world_map, 0, 0, frame_base=f)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            dm.fuse(d.points[f:f + 1], d.conf[f:f + 1], d.emb[f:f + 1], p)
+            times.append(1e3 * (time.perf_counter() - t0))
+    px = H * W
+    kept = float((d.conf >= float(thr)).float().mean().item())
+    out = {"frame": f"{W}x{H}", "frames": S, "mode": "sim3", "ms_per_frame_median": float(np.median(times)),
+           "ms_per_frame_max": float(np.max(times)), "points_per_frame": int(px * kept),
+           "Mpoints_per_s": px * kept / (np.median(times) * 1e-3) * 1e-6, "voxels": dm.num_voxels}
+    dm.close()
+    del d
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
 def main():
@@ -278,33 +391,48 @@ def main():
         cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.05) + 1024)
         return m, stats
 
+    # the clock poller (a child process) starts before the warm-up, so that its NVML client set-up is long over
+    sampler = ClockSampler(local_rank, period_s=float(os.environ.get("VSM_BENCH_CLOCK_PERIOD", "0.01")))
+    if rank == 0 and os.environ.get("VSM_BENCH_NO_CLOCKS") != "1":
+        sampler.start()
     # the first builds also warm the memory pool and the shared workspace: never fewer than 6 untimed builds
     n_warm = max(args.warmup, 6)
+    # Warm up exactly like the timed loop runs: the finished map of step i stays alive while step i+1 builds, so two
+    # maps alternate (libvsm parks a destroyed map and hands it to the next vsm_map_create).  A warm-up that dropped
+    # its map at once would leave the second of the two to be created -- allocated, grown -- inside the timed region.
+    m = None
     for _ in range(n_warm):
         m, stats = step()
-        del m
     n_fused_step = sum(s["n_fused"] for s in stats)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    import gc
+
+    gc.collect()
     barrier()
+    counters0 = {k: N.get_counter(k) for k in ("select_misses", "capacity_retries", "early_collects")}
+    sampler.mark_begin()
     launches0 = N.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = {"fuse_ms": 0.0, "accumulate_ms": 0.0, "accumulate_launches": 0, "accumulate_bytes": 0, "points_fused": 0}
     ev0.record()
     points = 0
     last = None
+    step_events = [ev0]
     for _ in range(args.steps):
         last = None
         m, stats = step()
+        step_events.append(torch.cuda.Event(enable_timing=True))
+        step_events[-1].record()
         points += sum(s["n_fused"] for s in stats)
         for k in prof:
             prof[k] += gm.last_profile[k]
         last = m
     ev1.record()
     barrier()
+    sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
+    counters = {k: N.get_counter(k) - v for k, v in counters0.items()}
+    step_ms = [step_events[i].elapsed_time(step_events[i + 1]) for i in range(len(step_events) - 1)]
     launches = N.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
@@ -432,6 +560,18 @@ def main():
                "api": "GraphMap.build_semantic_voxel_map on pinned host arrays -> vsm_fuse_submap_host; "
                       "get_features()/get_centers_world() read the map back"}
 
+    # ---- secondary measurements (BASELINE configs[3] and configs[4]), rank 0's GPU only, outside the timed step ----
+    secondary = None
+    if rank == 0 and not args.no_extras:
+        try:
+            N.lib.vsm_map_cache_release()
+            torch.cuda.empty_cache()
+            secondary = {"text_query": query_latency(args, dev), "frame_stream": frame_stream_latency(args, dev)}
+        except Exception as e:  # secondary numbers must never cost the headline line
+            secondary = {"error": repr(e)}
+    if world > 1:
+        dist.barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args)
@@ -445,7 +585,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 accumulate of " + args.emb_dtype + " embeddings; f64 transform",
                 "data": "synthetic (device-generated box-room pointmaps, 1+Gamma(2,2) confidence, N(0,1) embeddings)",
                 "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks}
+                "clocks": clocks, "step_ms": [round(x, 3) for x in step_ms], "retries_in_timed_region": counters, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -8,6 +8,7 @@ from vsm import synth_device, voxel_map as vm, _native as N
 from vsm.map import wrap_device_map
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+N.set_option('select_mode', int(os.environ.get('SELECT_MODE', '0')))
 subs = [synth_device.to_submap(synth_device.make_submap_device(1234, i), host=False) for i in range(n)]
 torch.cuda.synchronize()
 hint = 1 << 18

@@ -67,6 +67,42 @@ def test_config_shapes_against_torch(mode, S, H, W):
     torch.testing.assert_close(dm2.export_features(), feats, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["radix_select", "bracket_select"])
+def test_filter_bounds_at_config_size(mode):
+    """The bbox filter's 0.5 / 99.5 percentiles (map.py:257-258) at config-1 size against np.percentile on the same
+    world points, bit-exact, for both select implementations; the one-pass bracket select must answer without
+    falling back; both give the same map."""
+    import torch
+    from vsm import _native as N
+    from vsm import synth_device
+    from vsm import voxel_map as vm
+
+    S, H, W = 32, 294, 518
+    d = synth_device.make_submap_device(79, 0, S=S, H=H, W=W, d=64, mode="sl4", room=(6.0, 4.0, 3.0))
+    thr = vm.conf_threshold(d.conf, 25.0)
+    pw = vm.transform_points(d.points.reshape(-1, 3), d.H_world_map, out_f64=False).cpu().numpy()
+    keep = (d.conf.reshape(-1) >= float(thr)).cpu().numpy() & np.isfinite(pw).all(axis=1)
+    want_lo = np.percentile(pw[keep], 0.5, axis=0)
+    want_hi = np.percentile(pw[keep], 99.5, axis=0)
+    assert want_lo.dtype == np.float32
+    N.set_option("select_mode", mode)
+    try:
+        misses0 = N.get_counter("select_misses")
+        dm = vm.DeviceVoxelMap(0.05, 64, N.BF16, capacity=1 << 17)
+        st = dm.fuse(d.points, d.conf, d.emb, dm.make_params(S, H, W, S, 1, thr, d.H_world_map, 0, N.FUSE_FILTERS))
+        assert N.get_counter("select_misses") == misses0
+    finally:
+        N.set_option("select_mode", 0)
+    np.testing.assert_array_equal(np.asarray(st["bbox_lo"], np.float32), want_lo)
+    np.testing.assert_array_equal(np.asarray(st["bbox_hi"], np.float32), want_hi)
+    inside = keep & (pw >= want_lo).all(axis=1) & (pw <= want_hi).all(axis=1)
+    assert st["n_finite"] == int(keep.sum()) and st["n_bbox"] == int(inside.sum())
+    dm.finalize()
+    _, _, cnt, _ = dm.export_geometry()
+    assert int(cnt.sum()) == st["n_fused"] <= st["n_bbox"]
+    dm.close()
+
+
 def test_frame_by_frame_equals_whole_submap():
     """Config-5 style per-frame streaming fusion: S=1 calls with frame_base == one call over the submap
     (filters off: they are per call), including the contributor frame masks."""

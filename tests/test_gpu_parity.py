@@ -192,6 +192,17 @@ def test_fuse_submap_oracle(vsm_mod, seed, S, H, W, d, mode, kind):
 # ---------------------------------------------------------------------------
 # a7: global build with the three filters
 # ---------------------------------------------------------------------------
+@pytest.fixture(params=[1, 2], ids=["radix_select", "bracket_select"])
+def select_mode(request):
+    """Both implementations of the bbox percentiles (three-pass radix select / one-pass bracket select with its
+    retry path) must give the reference's bounds."""
+    from vsm import _native as N
+
+    N.set_option("select_mode", request.param)
+    yield request.param
+    N.set_option("select_mode", 0)
+
+
 def graph_from(vsm, subs, **kw):
     gm = vsm.GraphMap()
     for s in subs:
@@ -205,7 +216,7 @@ def graph_from(vsm, subs, **kw):
     ("s1_nodedup", dict(stride=1, deduplicate_contributors=False)),
 ])
 @pytest.mark.parametrize("streaming", [False, True])
-def test_build_global_golden(vsm_mod, tag, kw, streaming):
+def test_build_global_golden(vsm_mod, tag, kw, streaming, select_mode):
     z = gio.load("case_c_global_sl4.npz")
     gm = graph_from(vsm_mod, gio.inputs(z))
     m = gm.build_semantic_voxel_map(0.05, host_streaming=streaming, **kw)
@@ -216,7 +227,7 @@ def test_build_global_golden(vsm_mod, tag, kw, streaming):
     np.testing.assert_array_equal(m._voxel_coords, z[f"{tag}_recon_coords"])
 
 
-def test_build_global_filter_stages(vsm_mod):
+def test_build_global_filter_stages(vsm_mod, select_mode):
     """Survivor counts and the percentile box of every filter stage against the oracle."""
     z = gio.load("case_c_global_sl4.npz")
     subs = gio.inputs(z)
@@ -254,7 +265,7 @@ def test_build_global_errors_and_empty(vsm_mod):
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("stride", [1, 3])
-def test_build_global_oracle(vsm_mod, dtype, stride):
+def test_build_global_oracle(vsm_mod, dtype, stride, select_mode):
     """Four overlapping submaps, SL(4), d=64, clean embeddings (single optimistic pass), device inputs."""
     subs = [synth.make_submap(31, i, S=5, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
                               first_frame_number=5 * i, n_loop_frames=(1 if i == 2 else 0)) for i in range(4)]

@@ -93,17 +93,6 @@ Workspace* workspace_for_device(int device) {
   return table[device];
 }
 
-void prefer_max_smem(const void* kernel) {
-  static std::mutex mu;
-  static std::vector<const void*> done;
-  std::lock_guard<std::mutex> lock(mu);
-  for (const void* k : done)
-    if (k == kernel) return;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  cudaGetLastError();
-  done.push_back(kernel);
-}
-
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
   if (m->pinned_bytes < bytes) {
     if (m->pinned) cudaFreeHost(m->pinned);

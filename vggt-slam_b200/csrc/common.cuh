@@ -44,12 +44,6 @@ extern int64_t g_launches;  // kernels launched by this library (vsm_launch_coun
     }                                                                                      \
   } while (0)
 
-// Ask for the largest shared-memory carve-out for `kernel` (once per kernel).  An SM changes its L1/shared split only
-// when it is idle, so kernels that are meant to share SMs -- the accumulate kernel of one fuse call and the
-// preparation kernels of the next -- must agree on it, whether they use shared memory or not.
-void prefer_max_smem(const void* kernel);
-#define VSM_SHARE_SM(kernel) ::vsm::prefer_max_smem(reinterpret_cast<const void*>(kernel))
-
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
   int64_t g = cdiv(n, block);

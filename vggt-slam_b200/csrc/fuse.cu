@@ -22,9 +22,17 @@
 //   scatter           counting sort of the points by local voxel -> packed (voxel id, pixel) entries
 //   accumulate        warps walk 32-entry chunks of the sorted list, sum embedding rows in fp32 registers
 //                     (FHADD.BF16) and flush with vector REDs at voxel boundaries
+#include <atomic>
+
 #include "hash.cuh"
 
 namespace vsm {
+
+constexpr uint32_t kFuseForceRadix = 1u << 30;  // internal flag: this call must use the three-pass radix select
+std::atomic<int> g_select_mode{0};              // 0 auto, 1 radix, 2 bracket (vsm_set_option "select_mode")
+std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
+std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
+std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
 
 constexpr uint32_t PF_SEL = 1u;     // conf >= thr, on the stride grid, frame < end_idx
 constexpr uint32_t PF_FINITE = 2u;  // world point (and embedding row, if a mask was given) finite
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has
     const bool fits = ((unsigned long long)map_state[0] + ctr->n_new <= vcap) &&
                       ((unsigned long long)log_n + n_occ <= log_cap) &&
                       (ctr->n_finite <= (unsigned long long)entry_cap || ctr->n_fused <= (unsigned long long)entry_cap);
-    if (!fits || ctr->range_err || ctr->internal_err) {
+    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss) {
       ctr->abort = 1u;
     } else {
       ctr->log_base = log_n;  // calls on one stream run one after the other: plain read-modify-write
@@ -714,9 +722,7 @@ template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
   const int block = 256;
   // The sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks.  Two CTAs
-  // per SM (16 warps x 4 rows of 1 KB in flight) already saturate HBM (measured: same time as 3 or 6 per SM) and
-  // leave 24 K registers and 1536 threads per SM to the NEXT call's preparation kernels, which run concurrently
-  // on the caller's stream (fuse_enqueue).
+  // per SM (16 warps x 4 rows of 1 KB in flight) already saturate HBM (measured: same time as 3 or 6 per SM).
   int grid = 148 * 2;
   if (!sorted) {
     const int64_t n_chunks = (a.n + 31) >> 5;
@@ -725,13 +731,10 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
   const bool full = a.nvec == 32 * VPL;
 #define VSM_ACC(SORTED_, CHECK_)                                                      \
   do {                                                                                \
-    if (full) {                                                                       \
-      VSM_SHARE_SM((accumulate_kernel<BF16, VPL, SORTED_, CHECK_, true>));            \
+    if (full)                                                                         \
       accumulate_kernel<BF16, VPL, SORTED_, CHECK_, true><<<grid, block, 0, s>>>(a);  \
-    } else {                                                                          \
-      VSM_SHARE_SM((accumulate_kernel<BF16, VPL, SORTED_, CHECK_, false>));           \
+    else                                                                              \
       accumulate_kernel<BF16, VPL, SORTED_, CHECK_, false><<<grid, block, 0, s>>>(a); \
-    }                                                                                 \
   } while (0)
   if (sorted) {
     if (check)
@@ -940,8 +943,8 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
 
 static int ensure_acc_stream(Workspace* ws) {
   if (ws->acc_stream) return VSM_OK;
-  const char* e = getenv("VSM_NO_OVERLAP");
-  ws->overlap = !(e && e[0] == '1');
+  const char* e = getenv("VSM_OVERLAP");
+  ws->overlap = e && e[0] == '1';
   VSM_CUDA(cudaStreamCreateWithFlags(&ws->acc_stream, cudaStreamNonBlocking));
   for (int b = 0; b < 2; ++b) {
     VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_prep_done[b], cudaEventDisableTiming));
@@ -1029,14 +1032,19 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   }
   const bool check = filters && emb_ok == nullptr;  // optimistic non-finite detection on the embeddings
 
-  // ---- world points (+ pass 0 of the select) ---------------------------------------------------------
+  // ---- world points (+ pass 0 of the radix select) ------------------------------------------------------
+  // The bbox percentiles come from the one-pass bracket select for submap-sized inputs, from the three-pass radix
+  // select for small ones and whenever the bracket select could not answer (the call is then repeated).
+  const int sel_mode = g_select_mode.load();
+  const bool bracket = filters && !(p->flags & kFuseForceRadix) && sel_mode != 1 && (sel_mode == 2 || n_px >= (1 << 17));
   SelectState* sst = nullptr;
   uint32_t* hist = nullptr;
   float* sel_out = nullptr;
-  if (filters) {
+  if (filters && !bracket) {
     VSM_TRY(select_scratch(&sst, &hist, &sel_out));
     VSM_TRY(select_reset(sst, hist, s));
   }
+  if (bracket) VSM_TRY(ws->sel_bracket.ensure(bracket_scratch_bytes(n_px), s));
   HMat Hm;
   for (int i = 0; i < 16; ++i) Hm.m[i] = p->H_world_map[i];
   WorldArgs wa;
@@ -1052,13 +1060,14 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   wa.hist0 = hist;
   const bool vec4 = aligned16(pts) && aligned16(conf) && n_px >= 4;
   const int wgrid = grid_for(vec4 ? cdiv(n_px, 4) : n_px, 256);
+  const bool hist0 = filters && !bracket;
   if (vec4) {
-    if (filters)
+    if (hist0)
       world_points_kernel<true, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
     else
       world_points_kernel<true, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
   } else {
-    if (filters)
+    if (hist0)
       world_points_kernel<false, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
     else
       world_points_kernel<false, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
@@ -1084,7 +1093,10 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     src.n_items = n_px;
     const float q0 = (float)p->bbox_lo_pct / 100.0f;  // numpy: q / float32(100) in float32
     const float q1 = (float)p->bbox_hi_pct / 100.0f;
-    VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
+    if (bracket)
+      VSM_TRY(run_percentiles_bracket(ws->sel_bracket.p, src, q0, q1, ctr->bounds, &ctr->n_finite, &ctr->sel_miss, s));
+    else
+      VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
     fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
     bbox_coarse_kernel<<<grid, 256, 0, s>>>(fa, ta, ctr);
     VSM_LAUNCHED();
@@ -1201,7 +1213,10 @@ static int pregrow(vsm_map* m, cudaStream_t s) {
   if (m->pending.empty() && m->n_vox + per_call > m->vcap) VSM_TRY(map_grow(m, m->n_vox + 2 * per_call, s));
   const int64_t in_flight = (int64_t)m->pending.size() + 1;
   if (m->log_n + in_flight * 2 * per_call > m->log_cap) {
-    if (!m->pending.empty()) VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
+    if (!m->pending.empty()) {
+      ++g_early_collects;
+      VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
+    }
     VSM_TRY(log_grow(m, m->log_n + 32 * 2 * per_call, s));
   }
   return VSM_OK;
@@ -1209,7 +1224,10 @@ static int pregrow(vsm_map* m, cudaStream_t s) {
 
 static int fuse_submit_locked(vsm_map* m, const float* pts, const float* conf, const uint8_t* emb, const uint8_t* emb_ok,
                               const HostEmb* host, const vsm_fuse_params* p, cudaStream_t s) {
-  if ((int)m->pending.size() >= kCallRing) VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
+  if ((int)m->pending.size() >= kCallRing) {
+    ++g_early_collects;
+    VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
+  }
   VSM_TRY(pregrow(m, s));
   FuseRecord rec{};
   rec.submap_id = p->submap_id;
@@ -1273,8 +1291,15 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
       VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
       m->n_vox = state[0];
       m->log_n = state[1];
-      VSM_TRY(map_grow(m, m->n_vox + (int64_t)c.n_new, s));
-      VSM_TRY(log_grow(m, m->log_n + (int64_t)c.n_occ_b, s));
+      if (c.sel_miss) {
+        // the one-pass percentile select could not answer (its counts are meaningless): radix select this time
+        call.p.flags |= kFuseForceRadix;
+        ++g_select_misses;
+      } else {
+        ++g_capacity_retries;
+        VSM_TRY(map_grow(m, m->n_vox + (int64_t)c.n_new, s));
+        VSM_TRY(log_grow(m, m->log_n + (int64_t)c.n_occ_b, s));
+      }
       call.slot = 0;
       m->fuses[call.fuse_index].point_gid.release();
       VSM_TRY(fuse_enqueue(m, call, nullptr, s));
@@ -1308,7 +1333,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     }
     if (status == VSM_OK || status == VSM_E_NONFINITE_EMB) {
       m->last_n_occ = c.n_occ_b;
-      m->ws->hint_n_occ = c.n_occ_b;
+      m->ws->hint_n_occ = std::max<int64_t>(m->ws->hint_n_occ, c.n_occ_b);  // largest call seen on this device
       m->fuses[call.fuse_index].n_fused = (int64_t)c.n_fused;
       if (call.profiled && c.n_fused > 0 && !hc[k].abort) {
         float t_acc = 0.f;
@@ -1316,7 +1341,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
         VSM_CUDA(cudaEventElapsedTime(&t_acc, ev[1], ev[2]));
         if (!span_begin) span_begin = ev[0];
         span_end = ev[2];
-        if (getenv("VSM_TRACE")) {
+        if (getenv("VSM_TRACE") && getenv("VSM_TRACE")[0] == '1') {
           float a0 = 0.f, a1 = 0.f, a2 = 0.f;
           cudaEventElapsedTime(&a0, span_begin, ev[0]);
           cudaEventElapsedTime(&a1, span_begin, ev[1]);
@@ -1462,6 +1487,12 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
     if (c.abort && !c.internal_err && !c.range_err) {
       m->fuses.back().point_gid.release();
       m->fuses.pop_back();
+      if (c.sel_miss) {
+        q.flags |= kFuseForceRadix;
+        ++g_select_misses;
+        --attempt;  // not a capacity retry
+        continue;
+      }
       uint32_t state[2] = {0, 0};
       VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
       VSM_TRY(map_grow(m, (int64_t)state[0] + (int64_t)c.n_new, s));
@@ -1520,4 +1551,52 @@ extern "C" int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, c
                                                        p->W, p->stride, p->conf_threshold, out_mask_dev);
   VSM_LAUNCHED();
   return VSM_OK;
+}
+
+extern "C" int vsm_set_option(const char* key, int64_t value) {
+  if (!key) {
+    set_error("vsm_set_option: null key");
+    return VSM_E_INVALID;
+  }
+  if (!strcmp(key, "select_mode") && value >= 0 && value <= 2) {
+    g_select_mode = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "overlap") && (value == 0 || value == 1)) {
+    int dev = 0;
+    VSM_CUDA(cudaGetDevice(&dev));
+    Workspace* ws = workspace_for_device(dev);
+    if (!ws) {
+      set_error("vsm_set_option: no workspace for device %d", dev);
+      return VSM_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(ws->mu);
+    VSM_TRY(ensure_acc_stream(ws));
+    VSM_CUDA(cudaDeviceSynchronize());
+    ws->overlap = value != 0;
+    return VSM_OK;
+  }
+  set_error("vsm_set_option: unknown key or bad value: %s = %lld", key, (long long)value);
+  return VSM_E_INVALID;
+}
+
+extern "C" int vsm_get_counter(const char* key, int64_t* out_host) {
+  if (!key || !out_host) {
+    set_error("vsm_get_counter: null argument");
+    return VSM_E_INVALID;
+  }
+  if (!strcmp(key, "select_misses")) {
+    *out_host = g_select_misses.load();
+    return VSM_OK;
+  }
+  if (!strcmp(key, "capacity_retries")) {
+    *out_host = g_capacity_retries.load();
+    return VSM_OK;
+  }
+  if (!strcmp(key, "early_collects")) {
+    *out_host = g_early_collects.load();
+    return VSM_OK;
+  }
+  set_error("vsm_get_counter: unknown key %s", key);
+  return VSM_E_INVALID;
 }

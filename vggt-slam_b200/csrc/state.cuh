@@ -43,7 +43,8 @@ struct LocalTable {
 struct FuseCounters {
   unsigned long long n_conf, n_finite, n_bbox, n_fused, n_bad_emb;
   uint32_t n_occ_a, n_occ_b;
-  uint32_t n_new, pad0;  // this call's distinct voxels that are new to the map
+  uint32_t n_new;     // this call's distinct voxels that are new to the map
+  uint32_t sel_miss;  // the one-pass percentile select could not answer: repeat the call with the radix select
   uint32_t range_err, internal_err;
   uint32_t abort;      // set on the device when the call must stop before touching the global map
   uint32_t seg_total;  // running allocation of sorted-list positions
@@ -104,7 +105,8 @@ struct Workspace {
   uint64_t ta_cap = 0, tb_cap = 0;
   DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
   DevBuf sorted_pix[2], sorted_gid;
-  int64_t hint_n_occ = 0;  // distinct voxels of the last collected fuse call on this device
+  DevBuf sel_bracket;  // scratch of the one-pass percentile select
+  int64_t hint_n_occ = 0;  // most distinct voxels any collected fuse call on this device had (growth heuristic)
   // The accumulate kernel of a (voxel-sorted, device-resident) fuse call runs on this side stream, so that the
   // preparation kernels of the NEXT call -- queued on the caller's stream -- overlap it.  The sorted entry lists
   // are double-buffered; ev_acc_done[b] marks the end of the last accumulate that read sorted_pix[b].
@@ -113,7 +115,9 @@ struct Workspace {
   cudaEvent_t ev_acc_done[2] = {nullptr, nullptr};
   bool acc_used[2] = {false, false};
   int acc_parity = 0;
-  bool overlap = true;  // VSM_NO_OVERLAP=1 keeps everything on the caller's stream (profiling, A/B timing)
+  // Off by default: measured on B200, the HBM-saturating accumulate kernel and the latency-bound preparation
+  // kernels slow each other down by as much as the overlap hides.  VSM_OVERLAP=1 / vsm_set_option.
+  bool overlap = false;
 };
 Workspace* workspace_for_device(int device);
 }  // namespace vsm
@@ -202,6 +206,11 @@ int run_percentiles(SelectState* st, uint32_t* hist, const SelSrc& src, int npct
 int select_reset(SelectState* st, uint32_t* hist, cudaStream_t s);
 int run_percentiles_after_hist0(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1,
                                 float* out_dev, const unsigned long long* n_dev, cudaStream_t s);
+// the same percentiles with ONE pass over the data (sample -> bracket -> collect -> exact select); sets *miss_dev when
+// the result is not valid (the caller then repeats with the radix passes).  World-point layout only.
+size_t bracket_scratch_bytes(int64_t n_items);
+int run_percentiles_bracket(void* scratch, const SelSrc& src, float q0, float q1, float* out_dev,
+                            const unsigned long long* n_dev, uint32_t* miss_dev, cudaStream_t s);
 // process-wide scratch per device: select state, histograms, 16 result floats
 int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);

@@ -63,6 +63,8 @@ SIGNATURES = {
     "vsm_abi_version": (C.c_int, []),
     "vsm_last_error": (C.c_char_p, []),
     "vsm_launch_count": (_i64, []),
+    "vsm_set_option": (C.c_int, [C.c_char_p, _i64]),
+    "vsm_get_counter": (C.c_int, [C.c_char_p, _P(_i64)]),
     "vsm_map_create": (C.c_int, [_P(Config), _P(_vp)]),
     "vsm_map_destroy": (C.c_int, [_vp]),
     "vsm_map_cache_release": (C.c_int, []),
@@ -127,6 +129,16 @@ def check(status: int) -> None:
     ValueError for bad arguments and RuntimeError for missing state: submap.py:236-243, map.py:185-188)."""
     if status != OK:
         raise _EXC.get(status, RuntimeError)(f"libvsm[{status}]: {last_error()}")
+
+
+def set_option(key: str, value: int) -> None:
+    check(lib.vsm_set_option(key.encode(), int(value)))
+
+
+def get_counter(key: str) -> int:
+    out = C.c_int64(0)
+    check(lib.vsm_get_counter(key.encode(), C.byref(out)))
+    return int(out.value)
 
 
 def launch_count() -> int:

@@ -104,6 +104,41 @@ class ShardedVoxelMap:
         return bi.cpu().numpy(), bs.cpu().numpy()
 
 
+class _Phases:
+    """Wall-clock phases of build_sharded when VSM_DIST_TRACE=1 (synchronises the device at every mark)."""
+
+    def __init__(self, device):
+        import os
+        import time
+
+        self.on = os.environ.get("VSM_DIST_TRACE") == "1"
+        self.device, self.time, self.marks = device, time, []
+        self.mark("start")
+
+    def mark(self, name):
+        if self.on:
+            torch.cuda.synchronize(self.device)
+            self.marks.append((name, self.time.perf_counter()))
+
+    def report(self):
+        if self.on and dist.get_rank() == 0:
+            t = self.marks
+            print("[vsm dist] " + "  ".join(f"{t[i][0]} {1e3 * (t[i][1] - t[i - 1][1]):.2f}" for i in range(1, len(t))),
+                  flush=True)
+
+
+_NAMES_CACHE: dict = {}
+
+
+def _names_signature(fused) -> int:
+    """62-bit signature of this rank's (submap id, frame ids, frame names); stable within the process."""
+    items = []
+    for f in fused:
+        sm = f["submap"]
+        items.append((int(sm.get_id()), tuple(map(str, sm.frame_ids)), tuple(sorted((sm.frame_id_to_name or {}).items()))))
+    return hash(tuple(sorted(items))) & ((1 << 62) - 1)
+
+
 def _sizes_all(values, group, device) -> np.ndarray:
     """all-gather of a few int64 per rank -> (world, len(values))"""
     world = dist.get_world_size(group)
@@ -125,6 +160,7 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
     from .map import wrap_device_map
 
     world = dist.get_world_size(group)
+    ph = _Phases(torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None)
     dm, fused, names = graph_map.fuse_into_device_map(voxel_size, stride, ignore_loop_closure_frames, True,
                                                       capacity_hint, host_streaming, profile)
     stats = graph_map.last_build_stats
@@ -132,21 +168,28 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         raise RuntimeError("build_sharded: this rank has no submap to fuse")
     dev = dm.device
     d, code = dm.dim, dm.emb_dtype
+    names_sigs = None
+    ph.mark("fuse")
     if transport == "peer":
         from . import peer
 
         # the inboxes must hold what the owners receive: a hash spreads sum(V_r) voxels evenly over the owners;
         # 25 % + 64 K slots of slack, never more than everything
         n_log = int(sum(s["n_submap_voxels"] for s in stats))
-        sizes = _sizes_all([dm.num_voxels, n_log], group, dev)
+        sizes = _sizes_all([dm.num_voxels, n_log, _names_signature(fused)], group, dev)
+        names_sigs = sizes[:, 2]
         tot_v, tot_c = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
         need_rows = min(tot_v, int(1.25 * tot_v / world) + (1 << 16)) + 1
         need_contrib = min(tot_c, int(1.25 * tot_c / world) + (1 << 16)) + 1
+        ph.mark("sizes")
         ex = peer.exchange_for(dev, d, need_rows, need_contrib, group)
         ex.push(dm)
+        ph.mark("push")
         owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=ex.cap_rows, device=dev)
         ex.drain(owner)
+        ph.mark("drain")
         dm.close()
+        ph.mark("close")
     elif transport == "collective":
         # ---- voxels -> owners ------------------------------------------------------
         keys, counts, sums, send = dm.partials_pack(world)
@@ -169,11 +212,25 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
     else:
         raise ValueError(f"unknown transport {transport!r}")
     owner.finalize()
+    ph.mark("finalize")
     # frame ids of every submap, from every rank (contributor lists name frames of remote submaps too)
     mine = {int(f["submap"].get_id()): (list(f["submap"].frame_ids), dict(f["submap"].frame_id_to_name or {}))
             for f in fused}
-    everyone = [None] * world
-    dist.all_gather_object(everyone, mine, group=group)
+    # The pickled all-gather costs ~1 ms: skip it while no rank's frame ids have changed since the last build.  Every
+    # rank sees the same vector of per-rank signatures (all-gathered with the sizes), so all ranks decide alike.
+    my_sig = _names_signature(fused)
+    if names_sigs is None:
+        names_sigs = tuple(int(x) for x in _sizes_all([my_sig], group, dev)[:, 0])
+    else:
+        names_sigs = tuple(int(x) for x in names_sigs)
+    cache_key = (id(group) if group is not None else 0, dev.index)
+    cached = _NAMES_CACHE.get(cache_key)
+    if cached is not None and cached[0] == names_sigs and cached[1] == my_sig:
+        everyone = cached[2]
+    else:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        _NAMES_CACHE[cache_key] = (names_sigs, my_sig, everyone)
     frame_ids, all_names = {}, {}
     for part in everyone:
         for sid, (ids, nm) in part.items():
@@ -188,6 +245,10 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
             return self._sid
 
     fused_all = [{"submap": _SubmapStub(sid, ids)} for sid, ids in frame_ids.items()]
+    ph.mark("names")
     local = wrap_device_map(owner, fused_all, all_names, voxel_size, True, False) if owner.num_voxels else None
+    ph.mark("wrap")
     gidx, n_global = global_ranks(owner.export_packed_keys(), group)
+    ph.mark("ranks")
+    ph.report()
     return ShardedVoxelMap(local, owner, gidx, n_global, group), stats
