@@ -107,8 +107,8 @@ VSM_API const char* vsm_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 VSM_API int64_t vsm_launch_count(void);
 
-/* process-wide options: "select_mode" 0 auto / 1 three-pass radix select / 2 one-pass bracket select for the bbox
- * percentiles (identical results; tests force each); "overlap" 0/1 runs the accumulate kernel on a side stream beside the
+/* process-wide options: "select_mode" 0 default (= 1) / 1 three-pass radix select / 2 bracket select (sampled brackets,
+ * collect fused into the world-point kernel) for the bbox percentiles (identical results; tests force each); "overlap" 0/1 runs the accumulate kernel on a side stream beside the
  * next call's preparation kernels (current device).  Counters: "select_misses" = fuse calls repeated with the radix
  * select because the bracket select could not answer; "capacity_retries" = calls repeated after the map or the
  * contributor log had to grow; "early_collects" = times a submit had to collect the queued calls itself. */

@@ -22,14 +22,16 @@
 //   scatter           counting sort of the points by local voxel -> packed (voxel id, pixel) entries
 //   accumulate        warps walk 32-entry chunks of the sorted list, sum embedding rows in fp32 registers
 //                     (FHADD.BF16) and flush with vector REDs at voxel boundaries
+#include <algorithm>
 #include <atomic>
 
+#include "bracket.cuh"
 #include "hash.cuh"
 
 namespace vsm {
 
 constexpr uint32_t kFuseForceRadix = 1u << 30;  // internal flag: this call must use the three-pass radix select
-std::atomic<int> g_select_mode{0};              // 0 auto, 1 radix, 2 bracket (vsm_set_option "select_mode")
+std::atomic<int> g_select_mode{0};              // 0 default (= 1), 1 radix, 2 bracket (vsm_set_option "select_mode")
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
 std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
@@ -80,10 +82,69 @@ __device__ __forceinline__ void hist0_add(uint32_t* sh, const float4& p, bool va
   }
 }
 
-// VEC4: 4 pixels per thread -- three 128-bit loads of xyz, one of conf, four 128-bit stores
-template <bool VEC4, bool HIST>
-__global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr) {
+// One CTA per axis: transform a hashed sample of the RAW points, sort the valid ones, publish the brackets that the
+// world-point kernel collects into (bracket.cuh).
+__global__ void __launch_bounds__(1024) bracket_sample_kernel(WorldArgs a, HMat Hm, BracketState* bs, float q0, float q1) {
+  __shared__ float sv[kBrSample];
+  __shared__ uint32_t s_n;
+  const int c = blockIdx.x;
+  if (threadIdx.x == 0) s_n = 0u;
+  __syncthreads();
+  const uint32_t m = a.n_px < (uint32_t)kBrSample ? a.n_px : (uint32_t)kBrSample;
+  const uint32_t step = m > 0 ? a.n_px / m : 1u;
+  for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
+    const uint32_t pix = j * step + hash32(j * 3u + 0x9E3779B9u) % step;
+    uint32_t f;
+    const float4 w = world_one(a, Hm, pix, a.pts[3 * (size_t)pix], a.pts[3 * (size_t)pix + 1], a.pts[3 * (size_t)pix + 2],
+                               a.conf[pix], f);
+    if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) sv[atomicAdd(&s_n, 1u)] = c == 0 ? w.x : (c == 1 ? w.y : w.z);
+  }
+  __syncthreads();
+  const uint32_t mv = s_n;
+  for (uint32_t j = mv + threadIdx.x; j < (uint32_t)kBrSample; j += blockDim.x) sv[j] = __int_as_float(0x7F800000);  // +inf pads
+  __syncthreads();
+  // bitonic sort, one compare-exchange per thread and step
+  for (uint32_t k = 2; k <= (uint32_t)kBrSample; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (uint32_t)kBrSample / 2; t += blockDim.x) {
+        const uint32_t i = 2 * t - (t & (j - 1));  // index with bit j clear
+        const uint32_t l = i + j;
+        const bool up = (i & k) == 0;
+        const float x = sv[i], y = sv[l];
+        if ((x > y) == up) {
+          sv[i] = y;
+          sv[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < 2) {
+    const int t = c * 2 + threadIdx.x;
+    const float q = threadIdx.x == 0 ? q0 : q1;
+    float lo = -__int_as_float(0x7F800000), hi = __int_as_float(0x7F800000);
+    if (mv < 64u) {
+      atomicOr(&bs->miss, 1u);  // too few valid samples to bracket anything
+    } else {
+      const float r = q * (float)(mv - 1);
+      const float w = 6.0f * sqrtf(fmaxf((float)mv * q * (1.0f - q), 1.0f)) + 2.0f;
+      const float ra = floorf(r - w), rb = ceilf(r + w);
+      if (ra >= 1.0f) lo = sv[(uint32_t)ra];
+      if (rb <= (float)(mv - 2)) hi = sv[(uint32_t)rb];
+    }
+    bs->lo[t] = lo;
+    bs->hi[t] = hi;
+  }
+}
+
+// VEC4: 4 pixels per thread -- three 128-bit loads of xyz, one of conf, four 128-bit stores.
+// MODE 1: + pass 0 of the radix select (histogram of the top 11 bits); MODE 2: + the bracket select's collect step.
+template <bool VEC4, int MODE>
+__global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr, BracketArgs br) {
+  constexpr bool HIST = MODE == 1;
   __shared__ uint32_t sh[HIST ? 3 * 2048 : 1];
+  BracketLocal bl;
+  if (MODE == 2) bracket_load(bl, br.bs);
   if (HIST) {
     for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
@@ -133,8 +194,10 @@ __global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm,
       n_sel += (f[j] & PF_SEL) ? 1u : 0u;
       n_fin += (f[j] & PF_FINITE) ? 1u : 0u;
       if (HIST) hist0_add(sh, o[j], (f[j] & PF_FINITE) != 0u);
+      if (MODE == 2) bracket_collect(bl, br, o[j].x, o[j].y, o[j].z, (f[j] & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE));
     }
   }
+  if (MODE == 2) bracket_flush(bl, br);
   for (int o = 16; o > 0; o >>= 1) {
     n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
     n_fin += __shfl_xor_sync(0xffffffffu, n_fin, o);
@@ -1033,10 +1096,12 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   const bool check = filters && emb_ok == nullptr;  // optimistic non-finite detection on the embeddings
 
   // ---- world points (+ pass 0 of the radix select) ------------------------------------------------------
-  // The bbox percentiles come from the one-pass bracket select for submap-sized inputs, from the three-pass radix
-  // select for small ones and whenever the bracket select could not answer (the call is then repeated).
+  // The bbox percentiles come from the three-pass radix select (select.cu).  The bracket select (bracket.cuh: sample,
+  // collect inside the world-point kernel, exact resolve; repeated with the radix select when it cannot answer) gives
+  // the same bounds and is kept as an option: on B200 it measured 6 % SLOWER per fuse call (its collect step more
+  // than doubles the instruction-bound world-point kernel), see DESIGN.md 5.
   const int sel_mode = g_select_mode.load();
-  const bool bracket = filters && !(p->flags & kFuseForceRadix) && sel_mode != 1 && (sel_mode == 2 || n_px >= (1 << 17));
+  const bool bracket = filters && !(p->flags & kFuseForceRadix) && sel_mode == 2;
   SelectState* sst = nullptr;
   uint32_t* hist = nullptr;
   float* sel_out = nullptr;
@@ -1060,18 +1125,32 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   wa.hist0 = hist;
   const bool vec4 = aligned16(pts) && aligned16(conf) && n_px >= 4;
   const int wgrid = grid_for(vec4 ? cdiv(n_px, 4) : n_px, 256);
-  const bool hist0 = filters && !bracket;
-  if (vec4) {
-    if (hist0)
-      world_points_kernel<true, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
-    else
-      world_points_kernel<true, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
-  } else {
-    if (hist0)
-      world_points_kernel<false, true><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
-    else
-      world_points_kernel<false, false><<<wgrid, 256, 0, s>>>(wa, Hm, ctr);
+  const float q0 = (float)p->bbox_lo_pct / 100.0f;  // numpy: q / float32(100) in float32
+  const float q1 = (float)p->bbox_hi_pct / 100.0f;
+  BracketArgs br{};
+  if (bracket) {
+    br.bs = reinterpret_cast<BracketState*>(ws->sel_bracket.p);
+    br.lists = reinterpret_cast<float*>(reinterpret_cast<char*>(ws->sel_bracket.p) + 256);
+    br.cap = bracket_list_cap(n_px);
+    VSM_CUDA(cudaMemsetAsync(br.bs, 0, sizeof(BracketState), s));
+    bracket_sample_kernel<<<3, 1024, 0, s>>>(wa, Hm, br.bs, q0, q1);
+    VSM_LAUNCHED();
   }
+  const int wmode = !filters ? 0 : (bracket ? 2 : 1);
+#define VSM_WORLD(VEC4_)                                                            \
+  do {                                                                              \
+    if (wmode == 0)                                                                 \
+      world_points_kernel<VEC4_, 0><<<wgrid, 256, 0, s>>>(wa, Hm, ctr, br);         \
+    else if (wmode == 1)                                                            \
+      world_points_kernel<VEC4_, 1><<<wgrid, 256, 0, s>>>(wa, Hm, ctr, br);         \
+    else                                                                            \
+      world_points_kernel<VEC4_, 2><<<wgrid, 256, 0, s>>>(wa, Hm, ctr, br);         \
+  } while (0)
+  if (vec4)
+    VSM_WORLD(true);
+  else
+    VSM_WORLD(false);
+#undef VSM_WORLD
   VSM_LAUNCHED();
 
   // ---- filters and the two submap-local tables -----------------------------------------------------------
@@ -1091,12 +1170,13 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     src.flag_off = 3;
     src.flag_need = PF_SEL | PF_FINITE;
     src.n_items = n_px;
-    const float q0 = (float)p->bbox_lo_pct / 100.0f;  // numpy: q / float32(100) in float32
-    const float q1 = (float)p->bbox_hi_pct / 100.0f;
-    if (bracket)
-      VSM_TRY(run_percentiles_bracket(ws->sel_bracket.p, src, q0, q1, ctr->bounds, &ctr->n_finite, &ctr->sel_miss, s));
-    else
+    if (bracket) {
+      bracket_resolve_kernel<<<kBrLists, 1024, 0, s>>>(br.bs, br.lists, br.cap, &ctr->n_finite, q0, q1, ctr->bounds,
+                                                       &ctr->sel_miss);
+      VSM_LAUNCHED();
+    } else {
       VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
+    }
     fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
     bbox_coarse_kernel<<<grid, 256, 0, s>>>(fa, ta, ctr);
     VSM_LAUNCHED();

@@ -206,11 +206,6 @@ int run_percentiles(SelectState* st, uint32_t* hist, const SelSrc& src, int npct
 int select_reset(SelectState* st, uint32_t* hist, cudaStream_t s);
 int run_percentiles_after_hist0(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1,
                                 float* out_dev, const unsigned long long* n_dev, cudaStream_t s);
-// the same percentiles with ONE pass over the data (sample -> bracket -> collect -> exact select); sets *miss_dev when
-// the result is not valid (the caller then repeats with the radix passes).  World-point layout only.
-size_t bracket_scratch_bytes(int64_t n_items);
-int run_percentiles_bracket(void* scratch, const SelSrc& src, float q0, float q1, float* out_dev,
-                            const unsigned long long* n_dev, uint32_t* miss_dev, cudaStream_t s);
 // process-wide scratch per device: select state, histograms, 16 result floats
 int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);
