@@ -21,7 +21,8 @@ def _random_map(V, d, seed, device="cuda"):
     return dm, feats
 
 
-@pytest.mark.parametrize("V,d,P,k", [(70000, 512, 16, 10), (300001, 512, 64, 5), (200000, 64, 100, 20), (131072, 256, 9, 1)])
+@pytest.mark.parametrize("V,d,P,k", [(70000, 512, 16, 10), (300001, 512, 64, 5), (200000, 64, 100, 20), (131072, 256, 9, 1),
+                                     (150001, 512, 256, 10), (100000, 256, 200, 3), (90000, 512, 128, 4)])
 @pytest.mark.parametrize("normalize", [False, True])
 def test_engine2_equals_engine1(V, d, P, k, normalize):
     import torch

@@ -1,10 +1,13 @@
 // query_tc.cu -- tensor-core engine of vsm_query (engine 2): the (voxels x 512) x (512 x prompts) contraction on
 // Blackwell's 5th-generation tensor cores, hand-written for sm_100a:
 //   * TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages 128-voxel x 32-channel fp32 tiles of the voxel sums into
-//     shared memory through a 4-stage mbarrier pipeline; the prompt block (<= 64 prompts x d) is loaded once per
-//     CTA and stays resident;
-//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=64, K=8 per instruction) with the fp32
-//     accumulators in tensor memory (two 64-column accumulators: the epilogue of tile t overlaps the MMAs of t+1);
+//     shared memory through a 4-stage mbarrier pipeline.  Up to 64 prompts per pass: the prompt block (64 x d) is
+//     loaded once per CTA and stays resident.  128 or 256 prompts per pass: the matching 32-channel slice of the
+//     prompt block (16 / 32 KB, L2-resident) travels with every voxel stage, so that 256 prompts cost ONE pass over
+//     the voxels instead of four;
+//   * one elected thread issues tcgen05.mma.kind::tf32 (M=128, N=64/128/256, K=8 per instruction) with the fp32
+//     accumulators in tensor memory (two N-column accumulators -- all 512 columns at N=256: the epilogue of tile t
+//     overlaps the MMAs of t+1);
 //   * four epilogue warps read the accumulators back with tcgen05.ld, scale by 1/count (or the cosine
 //     normaliser) and compare with a per-prompt threshold; survivors are appended to per-prompt candidate lists.
 // TF32 drops mantissa bits, so the tensor-core scores only SELECT candidates, conservatively:
@@ -31,13 +34,19 @@ int query_select_from_keys(vsm_map* m, const unsigned long long* keys, const uin
 namespace tc {
 
 constexpr int kTileM = 128;      // voxels per tile (MMA M)
-constexpr int kTileN = 64;       // prompts per pass (MMA N)
+constexpr int kMaxTileN = 256;   // prompts per pass (MMA N): 64 (resident prompt block), 128 or 256 (streamed)
 constexpr int kChunkK = 32;      // fp32 channels per pipeline stage: 128 bytes = one swizzle row
-constexpr int kStages = 4;
 constexpr int kThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 epilogue
 constexpr uint32_t kABytes = kTileM * kChunkK * 4;  // 16 KB per stage
-constexpr uint32_t kBChunkBytes = kTileN * kChunkK * 4;  // 8 KB per K chunk of the prompt block
-constexpr int kTmemCols = 128;   // 2 accumulators x 64 columns
+
+template <int TN>
+struct Cfg {
+  static constexpr bool kStream = TN > 64;                      // prompt slices travel with the voxel stages
+  static constexpr uint32_t kBChunkBytes = TN * kChunkK * 4;    // one 32-channel slice of the prompt block
+  static constexpr uint32_t kStageBytes = kABytes + (kStream ? kBChunkBytes : 0u);
+  static constexpr int kStages = kStream ? (TN == 128 ? 6 : 4) : 4;
+  static constexpr int kTmemCols = 2 * TN;                      // two accumulators
+};
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,9 +139,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
-__host__ __device__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=tile_n, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int tile_n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
 }
 
 struct TcArgs {
@@ -140,8 +149,9 @@ struct TcArgs {
   const float* vnorm;    // ||sum_v||_2 per voxel id
   const float* thr;      // per prompt of this pass: sample threshold T_p (already in the scored units)
   const float* qnorm;    // per prompt of this pass: ||q_p||_2
-  uint32_t V;
-  int pb;                // prompts in this pass (<= kTileN)
+  uint32_t n_rows;       // voxel rows scored by this launch: ids 0, row_stride, 2*row_stride, ...
+  uint32_t row_stride;
+  int pb;                // prompts in this pass (<= TN)
   int p0;                // first prompt of the pass
   int normalize;
   uint32_t* cand;        // [P][cap] voxel ids
@@ -150,27 +160,31 @@ struct TcArgs {
   int n_kchunks;         // d / 32
 };
 
+template <int TN>
 __global__ void __launch_bounds__(kThreads, 1)
 query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  using C = Cfg<TN>;
+  constexpr int kStages = C::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];
-  // layout: [B: n_kchunks x 8 KB][A: kStages x 16 KB][barriers]
+  // layout, resident prompts: [B: n_kchunks x 8 KB][A: kStages x 16 KB][barriers]
+  //         streamed prompts: [kStages x (A 16 KB | B slice)][barriers]
   uint8_t* smem_b = smem;
-  uint8_t* smem_a = smem + (size_t)a.n_kchunks * kBChunkBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * kABytes);
+  uint8_t* smem_a = C::kStream ? smem : smem + (size_t)a.n_kchunks * C::kBChunkBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * C::kStageBytes);
   uint64_t* full = bars;                   // [kStages] TMA -> MMA
   uint64_t* empty = bars + kStages;        // [kStages] MMA -> TMA
   uint64_t* tfull = bars + 2 * kStages;    // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;            // [2] epilogue -> MMA
   uint64_t* bfull = tempty + 2;            // [1] prompt block resident
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bfull + 1);
-  __shared__ float s_thr[kTileN], s_qn[kTileN];
+  __shared__ float s_thr[TN], s_qn[TN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_tiles = (a.V + kTileM - 1) / kTileM;
+  const uint32_t n_tiles = (a.n_rows + kTileM - 1) / kTileM;
 
-  if (threadIdx.x < kTileN) {
-    s_thr[threadIdx.x] = threadIdx.x < a.pb ? a.thr[threadIdx.x] : __int_as_float(0x7f800000);
-    s_qn[threadIdx.x] = threadIdx.x < a.pb ? a.qnorm[threadIdx.x] : 0.f;
+  for (int i = threadIdx.x; i < TN; i += kThreads) {
+    s_thr[i] = i < a.pb ? a.thr[i] : __int_as_float(0x7f800000);
+    s_qn[i] = i < a.pb ? a.qnorm[i] : 0.f;
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -186,7 +200,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     mbar_init(bfull, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, kTmemCols);
+  if (warp == 2) tmem_alloc(tmem_base_smem, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -194,14 +208,19 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer =====
-    mbar_expect_tx(bfull, (uint32_t)a.n_kchunks * kBChunkBytes);
-    for (int kc = 0; kc < a.n_kchunks; ++kc) tma_load_2d(smem_b + (size_t)kc * kBChunkBytes, &map_b, bfull, kc * kChunkK, 0);
+    if (!C::kStream) {
+      mbar_expect_tx(bfull, (uint32_t)a.n_kchunks * C::kBChunkBytes);
+      for (int kc = 0; kc < a.n_kchunks; ++kc)
+        tma_load_2d(smem_b + (size_t)kc * C::kBChunkBytes, &map_b, bfull, kc * kChunkK, 0);
+    }
     uint32_t stage = 0, phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < a.n_kchunks; ++kc) {
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], kABytes);
-        tma_load_2d(smem_a + (size_t)stage * kABytes, &map_a, &full[stage], kc * kChunkK, (int)(tile * kTileM));
+        mbar_expect_tx(&full[stage], C::kStageBytes);
+        uint8_t* st = smem_a + (size_t)stage * C::kStageBytes;
+        tma_load_2d(st, &map_a, &full[stage], kc * kChunkK, (int)(tile * kTileM));
+        if (C::kStream) tma_load_2d(st + kABytes, &map_b, &full[stage], kc * kChunkK, 0);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -210,18 +229,19 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc();
-    mbar_wait(bfull, 0);
+    constexpr uint32_t idesc = make_idesc(TN);
+    if (!C::kStream) mbar_wait(bfull, 0);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * kTileN;
+      const uint32_t tmem_d = tmem_base + acc * TN;
       for (int kc = 0; kc < a.n_kchunks; ++kc) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + (size_t)stage * kABytes));
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + (size_t)kc * kBChunkBytes));
+        uint8_t* st = smem_a + (size_t)stage * C::kStageBytes;
+        const uint64_t adesc = make_smem_desc(smem_u32(st));
+        const uint64_t bdesc = make_smem_desc(smem_u32(C::kStream ? st + kABytes : smem_b + (size_t)kc * C::kBChunkBytes));
 #pragma unroll
         for (int k = 0; k < kChunkK / 8; ++k)  // K = 8 tf32 (32 bytes) per instruction: advance 32 bytes inside the atom
           mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
@@ -242,9 +262,10 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int ew = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const uint32_t id = tile * kTileM + ew * 32 + lane;
+      const uint32_t row = tile * kTileM + ew * 32 + lane;
+      const uint32_t id = row * a.row_stride;
       float inv = 0.f, fn = 0.f;
-      const bool valid = id < a.V;
+      const bool valid = row < a.n_rows;
       if (valid) {
         const float cnt = (float)a.vcount[id];
         const float nrm = a.vnorm[id];
@@ -252,28 +273,32 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = 1.0f;  // scored quantity is f/||f||: unit norm
       }
+      const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      uint32_t r[kTileN];
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kTileN;
-      tmem_ld32(taddr, r);
-      tmem_ld32(taddr + 32, r + 32);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (valid) {
-        const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        if (c0 >= a.pb) break;  // columns beyond the pass's prompts are padding
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll 8
-        for (int p = 0; p < kTileN; ++p) {
-          const float sc = __uint_as_float(r[p]) * inv;
-          // !(x < t) also keeps NaN scores (they rank first in torch.topk)
-          if (p < a.pb && !(sc + margin * s_qn[p] < s_thr[p])) {
-            const uint32_t pos = atomicAdd(&a.cand_cnt[a.p0 + p], 1u);
-            if (pos < a.cap) a.cand[(size_t)(a.p0 + p) * a.cap + pos] = id;
+          for (int j = 0; j < 32; ++j) {
+            const int p = c0 + j;
+            const float sc = __uint_as_float(r[j]) * inv;
+            // !(x < t) also keeps NaN scores (they rank first in torch.topk)
+            if (p < a.pb && !(sc + margin * s_qn[p] < s_thr[p])) {
+              const uint32_t pos = atomicAdd(&a.cand_cnt[a.p0 + p], 1u);
+              if (pos < a.cap) a.cand[(size_t)(a.p0 + p) * a.cap + pos] = id;
+            }
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -282,7 +307,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
 // ---- helpers ---------------------------------------------------------------------------------------------------
@@ -319,9 +344,9 @@ __global__ void prompt_prep_kernel(const float* __restrict__ q, int P, int d, co
   thr[p] = t;
 }
 
-// zero-padded copy of the prompts of one pass: [kTileN][d]
-__global__ void pad_prompts_kernel(const float* __restrict__ q, int p0, int pb, int d, float* __restrict__ out) {
-  const int total = kTileN * d;
+// zero-padded copy of the prompts of one pass: [tile_n][d]
+__global__ void pad_prompts_kernel(const float* __restrict__ q, int p0, int pb, int d, int tile_n, float* __restrict__ out) {
+  const int total = tile_n * d;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int p = i / d;
     out[i] = p < pb ? q[(size_t)(p0 + p) * d + (i % d)] : 0.f;
@@ -368,7 +393,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// rows x cols fp32 matrix whose rows start row_stride_elems floats apart (a strided sample of the voxel rows when
+// row_stride_elems > cols)
+static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint64_t row_stride_elems = 0) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -381,7 +409,7 @@ static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint6
     fn = (EncodeTiledFn)p;
   }
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 4};
+  const cuuint64_t strides[1] = {(row_stride_elems ? row_stride_elems : cols) * 4};
   const cuuint32_t box[2] = {(cuuint32_t)kChunkK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -396,6 +424,80 @@ static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint6
 
 }  // namespace tc
 
+namespace tc {
+
+struct Scratch {
+  float *qnorm, *thr, *qpad, *ssc;
+  int64_t* sidx;
+  uint32_t *cand_cnt, *cand;
+  unsigned long long* keys;
+  uint32_t cap;
+};
+
+// One level: tensor-core pass over the voxel rows 0, stride, 2*stride, ... (n_rows of them) with the thresholds in
+// sc.thr, exact re-scoring of the candidates, top-k.  *fell_back is set (and nothing written) when a candidate list
+// overflowed or came up short.
+static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize, uint32_t stride, uint32_t n_rows,
+                    const Scratch& sc, int tile_n, size_t smem, int64_t* idx_dev, float* score_dev, bool* fell_back,
+                    cudaStream_t s) {
+  const int d = m->d;
+  const int n_kchunks = d / kChunkK;
+  *fell_back = false;
+  VSM_CUDA(cudaMemsetAsync(sc.cand_cnt, 0, (size_t)P * 4, s));
+  CUtensorMap map_a, map_b;
+  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, kTileM, (uint64_t)stride * d));
+  VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)tile_n));
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const uint32_t n_tiles = (n_rows + kTileM - 1) / kTileM;
+  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
+  for (int p0 = 0; p0 < P; p0 += tile_n) {
+    const int pb = std::min(tile_n, P - p0);
+    pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, sc.qpad);
+    VSM_LAUNCHED();
+    TcArgs a;
+    a.vcount = m->vcount.as<uint32_t>();
+    a.vnorm = m->q_norm.as<float>();
+    a.thr = sc.thr + p0;
+    a.qnorm = sc.qnorm + p0;
+    a.n_rows = n_rows;
+    a.row_stride = stride;
+    a.pb = pb;
+    a.p0 = p0;
+    a.normalize = normalize;
+    a.cand = sc.cand;
+    a.cand_cnt = sc.cand_cnt;
+    a.cap = sc.cap;
+    a.n_kchunks = n_kchunks;
+    if (tile_n == 64)
+      query_tc_kernel<64><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+    else if (tile_n == 128)
+      query_tc_kernel<128><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+    else
+      query_tc_kernel<256><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+    VSM_LAUNCHED();
+  }
+  std::vector<uint32_t> h_cnt(P);
+  VSM_TRY(read_back(m, h_cnt.data(), sc.cand_cnt, (size_t)P * 4, s));
+  uint32_t mx = 0, mn = 0xFFFFFFFFu;
+  for (int p = 0; p < P; ++p) {
+    mx = std::max(mx, h_cnt[p]);
+    mn = std::min(mn, h_cnt[p]);
+  }
+  m->tc_last_candidates = mx;
+  if (mx > sc.cap || mn < (uint32_t)k) {
+    *fell_back = true;  // a list overflowed (dense ties) -- or, impossibly, lost candidates
+    return VSM_OK;
+  }
+  dim3 rgrid((unsigned)std::min<uint32_t>((mx + 7) / 8, 148u * 4u), (unsigned)P);
+  rescore_kernel<<<rgrid, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
+                                       normalize, sc.cand, sc.cand_cnt, sc.cap, P, sc.keys);
+  VSM_LAUNCHED();
+  return query_select_from_keys(m, sc.keys, sc.cand_cnt, P, (int)sc.cap, k, idx_dev, score_dev, s);
+}
+
+}  // namespace tc
+
 int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_t* idx_dev, float* score_dev,
              cudaStream_t s) {
   using namespace tc;
@@ -406,90 +508,80 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
     return VSM_E_INVALID;
   }
   const int n_kchunks = d / kChunkK;
-  const size_t smem = (size_t)n_kchunks * kBChunkBytes + (size_t)kStages * kABytes + 256;
+  // prompts per pass: 64 with the prompt block resident in shared memory, 128 / 256 with its slices streamed
+  const int tile_n = P <= 64 ? 64 : (P <= 128 ? 128 : 256);
+  const size_t smem = tile_n == 64    ? (size_t)n_kchunks * Cfg<64>::kBChunkBytes + (size_t)Cfg<64>::kStages * Cfg<64>::kStageBytes + 256
+                      : tile_n == 128 ? (size_t)Cfg<128>::kStages * Cfg<128>::kStageBytes + 256
+                                      : (size_t)Cfg<256>::kStages * Cfg<256>::kStageBytes + 256;
   if (smem > 227 * 1024) {
     set_error("vsm_query engine 2: d=%d needs %zu bytes of shared memory", d, smem);
     return VSM_E_INVALID;
   }
+  if (tile_n == 64)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (tile_n == 128)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // ---- scratch: norms (cached per finalisation), thresholds, candidates ------------------------------------
-  const uint32_t cap = 1u << 16;
+  Scratch sc;
+  sc.cap = 1u << 16;
   VSM_TRY(m->q_norm.ensure((size_t)std::max<uint32_t>(V, 1) * 4, s));
   if (!m->norms_valid) {
     row_norm_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), V, d, m->q_norm.as<float>());
     VSM_LAUNCHED();
     m->norms_valid = true;
   }
-  // layout of q_tc: [qnorm P][thr P][padded prompts kTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P]
+  // layout of q_tc: [qnorm P][thr P][padded prompts kMaxTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P]
   const size_t off_qn = 0, off_thr = off_qn + (size_t)P * 4, off_pad = (off_thr + (size_t)P * 4 + 255) & ~(size_t)255;
-  const size_t off_sidx = (off_pad + (size_t)kTileN * d * 4 + 255) & ~(size_t)255;
+  const size_t off_sidx = (off_pad + (size_t)kMaxTileN * d * 4 + 255) & ~(size_t)255;
   const size_t off_ssc = off_sidx + (size_t)P * k * 8, off_cnt = (off_ssc + (size_t)P * k * 4 + 255) & ~(size_t)255;
   const size_t small_bytes = off_cnt + (size_t)P * 4;
   VSM_TRY(m->q_tc.ensure(small_bytes, s));
-  VSM_TRY(m->q_tc_cand.ensure((size_t)P * cap * 12, s));  // ids (u32) + keys (u64)
+  VSM_TRY(m->q_tc_cand.ensure((size_t)P * sc.cap * 12, s));  // ids (u32) + keys (u64)
   uint8_t* base = m->q_tc.as<uint8_t>();
-  float* qnorm = (float*)(base + off_qn);
-  float* thr = (float*)(base + off_thr);
-  float* qpad = (float*)(base + off_pad);
-  int64_t* sidx = (int64_t*)(base + off_sidx);
-  float* ssc = (float*)(base + off_ssc);
-  uint32_t* cand_cnt = (uint32_t*)(base + off_cnt);
-  uint32_t* cand = m->q_tc_cand.as<uint32_t>();
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(m->q_tc_cand.as<uint8_t>() + (size_t)P * cap * 4);
+  sc.qnorm = (float*)(base + off_qn);
+  sc.thr = (float*)(base + off_thr);
+  sc.qpad = (float*)(base + off_pad);
+  sc.sidx = (int64_t*)(base + off_sidx);
+  sc.ssc = (float*)(base + off_ssc);
+  sc.cand_cnt = (uint32_t*)(base + off_cnt);
+  sc.cand = m->q_tc_cand.as<uint32_t>();
+  sc.keys = reinterpret_cast<unsigned long long*>(m->q_tc_cand.as<uint8_t>() + (size_t)P * sc.cap * 4);
 
-  // ---- 1. thresholds from an exactly scored strided sample -----------------------------------------------------
-  const uint32_t stride = std::max<uint32_t>(1, V / std::max<uint32_t>(65536u, V / 256));
-  const uint32_t n_sample = (V + stride - 1) / stride;
-  const int have_sample = n_sample >= (uint32_t)k ? 1 : 0;
-  if (have_sample) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride, n_sample, sidx, ssc, s));
-  prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, ssc, k, have_sample, qnorm, thr);
-  VSM_LAUNCHED();
-  VSM_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)P * 4, s));
-
-  // ---- 2. tensor-core pass(es): 64 prompts at a time ------------------------------------------------------------
-  CUtensorMap map_a, map_b;
-  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)m->vcap, (uint64_t)d, kTileM));
-  VSM_TRY(make_map_2d(&map_b, qpad, (uint64_t)kTileN, (uint64_t)d, kTileN));
-  VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
-  const uint32_t n_tiles = (V + kTileM - 1) / kTileM;
-  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
-  for (int p0 = 0; p0 < P; p0 += kTileN) {
-    const int pb = std::min(kTileN, P - p0);
-    pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, qpad);
+  // ---- 1. thresholds: the k-th best EXACT score of a subset of the voxels bounds the k-th best overall from below.
+  // Nested strided subsets:  C (ids 0, 16*stride, ...; a few thousand rows) is scored by the exact fp32 engine;
+  // B (ids 0, stride, ...; >= 65536 rows) by a tensor-core level of its own with C's thresholds -- engine 1 would
+  // need P/8 passes over B (5.6 ms of a 16 ms call at P = 256, measured); then the pass over everything uses B's.
+  const uint32_t target_b = std::max<uint32_t>(std::min<uint32_t>(65536u, V / 4), V / 256);
+  const uint32_t stride_b = std::max<uint32_t>(1, V / std::max<uint32_t>(target_b, 1u));
+  const uint32_t n_b = (V + stride_b - 1) / stride_b;
+  const uint32_t stride_c = stride_b * 16;
+  const uint32_t n_c = (V + stride_c - 1) / stride_c;
+  int have_sample = 0;
+  if (stride_b > 1 && n_c >= (uint32_t)std::max(4 * k, 2048)) {
+    VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_c, n_c, sc.sidx, sc.ssc, s));
+    prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 1, sc.qnorm, sc.thr);
     VSM_LAUNCHED();
-    TcArgs a;
-    a.vcount = m->vcount.as<uint32_t>();
-    a.vnorm = m->q_norm.as<float>();
-    a.thr = thr + p0;
-    a.qnorm = qnorm + p0;
-    a.V = V;
-    a.pb = pb;
-    a.p0 = p0;
-    a.normalize = normalize;
-    a.cand = cand;
-    a.cand_cnt = cand_cnt;
-    a.cap = cap;
-    a.n_kchunks = n_kchunks;
-    query_tc_kernel<<<grid, kThreads, smem, s>>>(map_a, map_b, a);
-    VSM_LAUNCHED();
+    bool fell_back = false;
+    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_b, n_b, sc, tile_n, smem, sc.sidx, sc.ssc, &fell_back, s));
+    if (fell_back) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_b, n_b, sc.sidx, sc.ssc, s));
+    have_sample = 1;
+  } else if (n_b >= (uint32_t)k && stride_b > 1) {
+    VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_b, n_b, sc.sidx, sc.ssc, s));
+    have_sample = 1;
   }
-  // ---- 3. exact re-scoring + top-k ----------------------------------------------------------------------------------
-  std::vector<uint32_t> h_cnt(P);
-  VSM_TRY(read_back(m, h_cnt.data(), cand_cnt, (size_t)P * 4, s));
-  uint32_t mx = 0;
-  for (int p = 0; p < P; ++p) mx = std::max(mx, h_cnt[p]);
-  m->tc_last_candidates = mx;
-  if (mx > cap || mx < (uint32_t)k) {
-    // a list overflowed (dense ties) -- or, impossibly, lost candidates: answer with the exact engine
+  prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, have_sample, sc.qnorm, sc.thr);
+  VSM_LAUNCHED();
+
+  // ---- 2. + 3. tensor-core pass over all voxels, exact re-scoring + top-k ---------------------------------------
+  bool fell_back = false;
+  VSM_TRY(tc_level(m, q_dev, P, k, normalize, 1u, V, sc, tile_n, smem, idx_dev, score_dev, &fell_back, s));
+  if (fell_back) {
     m->tc_fallbacks += 1;
     return query_exact(m, q_dev, P, k, normalize, idx_dev, score_dev, s);
   }
-  dim3 rgrid((unsigned)std::min<uint32_t>((mx + 7) / 8, 148u * 4u), (unsigned)P);
-  rescore_kernel<<<rgrid, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
-                                       normalize, cand, cand_cnt, cap, P, keys);
-  VSM_LAUNCHED();
-  return query_select_from_keys(m, keys, cand_cnt, P, (int)cap, k, idx_dev, score_dev, s);
+  return VSM_OK;
 }
 
 }  // namespace vsm

@@ -104,6 +104,39 @@ class ShardedVoxelMap:
         return bi.cpu().numpy(), bs.cpu().numpy()
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the
+    host-streaming path are allocated on the GPU's NUMA node (one process per GPU on a two-socket box otherwise
+    leaves half the ranks copying across sockets).  Returns the CPU list, or None if NVML / affinity is unavailable."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        want = f"{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0" if hasattr(props, "pci_bus_id") else None
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        if want is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                b = pynvml.nvmlDeviceGetPciInfo(hi).busId
+                b = b.decode() if isinstance(b, bytes) else b
+                if b.lower().endswith(want):
+                    h = hi
+                    break
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 class _Phases:
     """Wall-clock phases of build_sharded when VSM_DIST_TRACE=1 (synchronises the device at every mark)."""
 
