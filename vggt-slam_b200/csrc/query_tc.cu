@@ -36,16 +36,23 @@ namespace tc {
 constexpr int kTileM = 128;      // voxels per tile (MMA M)
 constexpr int kMaxTileN = 256;   // prompts per pass (MMA N): 64 (resident prompt block), 128 or 256 (streamed)
 constexpr int kChunkK = 32;      // fp32 channels per pipeline stage: 128 bytes = one swizzle row
-constexpr int kThreads = 256;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4..7 epilogue
-constexpr uint32_t kABytes = kTileM * kChunkK * 4;  // 16 KB per stage
+constexpr uint32_t kHalfBytes = kTileM * kChunkK * 4;  // 128 voxels x 32 channels: 16 KB
+constexpr int kWarpStage = 128;  // candidates an epilogue warp stages in shared memory before one global append
 
+// TN prompts per pass.  Streamed prompt slices are re-read from L2 for every voxel tile, so a streamed tile takes
+// 256 voxels (two M=128 MMAs per K step share one slice): half the L2 traffic per voxel.
 template <int TN>
 struct Cfg {
   static constexpr bool kStream = TN > 64;                      // prompt slices travel with the voxel stages
+  static constexpr int kMH = kStream ? 2 : 1;                   // M=128 halves per tile
+  static constexpr int kTileRows = kMH * kTileM;
+  static constexpr uint32_t kABytes = kMH * kHalfBytes;
   static constexpr uint32_t kBChunkBytes = TN * kChunkK * 4;    // one 32-channel slice of the prompt block
   static constexpr uint32_t kStageBytes = kABytes + (kStream ? kBChunkBytes : 0u);
-  static constexpr int kStages = kStream ? (TN == 128 ? 6 : 4) : 4;
-  static constexpr int kTmemCols = 2 * TN;                      // two accumulators
+  static constexpr int kStages = !kStream ? 4 : (TN == 128 ? 4 : 3);
+  static constexpr int kAccBufs = (2 * kMH * TN <= 512) ? 2 : 1;  // accumulator sets in the 512 TMEM columns
+  static constexpr int kTmemCols = kAccBufs * kMH * TN;
+  static constexpr int kThreads = 128 + 128 * kMH;              // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -154,20 +161,22 @@ struct TcArgs {
   int pb;                // prompts in this pass (<= TN)
   int p0;                // first prompt of the pass
   int normalize;
-  uint32_t* cand;        // [P][cap] voxel ids
-  uint32_t* cand_cnt;    // [P]
-  uint32_t cap;
+  unsigned long long* pairs;  // flat candidate list: (prompt << 32 | voxel id), in arrival order
+  uint32_t* pair_cnt;         // [1] entries appended (can exceed pair_cap: overflow)
+  uint32_t pair_cap;
   int n_kchunks;         // d / 32
 };
 
 template <int TN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<TN>::kThreads, 1)
 query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   using C = Cfg<TN>;
   constexpr int kStages = C::kStages;
+  constexpr int kThreads = C::kThreads;
+  constexpr uint32_t kABytes = C::kABytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   // layout, resident prompts: [B: n_kchunks x 8 KB][A: kStages x 16 KB][barriers]
-  //         streamed prompts: [kStages x (A 16 KB | B slice)][barriers]
+  //         streamed prompts: [kStages x (A 32 KB | B slice)][barriers]
   uint8_t* smem_b = smem;
   uint8_t* smem_a = C::kStream ? smem : smem + (size_t)a.n_kchunks * C::kBChunkBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)kStages * C::kStageBytes);
@@ -177,15 +186,14 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* tempty = tfull + 2;            // [2] epilogue -> MMA
   uint64_t* bfull = tempty + 2;            // [1] prompt block resident
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bfull + 1);
-  __shared__ float s_thr[TN], s_qn[TN];
+  __shared__ float2 s_col[TN];  // per prompt column: (||q_p||, threshold T_p); padding columns can never pass
+  __shared__ unsigned long long s_stage[4 * C::kMH][kWarpStage];  // candidates staged per epilogue warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n_tiles = (a.n_rows + kTileM - 1) / kTileM;
+  const uint32_t n_tiles = (a.n_rows + C::kTileRows - 1) / C::kTileRows;
 
-  for (int i = threadIdx.x; i < TN; i += kThreads) {
-    s_thr[i] = i < a.pb ? a.thr[i] : __int_as_float(0x7f800000);
-    s_qn[i] = i < a.pb ? a.qnorm[i] : 0.f;
-  }
+  for (int i = threadIdx.x; i < TN; i += kThreads)
+    s_col[i] = i < a.pb ? make_float2(a.qnorm[i], a.thr[i]) : make_float2(0.f, __int_as_float(0x7f800000));
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -195,7 +203,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty[i], 4 * C::kMH);  // one arrive per epilogue warp
     }
     mbar_init(bfull, 1);
     fence_barrier_init();
@@ -219,7 +227,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], C::kStageBytes);
         uint8_t* st = smem_a + (size_t)stage * C::kStageBytes;
-        tma_load_2d(st, &map_a, &full[stage], kc * kChunkK, (int)(tile * kTileM));
+        tma_load_2d(st, &map_a, &full[stage], kc * kChunkK, (int)(tile * C::kTileRows));
         if (C::kStream) tma_load_2d(st + kABytes, &map_b, &full[stage], kc * kChunkK, 0);
         if (++stage == kStages) {
           stage = 0;
@@ -235,16 +243,19 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * TN;
+      const uint32_t tmem_d = tmem_base + acc * (C::kMH * TN);
       for (int kc = 0; kc < a.n_kchunks; ++kc) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         uint8_t* st = smem_a + (size_t)stage * C::kStageBytes;
-        const uint64_t adesc = make_smem_desc(smem_u32(st));
         const uint64_t bdesc = make_smem_desc(smem_u32(C::kStream ? st + kABytes : smem_b + (size_t)kc * C::kBChunkBytes));
 #pragma unroll
-        for (int k = 0; k < kChunkK / 8; ++k)  // K = 8 tf32 (32 bytes) per instruction: advance 32 bytes inside the atom
-          mma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        for (int h = 0; h < C::kMH; ++h) {
+          const uint64_t adesc = make_smem_desc(smem_u32(st + (size_t)h * kHalfBytes));
+#pragma unroll
+          for (int k = 0; k < kChunkK / 8; ++k)  // K = 8 tf32 (32 bytes) per instruction: advance 32 bytes inside the atom
+            mma_tf32(tmem_d + h * TN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        }
         mma_commit(&empty[stage]);  // frees the smem stage when these MMAs are done
         if (++stage == kStages) {
           stage = 0;
@@ -252,46 +263,78 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
       mma_commit(&tfull[acc]);  // accumulator complete
-      if (++acc == 2) {
+      if (++acc == C::kAccBufs) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> threshold test -> candidate lists =====
-    const int ew = warp & 3;  // TMEM lane quarter this warp may read
+    const int ew = warp & 3;        // TMEM lane quarter this warp may read
+    const int mh = (warp - 4) >> 2;  // which M=128 half of the tile
+    // A candidate costs a slot in the global list.  Reserving it with a global atomic per hit stalls the warp for a
+    // full round trip per candidate (measured: the epilogue of a 256-prompt tile took longer than its MMAs), so
+    // each warp stages its hits in shared memory (positions from a ballot, no atomics) and appends ~100 at a time.
+    unsigned long long* wbuf = s_stage[warp - 4];
+    uint32_t wn = 0;  // staged entries (warp-uniform)
+    auto flush = [&]() {
+      if (wn) {
+        __syncwarp();
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.pair_cnt, wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < wn; i += 32)
+          if (base + i < a.pair_cap) a.pairs[base + i] = wbuf[i];
+        wn = 0;
+        __syncwarp();
+      }
+    };
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const uint32_t row = tile * kTileM + ew * 32 + lane;
+      const uint32_t row = tile * C::kTileRows + mh * kTileM + ew * 32 + lane;
       const uint32_t id = row * a.row_stride;
-      float inv = 0.f, fn = 0.f;
+      float inv = 0.f, fn = 0.f, nrm = 0.f;
       const bool valid = row < a.n_rows;
       if (valid) {
         const float cnt = (float)a.vcount[id];
-        const float nrm = a.vnorm[id];
+        nrm = a.vnorm[id];
         fn = __fdiv_rn(nrm, cnt);  // ||f_v||
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = 1.0f;  // scored quantity is f/||f||: unit norm
       }
       const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
+      // rows with non-finite sums (NaN scores rank first in torch.topk) always take the exact per-column path
+      const bool special = !(fabsf(nrm) <= 3.402823466e38f) || !(fabsf(fn) <= 3.402823466e38f) || !(fabsf(inv) <= 3.402823466e38f);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * C::kMH + mh) * TN;
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
         if (c0 >= a.pb) break;  // columns beyond the pass's prompts are padding
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (valid) {
-#pragma unroll 8
+        // keep (v, p) iff  x = a(v,p)/count + margin_v * ||q_p|| - T_p  is not < 0.  Hits are rare (< 1e-3), so the
+        // 32 columns are first reduced to one maximum: 3 instructions and one shared-memory read per score
+        float mx = __int_as_float(0xff800000);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float2 c = s_col[c0 + j];
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), inv, fmaf(margin, c.x, -c.y)));
+        }
+        const bool go = valid && (special || mx >= 0.f);
+        if (__any_sync(0xffffffffu, go)) {
+#pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int p = c0 + j;
-            const float sc = __uint_as_float(r[j]) * inv;
-            // !(x < t) also keeps NaN scores (they rank first in torch.topk)
-            if (p < a.pb && !(sc + margin * s_qn[p] < s_thr[p])) {
-              const uint32_t pos = atomicAdd(&a.cand_cnt[a.p0 + p], 1u);
-              if (pos < a.cap) a.cand[(size_t)(a.p0 + p) * a.cap + pos] = id;
+            const float2 c = s_col[c0 + j];
+            const float x = fmaf(__uint_as_float(r[j]), inv, fmaf(margin, c.x, -c.y));
+            const bool hit = go && (c0 + j < a.pb) && !(x < 0.f);  // also keeps NaN
+            const unsigned v = __ballot_sync(0xffffffffu, hit);
+            if (v) {
+              if (hit)
+                wbuf[wn + __popc(v & ((1u << lane) - 1u))] = ((unsigned long long)(uint32_t)(a.p0 + c0 + j) << 32) | id;
+              wn += __popc(v);
+              if (wn > (uint32_t)(kWarpStage - 32)) flush();
             }
           }
         }
@@ -299,11 +342,12 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) {
+      if (++acc == C::kAccBufs) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -353,20 +397,22 @@ __global__ void pad_prompts_kernel(const float* __restrict__ q, int p0, int pb, 
   }
 }
 
-// exact fp32 re-scoring of the candidates: one warp per candidate, key = (ordered(score) << 32 | ~rank)
+// exact fp32 re-scoring of the candidates: one warp per (prompt, voxel) entry of the flat list; the key
+// (ordered(score) << 32 | ~rank) goes to the prompt's own list
 __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ vsum, const uint32_t* __restrict__ vcount,
                                                       const uint32_t* __restrict__ rank_of_id, const float* __restrict__ q,
-                                                      int d, int normalize, const uint32_t* __restrict__ cand,
-                                                      const uint32_t* __restrict__ cand_cnt, uint32_t cap, int P,
+                                                      int d, int normalize, const unsigned long long* __restrict__ pairs,
+                                                      const uint32_t* __restrict__ pair_cnt, uint32_t pair_cap,
+                                                      uint32_t* __restrict__ cand_cnt, uint32_t cap,
                                                       unsigned long long* __restrict__ keys) {
   const int lane = lane_id();
-  const int p = blockIdx.y;
-  const uint32_t n = min(cand_cnt[p], cap);
+  const uint32_t n = min(*pair_cnt, pair_cap);
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const float* qp = q + (size_t)p * d;
   for (int64_t i = warp; i < n; i += n_warps) {
-    const uint32_t id = cand[(size_t)p * cap + i];
+    const unsigned long long e = pairs[i];
+    const uint32_t id = (uint32_t)e, p = (uint32_t)(e >> 32);
+    const float* qp = q + (size_t)p * d;
     float dot = 0.f, ss = 0.f;
     for (int c = lane; c < d / 4; c += 32) {
       const float4 v = *reinterpret_cast<const float4*>(vsum + (size_t)id * d + 4 * c);
@@ -383,8 +429,10 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ 
       float inv = 1.0f;
       if (normalize) inv = __fdiv_rn(1.0f, fmaxf(__fdiv_rn(sqrtf(ss), cnt), 1e-12f));
       const float sc = __fmul_rn(__fdiv_rn(dot, cnt), inv);
-      keys[(size_t)p * cap + i] =
-          ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - rank_of_id[id]);
+      const uint32_t pos = atomicAdd(&cand_cnt[p], 1u);
+      if (pos < cap)
+        keys[(size_t)p * cap + pos] =
+            ((unsigned long long)float_to_ordered(sc) << 32) | (unsigned long long)(0xFFFFFFFFu - rank_of_id[id]);
     }
   }
 }
@@ -429,8 +477,9 @@ namespace tc {
 struct Scratch {
   float *qnorm, *thr, *qpad, *ssc;
   int64_t* sidx;
-  uint32_t *cand_cnt, *cand;
-  unsigned long long* keys;
+  uint32_t* cand_cnt;         // [P] keys per prompt, then [1] entries of the flat list
+  unsigned long long* pairs;  // [P * cap] flat (prompt, voxel) candidates of the tensor-core pass
+  unsigned long long* keys;   // [P][cap] exact keys per prompt
   uint32_t cap;
 };
 
@@ -443,13 +492,16 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   const int d = m->d;
   const int n_kchunks = d / kChunkK;
   *fell_back = false;
-  VSM_CUDA(cudaMemsetAsync(sc.cand_cnt, 0, (size_t)P * 4, s));
+  VSM_CUDA(cudaMemsetAsync(sc.cand_cnt, 0, (size_t)(P + 1) * 4, s));
+  uint32_t* pair_cnt = sc.cand_cnt + P;
+  const uint32_t pair_cap = (uint32_t)std::min<uint64_t>((uint64_t)P * sc.cap, 0xFFFFFFFFull);
   CUtensorMap map_a, map_b;
-  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, kTileM, (uint64_t)stride * d));
+  const uint32_t tile_rows = tile_n == 64 ? Cfg<64>::kTileRows : Cfg<256>::kTileRows;
+  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, tile_rows, (uint64_t)stride * d));
   VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)tile_n));
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
-  const uint32_t n_tiles = (n_rows + kTileM - 1) / kTileM;
+  const uint32_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
   const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
   for (int p0 = 0; p0 < P; p0 += tile_n) {
     const int pb = std::min(tile_n, P - p0);
@@ -465,34 +517,34 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
     a.pb = pb;
     a.p0 = p0;
     a.normalize = normalize;
-    a.cand = sc.cand;
-    a.cand_cnt = sc.cand_cnt;
-    a.cap = sc.cap;
+    a.pairs = sc.pairs;
+    a.pair_cnt = pair_cnt;
+    a.pair_cap = pair_cap;
     a.n_kchunks = n_kchunks;
     if (tile_n == 64)
-      query_tc_kernel<64><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+      query_tc_kernel<64><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
     else if (tile_n == 128)
-      query_tc_kernel<128><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+      query_tc_kernel<128><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
     else
-      query_tc_kernel<256><<<grid, kThreads, smem, s>>>(map_a, map_b, a);
+      query_tc_kernel<256><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
     VSM_LAUNCHED();
   }
-  std::vector<uint32_t> h_cnt(P);
-  VSM_TRY(read_back(m, h_cnt.data(), sc.cand_cnt, (size_t)P * 4, s));
+  // the list's length lives on the device: a fixed grid strides over it
+  rescore_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
+                                         normalize, sc.pairs, pair_cnt, pair_cap, sc.cand_cnt, sc.cap, sc.keys);
+  VSM_LAUNCHED();
+  std::vector<uint32_t> h_cnt(P + 1);
+  VSM_TRY(read_back(m, h_cnt.data(), sc.cand_cnt, (size_t)(P + 1) * 4, s));  // the one synchronisation of a level
   uint32_t mx = 0, mn = 0xFFFFFFFFu;
   for (int p = 0; p < P; ++p) {
     mx = std::max(mx, h_cnt[p]);
     mn = std::min(mn, h_cnt[p]);
   }
   m->tc_last_candidates = mx;
-  if (mx > sc.cap || mn < (uint32_t)k) {
+  if (h_cnt[P] > pair_cap || mx > sc.cap || mn < (uint32_t)k) {
     *fell_back = true;  // a list overflowed (dense ties) -- or, impossibly, lost candidates
     return VSM_OK;
   }
-  dim3 rgrid((unsigned)std::min<uint32_t>((mx + 7) / 8, 148u * 4u), (unsigned)P);
-  rescore_kernel<<<rgrid, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
-                                       normalize, sc.cand, sc.cand_cnt, sc.cap, P, sc.keys);
-  VSM_LAUNCHED();
   return query_select_from_keys(m, sc.keys, sc.cand_cnt, P, (int)sc.cap, k, idx_dev, score_dev, s);
 }
 
@@ -532,13 +584,13 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
     VSM_LAUNCHED();
     m->norms_valid = true;
   }
-  // layout of q_tc: [qnorm P][thr P][padded prompts kMaxTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P]
+  // layout of q_tc: [qnorm P][thr P][padded prompts kMaxTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P + 1]
   const size_t off_qn = 0, off_thr = off_qn + (size_t)P * 4, off_pad = (off_thr + (size_t)P * 4 + 255) & ~(size_t)255;
   const size_t off_sidx = (off_pad + (size_t)kMaxTileN * d * 4 + 255) & ~(size_t)255;
   const size_t off_ssc = off_sidx + (size_t)P * k * 8, off_cnt = (off_ssc + (size_t)P * k * 4 + 255) & ~(size_t)255;
-  const size_t small_bytes = off_cnt + (size_t)P * 4;
+  const size_t small_bytes = off_cnt + (size_t)(P + 1) * 4;
   VSM_TRY(m->q_tc.ensure(small_bytes, s));
-  VSM_TRY(m->q_tc_cand.ensure((size_t)P * sc.cap * 12, s));  // ids (u32) + keys (u64)
+  VSM_TRY(m->q_tc_cand.ensure((size_t)P * sc.cap * 16, s));  // flat (prompt, voxel) list + keys per prompt
   uint8_t* base = m->q_tc.as<uint8_t>();
   sc.qnorm = (float*)(base + off_qn);
   sc.thr = (float*)(base + off_thr);
@@ -546,8 +598,8 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
   sc.sidx = (int64_t*)(base + off_sidx);
   sc.ssc = (float*)(base + off_ssc);
   sc.cand_cnt = (uint32_t*)(base + off_cnt);
-  sc.cand = m->q_tc_cand.as<uint32_t>();
-  sc.keys = reinterpret_cast<unsigned long long*>(m->q_tc_cand.as<uint8_t>() + (size_t)P * sc.cap * 4);
+  sc.pairs = m->q_tc_cand.as<unsigned long long>();
+  sc.keys = sc.pairs + (size_t)P * sc.cap;
 
   // ---- 1. thresholds: the k-th best EXACT score of a subset of the voxels bounds the k-th best overall from below.
   // Nested strided subsets:  C (ids 0, 16*stride, ...; a few thousand rows) is scored by the exact fp32 engine;
