@@ -602,20 +602,27 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
   sc.keys = sc.pairs + (size_t)P * sc.cap;
 
   // ---- 1. thresholds: the k-th best EXACT score of a subset of the voxels bounds the k-th best overall from below.
-  // Nested strided subsets:  C (ids 0, 16*stride, ...; a few thousand rows) is scored by the exact fp32 engine;
-  // B (ids 0, stride, ...; >= 65536 rows) by a tensor-core level of its own with C's thresholds -- engine 1 would
-  // need P/8 passes over B (5.6 ms of a 16 ms call at P = 256, measured); then the pass over everything uses B's.
+  // Nested strided subsets, each scored by a tensor-core level of its own (the exact engine would need P/8 passes
+  // per subset: 5.6 ms of a 16 ms call at P = 256, measured):  C (ids 0, 32*stride, ...; a few thousand rows) with
+  // threshold -inf, i.e. all of C re-scored exactly;  B (ids 0, stride, ...; >= 65536 rows) with C's thresholds;
+  // then the pass over everything with B's.
   const uint32_t target_b = std::max<uint32_t>(std::min<uint32_t>(65536u, V / 4), V / 256);
   const uint32_t stride_b = std::max<uint32_t>(1, V / std::max<uint32_t>(target_b, 1u));
   const uint32_t n_b = (V + stride_b - 1) / stride_b;
-  const uint32_t stride_c = stride_b * 16;
+  const uint32_t stride_c = stride_b * 32;
   const uint32_t n_c = (V + stride_c - 1) / stride_c;
   int have_sample = 0;
-  if (stride_b > 1 && n_c >= (uint32_t)std::max(4 * k, 2048)) {
-    VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_c, n_c, sc.sidx, sc.ssc, s));
-    prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 1, sc.qnorm, sc.thr);
+  if (stride_b > 1 && n_c >= (uint32_t)std::max(4 * k, 1024) && n_c <= sc.cap) {
+    // level C: every row of C is a candidate (threshold -inf), scored exactly by the re-scoring kernel -- one
+    // tensor-core launch instead of P/8 passes of the exact engine
+    prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 0, sc.qnorm, sc.thr);
     VSM_LAUNCHED();
     bool fell_back = false;
+    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_c, n_c, sc, tile_n, smem, sc.sidx, sc.ssc, &fell_back, s));
+    if (fell_back) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_c, n_c, sc.sidx, sc.ssc, s));
+    prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 1, sc.qnorm, sc.thr);
+    VSM_LAUNCHED();
+    fell_back = false;
     VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_b, n_b, sc, tile_n, smem, sc.sidx, sc.ssc, &fell_back, s));
     if (fell_back) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_b, n_b, sc.sidx, sc.ssc, s));
     have_sample = 1;
