@@ -334,6 +334,88 @@ def frame_stream_latency(args, dev):
     return out
 
 
+def indexed_embeddings(args, dev):
+    """SURVEY 8f-1, a DIFFERENT input contract from the headline (not comparable with `value` / `e2e`): the same
+    workload with the embeddings given as a mask-id image (S,H,W) int32 + a table (1024, d) instead of the dense
+    (S,H,W,d) array -- what the embedder actually produces (one CLIP vector per SAM mask).  Same build call; device-
+    resident inputs (CUDA events, 5 builds) and pinned host inputs (wall clock, H2D inside, 2 builds)."""
+    import torch
+    import vsm
+    from vsm import synth_device
+
+    emb_dtype = torch.bfloat16 if args.emb_dtype == "bf16" else torch.float32
+    S, H, W, d = args.frames, args.height, args.width, args.dim
+    gm, host = vsm.GraphMap(), []
+    for i in range(args.submaps):
+        dd = synth_device.make_submap_device(1234, i, S=S, H=H, W=W, d=d, mode="sl4", emb_dtype=emb_dtype,
+                                             first_frame_number=i * S, with_emb=False)
+        ids, table = synth_device.make_indexed_device(1234, i, S=S, H=H, W=W, d=d, emb_dtype=emb_dtype)
+        sm = vsm.Submap(i)
+        sm.add_all_points(dd.points, None, dd.conf, dd.conf_percentile, None)
+        sm.add_all_semantic_embeddings_indexed(ids, table)
+        sm.set_conf_masks(sm.conf)
+        sm.set_reference_homography(dd.H_world_map)
+        sm.set_frame_ids(dd.frame_paths)
+        sm.set_last_non_loop_frame_index(dd.last_non_loop_frame_index)
+        gm.add_submap(sm)
+        host.append((dd, ids, table, sm.conf_threshold))
+    hint, m = 1 << 18, None
+    for _ in range(4):
+        m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=hint)
+        hint = max(hint, int(m._dm.num_voxels * 1.05) + 1024)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=hint)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    n_fused = sum(s["n_fused"] for s in gm.last_build_stats)
+    out = {"input": f"mask ids (S,H,W) int32 + table (1024, {d}) {args.emb_dtype} per submap", "voxels": m._dm.num_voxels,
+           "points_fused_per_step": n_fused, "device_resident": {"ms_per_step": ms, "points_per_s": n_fused / (ms * 1e-3)}}
+    # host arrays: points, confidences and ids in pinned memory
+    gmh, h2d = vsm.GraphMap(), 0
+    for dd, ids, table, thr in host:
+        def pin(t):
+            o = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            o.copy_(t)
+            return o
+        sm = vsm.Submap(dd.submap_id)
+        sm.pointclouds, sm.conf, sm.conf_threshold = pin(dd.points).numpy(), pin(dd.conf).numpy(), thr
+        sm.add_all_semantic_embeddings_indexed(pin(ids).numpy(), pin(table))
+        sm.set_conf_masks(sm.conf)
+        sm.set_reference_homography(dd.H_world_map)
+        sm.set_frame_ids(dd.frame_paths)
+        sm.set_last_non_loop_frame_index(dd.last_non_loop_frame_index)
+        gmh.add_submap(sm)
+        h2d += dd.points.numel() * 4 + dd.conf.numel() * 4 + ids.numel() * 4 + table.numel() * table.element_size()
+    del gm, host, m
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        for sm in gmh.get_submaps():
+            sm.release_device_cache()
+        mm = gmh.build_semantic_voxel_map(args.voxel_size, capacity_hint=hint)
+        return mm.get_features().nbytes + mm.get_centers_world().nbytes
+
+    e2e_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        d2h = e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 2
+    out["host_arrays"] = {"ms_per_step": 1e3 * dt, "points_per_s": n_fused / dt, "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(d2h)}
+    del gmh
+    from vsm import _native as N
+
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
@@ -570,7 +652,8 @@ def main():
         try:
             N.lib.vsm_map_cache_release()
             torch.cuda.empty_cache()
-            secondary = {"text_query": query_latency(args, dev), "frame_stream": frame_stream_latency(args, dev)}
+            secondary = {"text_query": query_latency(args, dev), "frame_stream": frame_stream_latency(args, dev),
+                         "indexed_embeddings": indexed_embeddings(args, dev)}
         except Exception as e:  # secondary numbers must never cost the headline line
             secondary = {"error": repr(e)}
     if world > 1:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VSM_ABI_VERSION 1
+#define VSM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VSM_API __attribute__((visibility("default")))
@@ -88,6 +88,14 @@ typedef struct vsm_fuse_params {
   double coarse_factor;     /* 3.0  (map.py:271) */
   int32_t coarse_min_points;/* 10   (map.py:272) */
   int32_t frame_base;       /* index, inside its submap, of this call's frame 0 (per-frame streaming: S = 1 calls) */
+  /* Indexed embeddings.  The dense (S,H,W,d) array the reference fuses is piecewise constant: the embedder
+   * paints one CLIP vector per SAM mask into the pixels (semantic_embedder.py:324-349, zeros where no mask).  With
+   * emb_index_dev != NULL the `emb` argument of a fuse call is that TABLE, (emb_rows, d), and pixel p carries
+   * table[emb_index_dev[p]]: the same map as fusing the expanded array, from 4 bytes per pixel instead of 2d or 4d.
+   * Indices outside [0, emb_rows) fail the call with VSM_E_INVALID before the map is touched.  Device fuse calls only. */
+  const int32_t* emb_index_dev; /* int32 (S,H,W) on the device, or NULL for dense embeddings */
+  int32_t emb_rows;
+  int32_t reserved;
 } vsm_fuse_params;
 
 typedef struct vsm_fuse_stats {

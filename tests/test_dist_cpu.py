@@ -54,6 +54,27 @@ def _worker(rank, world, port, ret):
         sc = torch.tensor([[0.5, 0.9, 0.9, float("nan")], [0.1, 0.1, 0.1, 0.2]])
         bi, bs = vd.merge_topk(idx, sc, 3)
         assert bi.tolist() == [[7, 2, 9], [2, 0, 1]]
+        # sizes / signatures gathered before a peer exchange: every rank sees the same (world, n) table
+        table = vd._sizes_all([100 + rank, 7 * rank, (1 << 61) + rank], None, None)
+        assert table.shape == (world, 3) and table.dtype == np.int64
+        assert table[:, 0].tolist() == [100 + r for r in range(world)]
+        assert table[:, 2].tolist() == [(1 << 61) + r for r in range(world)]
+
+        class _Sm:  # what _names_signature reads of a Submap
+            def __init__(self, sid, ids, names):
+                self._sid, self.frame_ids, self.frame_id_to_name = sid, ids, names
+
+            def get_id(self):
+                return self._sid
+
+        fa = [{"submap": _Sm(3, [1.0, 2.0], {"1.0": "a.png", "2.0": "b.png"})}, {"submap": _Sm(1, [5.0], None)}]
+        sig = vd._names_signature(fa)
+        assert 0 <= sig < (1 << 62)
+        assert sig == vd._names_signature(list(reversed(fa)))            # order of the fuse records does not matter
+        fb = [{"submap": _Sm(3, [1.0, 2.0], {"1.0": "a.png", "2.0": "c.png"})}, {"submap": _Sm(1, [5.0], None)}]
+        assert sig != vd._names_signature(fb)                             # a renamed frame does
+        # no NVML / no GPU here: binding must decline quietly
+        assert vd.bind_to_gpu_numa(0) is None
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has
     const bool fits = ((unsigned long long)map_state[0] + ctr->n_new <= vcap) &&
                       ((unsigned long long)log_n + n_occ <= log_cap) &&
                       (ctr->n_finite <= (unsigned long long)entry_cap || ctr->n_fused <= (unsigned long long)entry_cap);
-    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss) {
+    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss || ctr->bad_index) {
       ctr->abort = 1u;
     } else {
       ctr->log_base = log_n;  // calls on one stream run one after the other: plain read-modify-write
@@ -603,6 +603,7 @@ struct RowVec<false> {
 };
 
 struct AccArgs {
+  const int32_t* emb_index;    // indexed embeddings: pixel p reads row emb_index[p] of the table `emb` (else nullptr)
   const uint8_t* emb;          // row of pixel p starts at emb + (p - pix_base) * row_bytes
   int64_t pix_base;
   int64_t row_bytes;
@@ -655,6 +656,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
     }
     // pixel mode: -1 = not selected; -2 = selected but filtered out (its row is only checked for non-finite values)
     if (!SORTED && __ballot_sync(0xffffffffu, CHECK ? (my_gid != -1) : (my_gid >= 0)) == 0u) continue;
+    // indexed embeddings: one gather per entry here, outside the row loop
+    if (a.emb_index != nullptr && lane < cnt && my_gid != -1) my_pix = (uint32_t)a.emb_index[my_pix];
 
     float acc[VPL * EPV];
 #pragma unroll
@@ -769,7 +772,8 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
     // check-only entries sit behind the fused ones: one warp per row, test the raw values
     const int64_t n_check = (int64_t)a.ctr->n_check;
     for (int64_t i = warp; i < n_check; i += n_warps) {
-      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      if (a.emb_index != nullptr) pj = (uint32_t)a.emb_index[pj];
       const uint8_t* row = emb0 + (unsigned long long)pj * rb;
       bool bad = false;
 #pragma unroll
@@ -833,9 +837,22 @@ int launch_accumulate(const AccArgs& a, bool bf16, bool sorted, bool check, cuda
   return VSM_E_INVALID;
 }
 
+// indexed embeddings: every pixel that can be selected must point into the table (checked before anything is fused)
+__global__ void __launch_bounds__(256) index_check_kernel(const float* __restrict__ conf, const int32_t* __restrict__ emb_index,
+                                                          uint32_t n_px, float thr, int32_t emb_rows, FuseCounters* ctr) {
+  unsigned bad = 0;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_px; pix += gridDim.x * blockDim.x) {
+    const int32_t r = emb_index[pix];
+    if ((r < 0 || r >= emb_rows) && conf[pix] >= thr) ++bad;
+  }
+  for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+  if (lane_id() == 0 && bad) atomicAdd(&ctr->bad_index, bad);
+}
+
 // uint8 row mask: 1 where the pixel passes conf/stride/end_idx and all d channels are finite (map.py:247)
 template <bool BF16>
 __global__ void __launch_bounds__(256) emb_row_mask_kernel(const float* __restrict__ conf, const uint8_t* __restrict__ emb,
+                                                           const int32_t* __restrict__ emb_index, int32_t emb_rows,
                                                            int64_t row_bytes, int nvec, int64_t n_px, int H, int W,
                                                            int stride, float thr, uint8_t* __restrict__ out) {
   const int lane = lane_id();
@@ -849,8 +866,17 @@ __global__ void __launch_bounds__(256) emb_row_mask_kernel(const float* __restri
     }
     bool bad = false;
     if (on) {
-      const uint8_t* row = emb + pix * row_bytes;
-      for (int c = lane; c < nvec; c += 32) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + (size_t)c * 16));
+      int64_t r = pix;
+      if (emb_index) {
+        r = emb_index[pix];
+        if (r < 0 || r >= emb_rows) r = -1;  // reported by index_check_kernel; never dereferenced
+      }
+      if (r < 0) {
+        bad = true;
+      } else {
+        const uint8_t* row = emb + r * row_bytes;
+        for (int c = lane; c < nvec; c += 32) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + (size_t)c * 16));
+      }
     }
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) out[pix] = (on && !bad) ? 1 : 0;
@@ -964,6 +990,10 @@ static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
     set_error("map was loaded from dense rows; fusing into it is not supported");
     return VSM_E_STATE;
   }
+  if (p->emb_index_dev != nullptr && p->emb_rows < 1) {
+    set_error("indexed embeddings need emb_rows >= 1 (got %d)", p->emb_rows);
+    return VSM_E_INVALID;
+  }
   return VSM_OK;
 }
 
@@ -1037,6 +1067,7 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   const float* conf = call.conf;
   const uint8_t* emb_dev = call.emb;
   const uint8_t* emb_ok = call.emb_ok;
+  const int32_t* emb_index = p->emb_index_dev;
 
   VSM_TRY(m->ctr_ring.ensure(sizeof(FuseCounters) * kCallRing, s));
   FuseCounters* ctr = m->ctr_ring.as<FuseCounters>() + call.slot;
@@ -1080,16 +1111,20 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   if (filters)
     ta = table_view(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, &ctr->n_occ_a);
 
+  if (emb_index != nullptr) {
+    index_check_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(conf, emb_index, (uint32_t)n_px, p->conf_threshold, p->emb_rows, ctr);
+    VSM_LAUNCHED();
+  }
   // optional exact finite-row filter on the embeddings (second read of the rows)
   if (filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr && emb_dev != nullptr) {
     VSM_TRY(call.precheck_mask.ensure((size_t)n_px, s));
     const int nvec = (int)(row_bytes / 16);
     if (bf16)
-      emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
-                                                        p->conf_threshold, call.precheck_mask.as<uint8_t>());
+      emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
+                                                        p->stride, p->conf_threshold, call.precheck_mask.as<uint8_t>());
     else
-      emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf, emb_dev, row_bytes, nvec, n_px, p->H, p->W, p->stride,
-                                                         p->conf_threshold, call.precheck_mask.as<uint8_t>());
+      emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
+                                                         p->stride, p->conf_threshold, call.precheck_mask.as<uint8_t>());
     VSM_LAUNCHED();
     emb_ok = call.precheck_mask.as<uint8_t>();
   }
@@ -1217,6 +1252,7 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   }
 
   AccArgs aa{};
+  aa.emb_index = emb_index;
   aa.row_bytes = row_bytes;
   aa.vsum = m->vsum.as<float>();
   aa.d = m->d;
@@ -1360,7 +1396,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     FuseCounters c = hc[k];
     const bool filters = (call.p.flags & VSM_FUSE_FILTERS) != 0;
     int status = VSM_OK;
-    for (int attempt = 0; c.abort && !c.internal_err && !c.range_err; ++attempt) {
+    for (int attempt = 0; c.abort && !c.internal_err && !c.range_err && !c.bad_index; ++attempt) {
       // nothing was modified: grow and run the call again, alone
       if (attempt >= 3) {
         set_error("internal: fuse call kept aborting after the map was grown");
@@ -1405,6 +1441,10 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
       } else if (c.range_err) {
         set_error("%u points have a finite voxel coordinate outside +-(2^20-1) cells", c.range_err);
         status = VSM_E_COORD_RANGE;
+      } else if (c.bad_index) {
+        set_error("%u confident pixels carry an embedding index outside the table of %d rows", c.bad_index,
+                  call.p.emb_rows);
+        status = VSM_E_INVALID;
       } else if (c.n_bad_emb) {
         set_error("%llu non-finite embedding rows / voxel sums met in the optimistic filter pass; clear the map "
                   "and fuse again with VSM_FUSE_EMB_PRECHECK", (unsigned long long)c.n_bad_emb);
@@ -1527,6 +1567,11 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
     set_error("null host pointer");
     return VSM_E_INVALID;
   }
+  if (p->emb_index_dev != nullptr) {
+    set_error("vsm_fuse_submap_host streams dense embeddings; copy an index image and its table to the device "
+              "(a few MB) and use vsm_fuse_submap");
+    return VSM_E_INVALID;
+  }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
   std::lock_guard<std::mutex> ws_lock(m->ws->mu);
@@ -1624,10 +1669,10 @@ extern "C" int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, c
   const int64_t row_bytes = (int64_t)m->d * m->esize;
   const int nvec = (int)(row_bytes / 16);
   if (m->cfg.emb_dtype == VSM_BF16)
-    emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, row_bytes, nvec, n_px, p->H,
+    emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
                                                       p->W, p->stride, p->conf_threshold, out_mask_dev);
   else
-    emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, row_bytes, nvec, n_px, p->H,
+    emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
                                                        p->W, p->stride, p->conf_threshold, out_mask_dev);
   VSM_LAUNCHED();
   return VSM_OK;

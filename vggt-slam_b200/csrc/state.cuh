@@ -50,6 +50,8 @@ struct FuseCounters {
   uint32_t seg_total;  // running allocation of sorted-list positions
   uint32_t n_check;    // check-only entries appended behind the fused ones
   uint32_t log_base;   // first contributor-log entry of this call (allocated on the device)
+  uint32_t bad_index;  // selected pixels whose embedding index lies outside the table
+  uint32_t pad1;
   float bounds[6];     // bbox filter bounds laid out [axis][lo,hi]
 };
 

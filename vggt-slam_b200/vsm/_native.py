@@ -36,7 +36,7 @@ class FuseParams(C.Structure):
                 ("stride", C.c_int32), ("conf_threshold", C.c_float), ("H_world_map", C.c_double * 16),
                 ("submap_id", C.c_int32), ("flags", C.c_uint32), ("bbox_lo_pct", C.c_double),
                 ("bbox_hi_pct", C.c_double), ("coarse_factor", C.c_double), ("coarse_min_points", C.c_int32),
-                ("frame_base", C.c_int32)]
+                ("frame_base", C.c_int32), ("emb_index", C.c_void_p), ("emb_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FuseStats(C.Structure):

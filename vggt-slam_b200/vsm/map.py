@@ -191,10 +191,14 @@ class GraphMap:
                 if bool((hs >= float(submap.conf_threshold)).any()):
                     raise IndexError("list index out of range")
             sid = int(submap.get_id())
-            params = dm.make_params(S, H, W, end_idx, stride, submap.conf_threshold, submap.H_world_map, sid, flags)
+            index = submap.index_on_device() if getattr(submap, "semantic_index", None) is not None else None
+            params = dm.make_params(S, H, W, end_idx, stride, submap.conf_threshold, submap.H_world_map, sid, flags,
+                                    emb_index=index, emb_rows=_shape(submap.semantic_embeddings)[0] if index is not None else 0)
             emb = submap.semantic_embeddings
             on_host = isinstance(emb, np.ndarray) or (isinstance(emb, torch.Tensor) and not emb.is_cuda)
             stream_it = on_host if host_streaming is None else (host_streaming and on_host)
+            if index is not None:
+                stream_it = False  # an index image and its table are a few MB: copied whole, fused on the device path
             if stream_it and not (flags & N.FUSE_EMB_PRECHECK):
                 pts = submap.pointclouds if isinstance(submap.pointclouds, np.ndarray) else None
                 if pts is None or not isinstance(submap.conf, np.ndarray):
@@ -210,7 +214,9 @@ class GraphMap:
                 stats = dm.fuse_host(pts_h, conf_h, emb_h, params)
             else:
                 # device-resident inputs: queue the call, collect all of them with one synchronisation below
-                dm.fuse_async(submap._device("points"), submap._device("conf"), submap.embeddings_on_device(), params)
+                dm.fuse_async(submap._device("points"), submap._device("conf"),
+                              submap.embeddings_on_device(cache=index is not None), params,
+                              keep_alive=index)
                 stats = None
             queued.append((stats, {"fuse_index": dm.fuse_calls - 1, "submap": submap, "S": S, "H": H, "W": W,
                                    "end_idx": end_idx, "sid": sid}))

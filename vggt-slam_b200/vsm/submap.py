@@ -43,7 +43,8 @@ class Submap:
         self.frame_ids = None
         self.frame_names = None
         self.frame_id_to_name = None
-        self.semantic_embeddings = None  # (S, H, W, d)
+        self.semantic_embeddings = None  # (S, H, W, d) -- or the (M, d) table when semantic_index is set
+        self.semantic_index = None       # (S, H, W) integer rows of that table (indexed embeddings)
         self.embeddings_are_bf16_bits = False
         self._dev_cache: Dict[str, torch.Tensor] = {}
 
@@ -77,8 +78,58 @@ class Submap:
                 raise ValueError("semantic_embeddings spatial dims must match pointclouds. "
                                  f"semantic={_shape(semantic_embeddings)[:3]} vs points={_shape(self.pointclouds)[:3]}")
         self.semantic_embeddings = semantic_embeddings
+        self.semantic_index = None
         self.embeddings_are_bf16_bits = bool(embeddings_are_bf16_bits)
         self._dev_cache.pop("emb", None)
+
+    def add_all_semantic_embeddings_indexed(self, mask_ids, table, embeddings_are_bf16_bits: bool = False):
+        """Indexed form of ``add_all_semantic_embeddings`` (no upstream counterpart): ``mask_ids`` (S,H,W)
+        integers and ``table`` (M,d) such that pixel (s,h,w) carries ``table[mask_ids[s,h,w]]``.  That is what the
+        embedder paints into its dense image -- one CLIP vector per SAM mask, zeros where there is none
+        (semantic_embedder.py:324-349): row 0 = zeros, row i+1 = the i-th mask's vector, later masks overwrite earlier
+        ones.  The fused map equals that of the expanded array ``table[mask_ids]``; the submap holds 4 bytes per pixel
+        instead of 2 KB.  Same exception types as the dense call (submap.py:52-63)."""
+        if not isinstance(mask_ids, (np.ndarray, torch.Tensor)) or not isinstance(table, (np.ndarray, torch.Tensor)):
+            raise TypeError("mask_ids must be an integer array of shape (S,H,W) and table an array of shape (M,d)")
+        if mask_ids.ndim != 3:
+            raise ValueError(f"mask_ids must have 3 dims (S,H,W), got shape={_shape(mask_ids)}")
+        if table.ndim != 2 or _shape(table)[0] < 1:
+            raise ValueError(f"table must have 2 dims (M,d) with M >= 1, got shape={_shape(table)}")
+        is_int = (mask_ids.dtype in (torch.int16, torch.int32, torch.int64, torch.uint8)) if isinstance(mask_ids, torch.Tensor) \
+            else np.issubdtype(mask_ids.dtype, np.integer)
+        if not is_int:
+            raise TypeError(f"mask_ids must be integers, got {mask_ids.dtype}")
+        if self.pointclouds is not None and _shape(mask_ids) != _shape(self.pointclouds)[:3]:
+            raise ValueError("mask_ids spatial dims must match pointclouds. "
+                             f"semantic={_shape(mask_ids)} vs points={_shape(self.pointclouds)[:3]}")
+        self.semantic_embeddings = table
+        self.semantic_index = mask_ids
+        self.embeddings_are_bf16_bits = bool(embeddings_are_bf16_bits)
+        self._dev_cache.pop("emb", None)
+        self._dev_cache.pop("emb_index", None)
+
+    def index_on_device(self) -> Optional[torch.Tensor]:
+        """int32 device tensor of the embedding indices (cached: 4 bytes per pixel), or None for dense embeddings."""
+        if self.semantic_index is None:
+            return None
+        t = self._dev_cache.get("emb_index")
+        if t is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            src = self.semantic_index
+            src = torch.from_numpy(np.ascontiguousarray(src)) if isinstance(src, np.ndarray) else src
+            t = src.to(dev).to(torch.int32).contiguous()
+            self._dev_cache["emb_index"] = t
+        return t
+
+    def dense_semantic_embeddings(self):
+        """The (S,H,W,d) array the reference would hold: table[mask_ids] for indexed embeddings (host numpy, float32)."""
+        if self.semantic_index is None:
+            return self.semantic_embeddings
+        tab = self.semantic_embeddings
+        tab = tab.float().cpu().numpy() if isinstance(tab, torch.Tensor) else np.asarray(tab, dtype=np.float32)
+        ids = self.semantic_index
+        ids = ids.cpu().numpy() if isinstance(ids, torch.Tensor) else np.asarray(ids)
+        return tab[ids]
 
     def add_all_frames(self, frames):
         self.frames = frames
@@ -252,8 +303,10 @@ class Submap:
         if ignore_loop_closure_frames and self.last_non_loop_frame_index is not None:
             end_idx = min(end_idx, int(self.last_non_loop_frame_index) + 1)
         dm = vm.DeviceVoxelMap(float(voxel_size), d, self.embedding_dtype_code(), capacity=1 << 16)
+        index = self.index_on_device()
         params = dm.make_params(S, H, W, end_idx, 1, self.conf_threshold, self.H_world_map, int(self.submap_id),
-                                N.FUSE_KEEP_POINT_INDEX)
+                                N.FUSE_KEEP_POINT_INDEX, emb_index=index,
+                                emb_rows=_shape(self.semantic_embeddings)[0] if index is not None else 0)
         stats = dm.fuse(self._device("points"), self._device("conf"), self.embeddings_on_device(), params)
         dm.finalize()
         V = dm.num_voxels

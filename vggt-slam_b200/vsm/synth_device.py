@@ -69,7 +69,8 @@ def box_room_frames_device(gen: torch.Generator, S: int, H: int, W: int, room, n
 def make_submap_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: int = 518, d: int = 512,
                        mode: str = "sl4", room=(12.0, 8.0, 3.0), start: Optional[float] = None, noise: float = 0.005,
                        emb_dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None,
-                       first_frame_number: int = 0) -> DeviceSubmapData:
+                       first_frame_number: int = 0, with_emb: bool = True) -> DeviceSubmapData:
+    """with_emb=False leaves ``emb`` None (callers that attach indexed embeddings: make_indexed_device)."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     gen = torch.Generator(device=device)
     gen.manual_seed(seed * 1000003 + submap_id)
@@ -80,10 +81,12 @@ def make_submap_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: 
     u = torch.rand((2, S, H, W), dtype=torch.float32, device=device, generator=gen).clamp_min_(1e-12)
     conf = (1.0 - 2.0 * (torch.log(u[0]) + torch.log(u[1]))).contiguous()
     del u
-    emb = torch.empty((S, H, W, d), dtype=emb_dtype, device=device)
-    for s in range(S):  # frame by frame: keeps the float32 temporary small
-        emb[s] = torch.randn((H, W, d), dtype=torch.float32, device=device, generator=gen).to(torch.bfloat16).to(
-            emb_dtype)
+    emb = None
+    if with_emb:
+        emb = torch.empty((S, H, W, d), dtype=emb_dtype, device=device)
+        for s in range(S):  # frame by frame: keeps the float32 temporary small
+            emb[s] = torch.randn((H, W, d), dtype=torch.float32, device=device, generator=gen).to(torch.bfloat16).to(
+                emb_dtype)
     rng = np.random.default_rng([seed, submap_id])
     grng = np.random.default_rng([seed, 987654321])
     G = synth.random_sl4(grng) if mode == "sl4" else synth.random_sim3(grng, scale=None if mode == "se3" else 1.7)
@@ -95,6 +98,22 @@ def make_submap_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: 
         Hm[3, :] = [0.0, 0.0, 0.0, 1.0]
     paths = [f"left_{first_frame_number + i:06d}.png" for i in range(S)]
     return DeviceSubmapData(submap_id, pts, conf, emb, Hm.astype(np.float64), paths, S - 1)
+
+
+def make_indexed_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: int = 518, d: int = 512, n_masks: int = 1024,
+                        block: int = 16, emb_dtype: torch.dtype = torch.bfloat16, device: Optional[torch.device] = None):
+    """SAM-like indexed embeddings: mask ids (S,H,W) int32, piecewise constant over block x block pixels (0 = no mask),
+    and a table (n_masks, d) of unit vectors whose row 0 is zero (semantic_embedder.py:324-349 paints exactly this)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 7919 + submap_id)
+    coarse = torch.randint(0, n_masks, (S, (H + block - 1) // block, (W + block - 1) // block), device=device, generator=gen,
+                           dtype=torch.int32)
+    ids = coarse.repeat_interleave(block, dim=1).repeat_interleave(block, dim=2)[:, :H, :W].contiguous()
+    table = torch.randn((n_masks, d), dtype=torch.float32, device=device, generator=gen)
+    table = table / table.norm(dim=1, keepdim=True)
+    table[0] = 0.0
+    return ids, table.to(emb_dtype).contiguous()
 
 
 def to_submap(data: DeviceSubmapData, host: bool = False, pin: bool = True):

@@ -97,7 +97,9 @@ class DeviceVoxelMap:
 
     # -- fusion -----------------------------------------------------------
     def make_params(self, S, H, W, end_idx, stride, conf_threshold, H_world_map, submap_id, flags,
-                    frame_base: int = 0) -> N.FuseParams:
+                    frame_base: int = 0, emb_index: Optional[torch.Tensor] = None, emb_rows: int = 0) -> N.FuseParams:
+        """emb_index: int32 device tensor (S,H,W) of table rows -- the `emb` of the fuse call is then the (emb_rows, d)
+        table (indexed embeddings).  The caller keeps the tensor alive until the call has been collected."""
         p = N.FuseParams()
         p.S, p.H, p.W, p.end_idx, p.stride = int(S), int(H), int(W), int(end_idx), int(stride)
         p.conf_threshold = float(conf_threshold)
@@ -108,6 +110,11 @@ class DeviceVoxelMap:
         p.flags = int(flags)
         p.bbox_lo_pct, p.bbox_hi_pct, p.coarse_factor, p.coarse_min_points = 0.5, 99.5, 3.0, 10
         p.frame_base = int(frame_base)
+        if emb_index is not None:
+            assert emb_index.is_cuda and emb_index.dtype == torch.int32 and emb_index.is_contiguous()
+            assert tuple(emb_index.shape) == (int(S), int(H), int(W)), (tuple(emb_index.shape), (S, H, W))
+            p.emb_index = emb_index.data_ptr()
+            p.emb_rows = int(emb_rows)
         return p
 
     def fuse(self, points: torch.Tensor, conf: torch.Tensor, emb: torch.Tensor, params: N.FuseParams,
@@ -117,6 +124,7 @@ class DeviceVoxelMap:
         assert points.dtype == torch.float32 and conf.dtype == torch.float32
         assert points.is_contiguous() and conf.is_contiguous() and emb.is_contiguous()
         assert emb_dtype_code(emb) == self.emb_dtype and emb.shape[-1] == self.dim
+        assert not params.emb_index or (emb.ndim == 2 and emb.shape[0] == params.emb_rows)
         st = N.FuseStats()
         rc = N.lib.vsm_fuse_submap(self._h, _ptr(points), _ptr(conf), _ptr(emb), _ptr(emb_ok), C.byref(params),
                                    C.byref(st), _stream_ptr(self.device))
@@ -126,16 +134,17 @@ class DeviceVoxelMap:
         return self.last_stats
 
     def fuse_async(self, points: torch.Tensor, conf: torch.Tensor, emb: torch.Tensor, params: N.FuseParams,
-                   emb_ok: Optional[torch.Tensor] = None) -> None:
+                   emb_ok: Optional[torch.Tensor] = None, keep_alive=None) -> None:
         """vsm_fuse_submap_async: queue the call on the current stream and return; `collect` gets the stats.
         The tensors are kept alive here until then."""
         assert points.is_cuda and conf.is_cuda and emb.is_cuda
         assert points.dtype == torch.float32 and conf.dtype == torch.float32
         assert points.is_contiguous() and conf.is_contiguous() and emb.is_contiguous()
         assert emb_dtype_code(emb) == self.emb_dtype and emb.shape[-1] == self.dim
+        assert not params.emb_index or (emb.ndim == 2 and emb.shape[0] == params.emb_rows)
         N.check(N.lib.vsm_fuse_submap_async(self._h, _ptr(points), _ptr(conf), _ptr(emb), _ptr(emb_ok),
                                             C.byref(params), _stream_ptr(self.device)))
-        self._inflight.append((points, conf, emb, emb_ok))
+        self._inflight.append((points, conf, emb, emb_ok, keep_alive))
         self.fuse_calls += 1
 
     def collect(self) -> list:
