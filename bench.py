@@ -334,6 +334,53 @@ def frame_stream_latency(args, dev):
     return out
 
 
+def sharded_query_latency(args, dev, rank, world):
+    """Collective: V voxels per rank (V*world in total), the same prompts on every rank, top-10 of the whole map."""
+    import torch
+    import torch.distributed as dist
+    from vsm import _native as N
+    from vsm import dist as vdist
+    from vsm import voxel_map as vm
+
+    V, d, k = int(args.query_voxels), args.dim, 10
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    feats = torch.empty((V, d), dtype=torch.float32, device=dev)
+    for r0 in range(0, V, 1 << 20):
+        r1 = min(V, r0 + (1 << 20))
+        x = torch.randn((r1 - r0, d), dtype=torch.float32, device=dev, generator=g)
+        feats[r0:r1] = x / x.norm(dim=1, keepdim=True) * (0.3 + 0.7 * torch.rand((r1 - r0, 1), device=dev, generator=g))
+    centers = torch.rand((V, 3), dtype=torch.float32, device=dev, generator=g) * 1000.0
+    dm = vm.DeviceVoxelMap(0.05, d, N.F32, capacity=V)
+    dm.load_dense(centers, feats)
+    del feats, centers
+    torch.cuda.empty_cache()
+    shard = vdist.ShardedVoxelMap(None, dm, torch.arange(V, dtype=torch.int64, device=dev) + rank * V, V * world)
+    out = {"voxels_total": V * world, "voxels_per_gpu": V, "top_k": k, "points": []}
+    rng = np.random.default_rng(0)
+    for P in (1, 64, 256):
+        q = rng.normal(size=(P, d)).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1, keepdims=True)
+        for _ in range(2):
+            shard.query_with_embeddings(q, top_k=k)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            shard.query_with_embeddings(q, top_k=k)
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["points"].append({"prompts": P, "ms": 1e3 * float(dt[0]),
+                              "aggregate_GBps": V * world * d * 4 / float(dt[0]) * 1e-9})
+    dm.close()
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    return out
+
+
 def indexed_embeddings(args, dev):
     """SURVEY 8f-1, a DIFFERENT input contract from the headline (not comparable with `value` / `e2e`): the same
     workload with the embeddings given as a mask-id image (S,H,W) int32 + a table (1024, d) instead of the dense
@@ -656,6 +703,16 @@ def main():
                          "indexed_embeddings": indexed_embeddings(args, dev)}
         except Exception as e:  # secondary numbers must never cost the headline line
             secondary = {"error": repr(e)}
+    # ---- sharded text query (N > 1): every rank owns a shard of `query_voxels` voxels, prompts are scored per shard,
+    # P x k candidates are all-gathered and merged (vsm.dist.ShardedVoxelMap); weak scaling of BASELINE configs[3]
+    sharded_query = None
+    if world > 1 and not args.no_extras:
+        try:
+            sharded_query = sharded_query_latency(args, dev, rank, world)
+        except Exception as e:
+            sharded_query = {"error": repr(e)}
+        if rank == 0 and secondary is not None:
+            secondary["sharded_text_query"] = sharded_query
     if world > 1:
         dist.barrier()
 
