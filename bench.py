@@ -548,6 +548,7 @@ def main():
     points = 0
     last = None
     step_events = [ev0]
+    step_fuse_ms = []  # device time of the step's fuse calls (first kernel to last accumulate), from libvsm's events
     for _ in range(args.steps):
         last = None
         m, stats = step()
@@ -556,6 +557,7 @@ def main():
         points += sum(s["n_fused"] for s in stats)
         for k in prof:
             prof[k] += gm.last_profile[k]
+        step_fuse_ms.append(round(gm.last_profile["fuse_ms"], 3))
         last = m
     ev1.record()
     barrier()
@@ -729,7 +731,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 accumulate of " + args.emb_dtype + " embeddings; f64 transform",
                 "data": "synthetic (device-generated box-room pointmaps, 1+Gamma(2,2) confidence, N(0,1) embeddings)",
                 "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "step_ms": [round(x, 3) for x in step_ms], "retries_in_timed_region": counters, "secondary": secondary}
+                "clocks": clocks, "step_ms": [round(x, 3) for x in step_ms], "step_fuse_ms": step_fuse_ms, "retries_in_timed_region": counters, "secondary": secondary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -15,8 +15,9 @@ for i in range(n):
 torch.cuda.synchronize()
 hint = 1 << 18
 child = None
+keep = None
 for rep in range(40):
-    if rep == 10:
+    if rep == 10 and os.environ.get('POLL') == '1':
         child = subprocess.Popen([sys.executable, "-c", bench._CLOCK_CHILD, "", "0.01"], stdout=subprocess.DEVNULL)
         time.sleep(0.5)
     torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -27,10 +28,16 @@ for rep in range(40):
     m = wrap_device_map(dm, fused, names, 0.05)
     t3 = time.perf_counter()
     hint = max(hint, int(dm.num_voxels * 1.05) + 1024)
-    del m, fused
-    dm.close(); torch.cuda.synchronize()
+    del fused
+    if os.environ.get("ALTERNATE") == "1":
+        prev, keep = keep, (m, dm)       # the previous map dies here, like in bench.py's loop
+        del prev, m
+    else:
+        del m
+        dm.close()
+    torch.cuda.synchronize()
     t4 = time.perf_counter()
     f = lambda a, b: f"{1e3*(b-a):7.2f}"
     if rep >= 8:
         print(f"rep {rep:2d}{' poll' if child else '     '}: total {f(t0,t4)} | fuse {f(t0,t1)} finalize {f(t1,t2)} wrap {f(t2,t3)} close {f(t3,t4)}")
-child.terminate()
+if child: child.terminate()

@@ -237,12 +237,15 @@ class GraphMap:
 def wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contributors=True, exact_coords=False):
     """SemanticVoxelMap over a finalised DeviceVoxelMap: centres now, features / contributors lazily."""
     V = dm.num_voxels
-    _, centers, _, _ = dm.export_geometry(coords=False, centers=True, counts=False, recon=False)
+
+    def centers():  # fetched on first read, like the features
+        return dm.export_geometry(coords=False, centers=True, counts=False, recon=False)[1].cpu().numpy()
+
     if deduplicate_contributors:
         contributors = _dedup_contributors(dm, fused, V)
     else:
         contributors = _per_point_contributors_global(dm, fused, V)
-    vox = SemanticVoxel.lazy(float(voxel_size), centers.cpu().numpy(), dm.features_to_host, contributors)
+    vox = SemanticVoxel.lazy(float(voxel_size), centers, dm.features_to_host, contributors)
     return SemanticVoxelMap(vox, frame_name_maps=frame_name_maps, _device_map=dm, exact_coords=exact_coords)
 
 

@@ -66,12 +66,13 @@ class SemanticVoxel:
     """Same fields as the reference dataclass (vggt_slam/semantic_voxel.py:12-26): voxel_size,
     centers_world (N,3), features (N,d), contributors (length-N list of lists of (submap_id, frame_id)).
 
-    When built by the device path, ``features`` and ``contributors`` are fetched from the GPU the first
-    time they are read."""
+    When built by the device path, ``centers_world``, ``features`` and ``contributors`` are fetched from the GPU
+    the first time they are read (``centers_world`` may be passed as a function returning the array)."""
 
     def __init__(self, voxel_size, centers_world, features, contributors):
         self.voxel_size = voxel_size
-        self.centers_world = centers_world
+        self._centers = None if callable(centers_world) else centers_world
+        self._centers_fn = centers_world if callable(centers_world) else None
         self._features = features
         self._features_fn = None
         self.contributors = contributors
@@ -81,6 +82,21 @@ class SemanticVoxel:
         v = cls(voxel_size, centers_world, None, contributors)
         v._features_fn = features_fn
         return v
+
+    @property
+    def centers_world(self):
+        if self._centers is None and self._centers_fn is not None:
+            self._centers = self._centers_fn()
+        return self._centers
+
+    @centers_world.setter
+    def centers_world(self, value):
+        self._centers, self._centers_fn = value, None
+
+    def __len__(self):
+        if self._centers is None and self._centers_fn is not None:
+            return len(self.contributors)
+        return 0 if self._centers is None else int(np.asarray(self._centers).shape[0])
 
     @property
     def features(self):
@@ -93,8 +109,7 @@ class SemanticVoxel:
         self._features = value
 
     def __repr__(self):
-        n = 0 if self.centers_world is None else len(self.centers_world)
-        return f"SemanticVoxel(voxel_size={self.voxel_size}, n_voxels={n})"
+        return f"SemanticVoxel(voxel_size={self.voxel_size}, n_voxels={len(self)})"
 
 
 class SemanticVoxelMap:
@@ -108,7 +123,7 @@ class SemanticVoxelMap:
         self.exact_coords = bool(exact_coords)
         self._dm: Optional[DeviceVoxelMap] = _device_map
         self._coord_dict = None
-        n = 0 if voxels.centers_world is None else int(np.asarray(voxels.centers_world).shape[0])
+        n = len(voxels) if isinstance(voxels, SemanticVoxel) else int(np.asarray(voxels.centers_world).shape[0])
         if self._dm is None and n > 0:
             # a map made from host arrays (load_from_directory, or user code): upload once
             require_cuda()
@@ -118,11 +133,18 @@ class SemanticVoxelMap:
                 raise ValueError("feature dimension must be a multiple of 8")
             self._dm = DeviceVoxelMap(self.voxel_size, d, N.F32, capacity=max(n, 1024))
             self._dm.load_dense(np.ascontiguousarray(voxels.centers_world, dtype=np.float32), feats)
-        if self._dm is not None and self._dm.num_voxels > 0:
-            _, _, _, recon = self._dm.export_geometry(coords=False, centers=False, counts=False, recon=True)
-            self._voxel_coords = recon.cpu().numpy()
-        else:
-            self._voxel_coords = np.zeros((0, 3), dtype=np.int64)
+        self._recon_coords = None  # fetched from the device on first use (6 MB of int64 at 250 k voxels)
+
+    @property
+    def _voxel_coords(self) -> np.ndarray:
+        """The reference's reconstructed coordinates floor(centers/vs - 0.5) (semantic_voxel.py:38, 62-66)."""
+        if self._recon_coords is None:
+            if self._dm is not None and self._dm.num_voxels > 0:
+                _, _, _, recon = self._dm.export_geometry(coords=False, centers=False, counts=False, recon=True)
+                self._recon_coords = recon.cpu().numpy()
+            else:
+                self._recon_coords = np.zeros((0, 3), dtype=np.int64)
+        return self._recon_coords
 
     # -- getters (semantic_voxel.py:43-56) -----------------------------------
     def get_voxels(self) -> SemanticVoxel:
