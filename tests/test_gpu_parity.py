@@ -203,6 +203,17 @@ def select_mode(request):
     N.set_option("select_mode", 0)
 
 
+@pytest.fixture(params=[0, 1], ids=["one_stream", "overlap"])
+def fuse_overlap(request):
+    """vsm_set_option("overlap", 1): the accumulate kernel of a call runs on a side stream beside the next call's
+    preparation kernels (double-buffered entry lists) -- same map."""
+    from vsm import _native as N
+
+    N.set_option("overlap", request.param)
+    yield request.param
+    N.set_option("overlap", 0)
+
+
 def graph_from(vsm, subs, **kw):
     gm = vsm.GraphMap()
     for s in subs:
@@ -265,7 +276,7 @@ def test_build_global_errors_and_empty(vsm_mod):
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("stride", [1, 3])
-def test_build_global_oracle(vsm_mod, dtype, stride, select_mode):
+def test_build_global_oracle(vsm_mod, dtype, stride, select_mode, fuse_overlap):
     """Four overlapping submaps, SL(4), d=64, clean embeddings (single optimistic pass), device inputs."""
     subs = [synth.make_submap(31, i, S=5, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
                               first_frame_number=5 * i, n_loop_frames=(1 if i == 2 else 0)) for i in range(4)]

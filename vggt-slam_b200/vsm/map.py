@@ -165,6 +165,10 @@ class GraphMap:
 
     def _fuse_all(self, dm, todo, stride, ignore_loop, flags, host_streaming, fused, frame_name_maps):
         queued = []
+        copy_stream = [None]
+
+        def index_is_set(sm):
+            return getattr(sm, "semantic_index", None) is not None
 
         def flush():
             waiting = [i for i, (st, _) in enumerate(queued) if st is None]
@@ -191,15 +195,22 @@ class GraphMap:
                 if bool((hs >= float(submap.conf_threshold)).any()):
                     raise IndexError("list index out of range")
             sid = int(submap.get_id())
-            index = submap.index_on_device() if getattr(submap, "semantic_index", None) is not None else None
-            params = dm.make_params(S, H, W, end_idx, stride, submap.conf_threshold, submap.H_world_map, sid, flags,
-                                    emb_index=index, emb_rows=_shape(submap.semantic_embeddings)[0] if index is not None else 0)
             emb = submap.semantic_embeddings
             on_host = isinstance(emb, np.ndarray) or (isinstance(emb, torch.Tensor) and not emb.is_cuda)
             stream_it = on_host if host_streaming is None else (host_streaming and on_host)
-            if index is not None:
+            if index_is_set(submap):
                 stream_it = False  # an index image and its table are a few MB: copied whole, fused on the device path
-            if stream_it and not (flags & N.FUSE_EMB_PRECHECK):
+            stream_it = stream_it and not (flags & N.FUSE_EMB_PRECHECK)
+            if not stream_it:
+                # device path: host arrays (geometry; index image + table) are copied on a side stream, beside the
+                # kernels of the calls already queued
+                if copy_stream[0] is None:
+                    copy_stream[0] = torch.cuda.Stream()
+                submap.prefetch_to_device(copy_stream[0], with_embeddings=index_is_set(submap))
+            index = submap.index_on_device() if index_is_set(submap) else None
+            params = dm.make_params(S, H, W, end_idx, stride, submap.conf_threshold, submap.H_world_map, sid, flags,
+                                    emb_index=index, emb_rows=_shape(emb)[0] if index is not None else 0)
+            if stream_it:
                 pts = submap.pointclouds if isinstance(submap.pointclouds, np.ndarray) else None
                 if pts is None or not isinstance(submap.conf, np.ndarray):
                     pts_h = submap._device("points").cpu().numpy()
@@ -213,7 +224,7 @@ class GraphMap:
                 flush()  # the host-streamed call synchronises: take the queued calls' stats first
                 stats = dm.fuse_host(pts_h, conf_h, emb_h, params)
             else:
-                # device-resident inputs: queue the call, collect all of them with one synchronisation below
+                # queue the call; all queued calls are collected with one synchronisation below
                 dm.fuse_async(submap._device("points"), submap._device("conf"),
                               submap.embeddings_on_device(cache=index is not None), params,
                               keep_alive=index)

@@ -239,6 +239,40 @@ class Submap:
             self._dev_cache["emb"] = t
         return t
 
+    def prefetch_to_device(self, copy_stream: "torch.cuda.Stream", with_embeddings: bool) -> None:
+        """Start the host->device copies of this submap's small arrays (points, confidences and -- for indexed
+        embeddings -- the index image and the table) on ``copy_stream`` and make the CURRENT stream wait for them.
+        Copies from pinned memory then overlap the fuse calls already queued on the current stream (the copies of
+        submap i+1 run beside the kernels of submap i); pageable sources are copied synchronously, as before."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        main = torch.cuda.current_stream(dev)
+        todo = [("points", self.pointclouds, torch.float32), ("conf", self.conf, torch.float32)]
+        if with_embeddings and self.semantic_index is not None:
+            todo += [("emb_index", self.semantic_index, torch.int32), ("emb", self.semantic_embeddings, None)]
+        started = False
+        with torch.cuda.stream(copy_stream):
+            for key, src, dt in todo:
+                if key in self._dev_cache or src is None:
+                    continue
+                if key == "emb" and isinstance(src, np.ndarray) and src.dtype == np.uint16 and self.embeddings_are_bf16_bits:
+                    t = torch.from_numpy(np.ascontiguousarray(src).view(np.int16))
+                else:
+                    t = torch.from_numpy(np.ascontiguousarray(src)) if isinstance(src, np.ndarray) else src
+                if t.is_cuda:
+                    continue
+                if dt is not None and t.dtype != dt:
+                    t = t.to(dt)
+                elif key == "emb" and t.dtype not in (torch.float32, torch.bfloat16, torch.int16):
+                    t = t.to(torch.float32)
+                d = t.to(dev, non_blocking=True).contiguous()
+                if key == "emb" and d.dtype == torch.int16:
+                    d = d.view(torch.bfloat16)
+                d.record_stream(main)
+                self._dev_cache[key] = d
+                started = True
+        if started:
+            main.wait_stream(copy_stream)
+
     def release_device_cache(self) -> None:
         self._dev_cache.clear()
 
