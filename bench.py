@@ -307,30 +307,35 @@ def frame_stream_latency(args, dev):
     from vsm import synth_device
     from vsm import voxel_map as vm
 
-    S, H, W = 64, 518, 518
-    d = synth_device.make_submap_device(4321, 0, S=S, H=H, W=W, d=args.dim, mode="sim3", room=(6.0, 4.0, 3.0),
-                                        emb_dtype=torch.bfloat16)
-    thr = vm.conf_threshold(d.conf, 25.0)
-    dm = vm.DeviceVoxelMap(args.voxel_size, args.dim, N.BF16, capacity=1 << 19)
-    times = []
-    for rep in range(2):  # the first sweep warms the pool and the map
-        dm.clear()
+    def run(S, H, W):
+        d = synth_device.make_submap_device(4321, 0, S=S, H=H, W=W, d=args.dim, mode="sim3", room=(6.0, 4.0, 3.0),
+                                            emb_dtype=torch.bfloat16)
+        thr = vm.conf_threshold(d.conf, 25.0)
+        dm = vm.DeviceVoxelMap(args.voxel_size, args.dim, N.BF16, capacity=1 << 19)
         times = []
-        for f in range(S):
-            p = dm.make_params(1, H, W, 1, 1, thr, d.H_world_map, 0, 0, frame_base=f)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            dm.fuse(d.points[f:f + 1], d.conf[f:f + 1], d.emb[f:f + 1], p)
-            times.append(1e3 * (time.perf_counter() - t0))
-    px = H * W
-    kept = float((d.conf >= float(thr)).float().mean().item())
-    out = {"frame": f"{W}x{H}", "frames": S, "mode": "sim3", "ms_per_frame_median": float(np.median(times)),
-           "ms_per_frame_max": float(np.max(times)), "points_per_frame": int(px * kept),
-           "Mpoints_per_s": px * kept / (np.median(times) * 1e-3) * 1e-6, "voxels": dm.num_voxels}
-    dm.close()
-    del d
-    N.lib.vsm_map_cache_release()
-    torch.cuda.empty_cache()
+        for rep in range(2):  # the first sweep warms the pool and the map
+            dm.clear()
+            times = []
+            for f in range(S):
+                p = dm.make_params(1, H, W, 1, 1, thr, d.H_world_map, 0, 0, frame_base=f)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                dm.fuse(d.points[f:f + 1], d.conf[f:f + 1], d.emb[f:f + 1], p)
+                times.append(1e3 * (time.perf_counter() - t0))
+        px = H * W
+        kept = float((d.conf >= float(thr)).float().mean().item())
+        out = {"frame": f"{W}x{H}", "frames": S, "mode": "sim3", "ms_per_frame_median": float(np.median(times)),
+               "ms_per_frame_max": float(np.max(times)), "points_per_frame": int(px * kept),
+               "Mpoints_per_s": px * kept / (np.median(times) * 1e-3) * 1e-6, "voxels": dm.num_voxels}
+        dm.close()
+        del d
+        N.lib.vsm_map_cache_release()
+        torch.cuda.empty_cache()
+        return out
+
+    out = run(64, 518, 518)
+    # the literal reading of configs[4]: 1600x1600 point maps (2.56 M pixels, 2.6 GB of bf16 embeddings per frame)
+    out["stress_1600x1600"] = run(8, 1600, 1600)
     return out
 
 
@@ -441,10 +446,18 @@ def indexed_embeddings(args, dev):
     torch.cuda.empty_cache()
 
     def e2e_step():
+        ta = time.perf_counter()
         for sm in gmh.get_submaps():
             sm.release_device_cache()
         mm = gmh.build_semantic_voxel_map(args.voxel_size, capacity_hint=hint)
-        return mm.get_features().nbytes + mm.get_centers_world().nbytes
+        tb = time.perf_counter()
+        nb = mm.get_features().nbytes
+        tc = time.perf_counter()
+        nb += mm.get_centers_world().nbytes
+        if os.environ.get("VSM_BENCH_TRACE") == "1":
+            print(f"[indexed e2e] build {1e3 * (tb - ta):.1f} ms, features {1e3 * (tc - tb):.1f} ms, centres "
+                  f"{1e3 * (time.perf_counter() - tc):.1f} ms", file=sys.stderr, flush=True)
+        return nb
 
     e2e_step()
     torch.cuda.synchronize()
