@@ -143,6 +143,40 @@ __global__ void __launch_bounds__(256) sel_histn_kernel(SelSrc src, uint32_t* __
   }
 }
 
+// The same pass specialised for the world-point layout (float4 per element: x, y, z, flags; 3 columns x 4 targets):
+// ONE 128-bit load per element instead of four scalar ones, the twelve prefixes in registers, and the matches of a
+// warp grouped (match.any on target and digit) so that neighbouring pixels on the same wall add to a bin once.
+__global__ void __launch_bounds__(256) sel_histn4_kernel(const float4* __restrict__ pts, int64_t n_items, uint32_t flag_need,
+                                                          uint32_t* __restrict__ hist, const SelectState* st,
+                                                          int prefix_shift, int bins_shift, uint32_t bins_mask) {
+  uint32_t prefix[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) prefix[t] = st->prefix[t];
+  const int lane = lane_id();
+  const int64_t n_round = (n_items + 31) & ~(int64_t)31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n_items) p = pts[i];
+    const bool valid = (__float_as_uint(p.w) & flag_need) == flag_need && i < n_items;
+    const float v[3] = {p.x, p.y, p.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t o = float_to_ordered(v[c]);
+      const uint32_t hi = o >> prefix_shift;
+      const uint32_t dig = (o >> bins_shift) & bins_mask;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = c * 4 + k;
+        const bool hit = valid && hi == prefix[t];
+        const unsigned any = __ballot_sync(0xffffffffu, hit);
+        if (any == 0u) continue;  // warp-uniform
+        const unsigned grp = __match_any_sync(0xffffffffu, hit ? dig : 0xFFFFFFFFu);
+        if (hit && lane == __ffs(grp) - 1) atomicAdd(&hist[(size_t)t * (bins_mask + 1) + dig], (uint32_t)__popc(grp));
+      }
+    }
+  }
+}
+
 // value[t] from the completed 32-bit prefix; then the numpy lerp per (column, percentile) pair into out[]
 __global__ void sel_finish_kernel(SelectState* st, float* __restrict__ out, int n_out) {
   const int j = threadIdx.x;
@@ -239,11 +273,20 @@ int run_percentiles_after_hist0(SelectState* st, uint32_t* h0, const SelSrc& src
   VSM_LAUNCHED();
   sel_pick_kernel<<<nt, 32, 0, s>>>(st, h0, 2048, 11, 1);
   VSM_LAUNCHED();
-  sel_histn_kernel<<<grid, 256, 0, s>>>(src, h1, st, 21, 10, 2047u);
+  const bool world_layout = src.ncol == 3 && npct == 2 && src.stride == 4 && src.flag_off == 3 &&
+                            (reinterpret_cast<uintptr_t>(src.base) & 15u) == 0;
+  const float4* p4 = reinterpret_cast<const float4*>(src.base);
+  if (world_layout)
+    sel_histn4_kernel<<<grid, 256, 0, s>>>(p4, src.n_items, src.flag_need, h1, st, 21, 10, 2047u);
+  else
+    sel_histn_kernel<<<grid, 256, 0, s>>>(src, h1, st, 21, 10, 2047u);
   VSM_LAUNCHED();
   sel_pick_kernel<<<nt, 32, 0, s>>>(st, h1, 2048, 11, 0);
   VSM_LAUNCHED();
-  sel_histn_kernel<<<grid, 256, 0, s>>>(src, h2, st, 10, 0, 1023u);
+  if (world_layout)
+    sel_histn4_kernel<<<grid, 256, 0, s>>>(p4, src.n_items, src.flag_need, h2, st, 10, 0, 1023u);
+  else
+    sel_histn_kernel<<<grid, 256, 0, s>>>(src, h2, st, 10, 0, 1023u);
   VSM_LAUNCHED();
   sel_pick_kernel<<<nt, 32, 0, s>>>(st, h2, 1024, 10, 0);
   VSM_LAUNCHED();
