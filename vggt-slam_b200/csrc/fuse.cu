@@ -575,6 +575,15 @@ struct RowVec<true> {
     acc[6] = add_bf16_lo(acc[6], v.w);
     acc[7] = add_bf16_hi(acc[7], v.w);
   }
+  // acc += scale * v  (run-length path of indexed embeddings)
+  __device__ static __forceinline__ void fma(float* acc, const uint4& v, float scale) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] = fmaf(__uint_as_float(w[i] << 16), scale, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(__uint_as_float(w[i] & 0xFFFF0000u), scale, acc[2 * i + 1]);
+    }
+  }
   // exponent all ones in either half
   __device__ static __forceinline__ bool nonfinite(const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -592,6 +601,12 @@ struct RowVec<false> {
     acc[1] += __uint_as_float(v.y);
     acc[2] += __uint_as_float(v.z);
     acc[3] += __uint_as_float(v.w);
+  }
+  __device__ static __forceinline__ void fma(float* acc, const uint4& v, float scale) {
+    acc[0] = fmaf(__uint_as_float(v.x), scale, acc[0]);
+    acc[1] = fmaf(__uint_as_float(v.y), scale, acc[1]);
+    acc[2] = fmaf(__uint_as_float(v.z), scale, acc[2]);
+    acc[3] = fmaf(__uint_as_float(v.w), scale, acc[3]);
   }
   __device__ static __forceinline__ bool nonfinite(const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -622,7 +637,10 @@ struct AccArgs {
 // tested directly.  Any hit is counted in ctr->n_bad_emb and makes the fuse call fail with VSM_E_NONFINITE_EMB
 // (the caller redoes the build with the exact pre-check).
 // FULL: every lane owns VPL vectors (nvec == 32*VPL, e.g. d=512): no per-lane predicates in the hot loop.
-template <bool BF16, int VPL, bool SORTED, bool CHECK, bool FULL>
+// RLE (indexed embeddings, SORTED && FULL): neighbouring entries of a voxel mostly carry the same table row (pixels of
+// one mask), so runs of equal (voxel, row) are found with one ballot per chunk and added as  length x row  -- one row
+// read per run instead of one per point.
+template <bool BF16, int VPL, bool SORTED, bool CHECK, bool FULL, bool RLE = false>
 __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(AccArgs a) {
   constexpr int EPV = RowVec<BF16>::EPV;
   constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
@@ -692,7 +710,44 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
     };
 
     int j = 0;
-    if (SORTED && FULL) {
+    if (RLE) {
+      const int pg = __shfl_up_sync(0xffffffffu, my_gid, 1);
+      const uint32_t pr = __shfl_up_sync(0xffffffffu, my_pix, 1);
+      unsigned starts = __ballot_sync(0xffffffffu, lane < cnt && (lane == 0 || my_gid != pg || my_pix != pr));
+      while (starts) {
+        // up to U runs in flight
+        uint4 rows[U][VPL];
+        int gids[U];
+        float len[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          gids[u] = -1;
+          len[u] = 0.f;
+          if (starts) {
+            const int sidx = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int eidx = starts ? __ffs(starts) - 1 : cnt;
+            len[u] = (float)(eidx - sidx);
+            gids[u] = __shfl_sync(0xffffffffu, my_gid, sidx);
+            const uint32_t rj = __shfl_sync(0xffffffffu, my_pix, sidx);
+            const uint8_t* row = emb0 + (unsigned long long)rj * rb;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) rows[u][v] = ld_stream_v4(row + v * 512);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (gids[u] < 0) continue;  // warp-uniform
+          if (gids[u] != cur) {
+            flush();
+            cur = gids[u];
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::fma(acc + v * EPV, rows[u][v], len[u]);
+        }
+      }
+      j = cnt;
+    } else if (SORTED && FULL) {
       // hot loop: U rows in flight, every entry is a fused point, every lane owns VPL vectors
       for (; j + U <= cnt; j += U) {
         uint4 rows[U][VPL];
@@ -796,6 +851,14 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)148 * 6);
   }
   const bool full = a.nvec == 32 * VPL;
+  if (sorted && full && a.emb_index != nullptr) {
+    if (check)
+      accumulate_kernel<BF16, VPL, true, true, true, true><<<grid, block, 0, s>>>(a);
+    else
+      accumulate_kernel<BF16, VPL, true, false, true, true><<<grid, block, 0, s>>>(a);
+    VSM_LAUNCHED();
+    return VSM_OK;
+  }
 #define VSM_ACC(SORTED_, CHECK_)                                                      \
   do {                                                                                \
     if (full)                                                                         \
