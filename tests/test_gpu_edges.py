@@ -1,0 +1,113 @@
+"""Edge cases of the fuse path through the C ABI: capacity growth by retry, more queued calls than the ring holds,
+submaps that contribute nothing, strides beyond the image, the frame limit, coordinates outside the packable range."""
+import numpy as np
+import pytest
+
+import golden_io as gio
+from oracle import voxel_oracle as vo
+from vsm import synth
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-5
+
+
+def _dev(s):
+    import torch
+
+    return torch.from_numpy(s.points).cuda(), torch.from_numpy(s.conf).cuda(), torch.from_numpy(s.emb).cuda()
+
+
+def test_tiny_capacity_grows_by_retry_and_ring_overflow_collects_early():
+    """70 fuse calls queued into a map of 1024 voxels: calls that do not fit are aborted on the device before they
+    touch the map and repeated after growing; the 65th submit collects the first 64 itself.  Same map as one call
+    at a time into a large map."""
+    import vsm
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    subs = [synth.make_submap(91, i, S=2, H=40, W=60, d=32, mode="sl4", room=(2.4, 1.8, 1.2), start=0.05 * i)
+            for i in range(70)]
+    thr = [vm.conf_threshold(s.conf, 25.0) for s in subs]
+    big = vm.DeviceVoxelMap(0.02, 32, N.F32, capacity=1 << 18)   # 2 cm voxels: ~10^5 of them
+    for s, t in zip(subs, thr):
+        big.fuse(*_dev(s), big.make_params(2, 40, 60, 2, 1, t, s.H_world_map, s.submap_id, 0))
+    big.finalize()
+    r0, e0 = N.get_counter("capacity_retries"), N.get_counter("early_collects")
+    small = vm.DeviceVoxelMap(0.02, 32, N.F32, capacity=1024)
+    keep = []
+    for s, t in zip(subs, thr):
+        d = _dev(s)
+        keep.append(d)
+        small.fuse_async(*d, small.make_params(2, 40, 60, 2, 1, t, s.H_world_map, s.submap_id, 0))
+    stats = small.collect()
+    assert len(stats) == 70
+    assert N.get_counter("capacity_retries") > r0 and N.get_counter("early_collects") > e0
+    small.finalize()
+    assert small.num_voxels == big.num_voxels > 20000
+    for a, b in zip(small.export_geometry(), big.export_geometry()):
+        assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+    np.testing.assert_allclose(small.features_to_host(), big.features_to_host(), rtol=1e-5, atol=1e-6)
+    oa, sa, ma = small.export_contributors()
+    ob, sb, mb = big.export_contributors()
+    assert np.array_equal(oa, ob)
+    for v in range(0, small.num_voxels, 37):   # entries of a voxel may come in any order: compare as sets
+        ea = {(int(sa[e]), int(ma[e, 0]), int(ma[e, 1])) for e in range(int(oa[v]), int(oa[v + 1]))}
+        eb = {(int(sb[e]), int(mb[e, 0]), int(mb[e, 1])) for e in range(int(ob[v]), int(ob[v + 1]))}
+        assert ea == eb
+
+
+def test_submap_that_contributes_nothing_and_stride_beyond_the_image():
+    import vsm
+    from test_gpu_parity import to_submap
+
+    subs = [synth.make_submap(93, i, S=3, H=40, W=60, d=16, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
+                              first_frame_number=3 * i) for i in range(3)]
+    gm = vsm.GraphMap()
+    osubs = []
+    for i, s in enumerate(subs):
+        sm = to_submap(vsm, s, device_inputs=True)
+        o = gio.to_oracle_submap(s)
+        if i == 1:  # nothing passes this threshold
+            sm.conf_threshold = np.float32(1e9)
+            o.conf_threshold = np.float32(1e9)
+        gm.add_submap(sm)
+        osubs.append(o)
+    with np.errstate(all="ignore"):
+        want = vo.build_global(osubs, 0.05, exact_order=False)
+    m = gm.build_semantic_voxel_map(0.05)
+    np.testing.assert_array_equal(m.get_centers_world(), want.centers_world)
+    np.testing.assert_allclose(m.get_features(), want.features, rtol=RTOL, atol=ATOL)
+    assert m.get_contributors() == want.contributors
+    assert [st["n_fused"] for st in gm.last_build_stats][1] == 0
+    assert sorted(m.frame_name_maps) == ["0", "2"]          # map.py:282-297: only submaps that contributed points
+    # stride beyond the image: one pixel per frame survives the grid, far too few for the coarse filter
+    empty = gm.build_semantic_voxel_map(0.05, stride=1000)
+    assert empty.get_centers_world().shape == (0, 3) and empty.get_features().shape == (0, 0)
+
+
+def test_frame_limit_and_coordinate_range():
+    import torch
+    import vsm
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    dm = vm.DeviceVoxelMap(0.05, 8, N.F32)
+    H = np.eye(4)
+    pts = torch.rand((129, 2, 2, 3), device="cuda")
+    conf = torch.full((129, 2, 2), 2.0, device="cuda")
+    emb = torch.ones((129, 2, 2, 8), device="cuda")
+    with pytest.raises(ValueError, match="frames in one submap"):
+        dm.fuse(pts, conf, emb, dm.make_params(129, 2, 2, 129, 1, 1.0, H, 0, 0))
+    st = dm.fuse(pts[:128].contiguous(), conf[:128].contiguous(), emb[:128].contiguous(),
+                 dm.make_params(128, 2, 2, 128, 1, 1.0, H, 0, 0))
+    assert st["n_fused"] == 128 * 4
+    n_before = dm.num_voxels
+    far = pts[:2].clone().contiguous()
+    far[0, 0, 0, 0] = 1.0e5                                   # 2e6 cells at 5 cm: beyond +-(2^20 - 1)
+    with pytest.raises(OverflowError, match="outside"):
+        dm.fuse(far, conf[:2].contiguous(), emb[:2].contiguous(), dm.make_params(2, 2, 2, 2, 1, 1.0, H, 1, 0))
+    assert dm.num_voxels == n_before                          # the call was stopped before it touched the map
+    dm.finalize()
+    _, _, counts, _ = dm.export_geometry()
+    assert int(counts.sum()) == 128 * 4
+    dm.close()
