@@ -61,9 +61,10 @@ if rank == 0:
     si, _, ss = single.query_with_embeddings(Q, top_k=7)
     np.testing.assert_array_equal(qi, si)
     np.testing.assert_allclose(qs, ss, rtol=1e-3, atol=1e-6)
-    print(f"dist_check ok: transport={transport} world={world} voxels={V} shards={[len(p[0]) for p in parts]}")
+    print(f"dist_check ok: transport={transport} (peer broken: {bool(vdist._PEER_BROKEN)}) world={world} voxels={V} "
+          f"shards={[len(p[0]) for p in parts]}")
 dist.barrier()
-if transport == "peer":
+if transport in ("peer", "auto"):
     from vsm import peer
 
     peer.close_all()

@@ -161,6 +161,7 @@ class _Phases:
 
 
 _NAMES_CACHE: dict = {}
+_PEER_BROKEN: dict = {}  # group -> True once the peer-memory exchange has failed to set up (transport="auto")
 
 
 def _names_signature(fused) -> int:
@@ -183,12 +184,14 @@ def _sizes_all(values, group, device) -> np.ndarray:
 
 def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_closure_frames: bool = True,
                   capacity_hint: Optional[int] = None, host_streaming: Optional[bool] = None, profile: bool = False,
-                  group=None, transport: str = "peer"):
+                  group=None, transport: str = "auto"):
     """Collective multi-GPU build.  Returns (ShardedVoxelMap, this rank's per-submap fuse stats).
 
-    transport "peer" (default): voxel partials and contributor entries are pushed straight into the owners' inboxes
-    over NVLink peer memory by one kernel pass (vsm/peer.py, csrc/peer.cu); "collective": pack on the device, one
-    torch.distributed all-to-all per array, merge (works with any backend)."""
+    transport "peer": voxel partials and contributor entries are pushed straight into the owners' inboxes over
+    NVLink peer memory by one kernel pass (vsm/peer.py, csrc/peer.cu); "collective": pack on the device, one
+    torch.distributed all-to-all per array, merge (works with any backend); "auto" (default): "peer", and
+    "collective" from then on if CUDA IPC / peer access turns out not to work between the GPUs of the group (all
+    ranks learn that together)."""
     from . import voxel_map as vm
     from .map import wrap_device_map
 
@@ -203,6 +206,13 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
     d, code = dm.dim, dm.emb_dtype
     names_sigs = None
     ph.mark("fuse")
+    auto_key = id(group) if group is not None else 0
+    if transport == "auto":
+        transport = "collective" if _PEER_BROKEN.get(auto_key) else "peer"
+        fall_back = True
+    else:
+        fall_back = False
+    ex = None
     if transport == "peer":
         from . import peer
 
@@ -215,7 +225,14 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         need_rows = min(tot_v, int(1.25 * tot_v / world) + (1 << 16)) + 1
         need_contrib = min(tot_c, int(1.25 * tot_c / world) + (1 << 16)) + 1
         ph.mark("sizes")
-        ex = peer.exchange_for(dev, d, need_rows, need_contrib, group)
+        try:
+            ex = peer.exchange_for(dev, d, need_rows, need_contrib, group)
+        except peer.PeerUnavailable:
+            if not fall_back:
+                raise
+            _PEER_BROKEN[auto_key] = True
+            transport = "collective"
+    if transport == "peer":
         ex.push(dm)
         ph.mark("push")
         owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=ex.cap_rows, device=dev)
@@ -223,7 +240,7 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         ph.mark("drain")
         dm.close()
         ph.mark("close")
-    elif transport == "collective":
+    if transport == "collective":
         # ---- voxels -> owners ------------------------------------------------------
         keys, counts, sums, send = dm.partials_pack(world)
         recv = exchange_counts(send.tolist(), group, dev)
@@ -242,7 +259,7 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         owner.partials_merge(r_keys, r_counts, r_sums)
         owner.contrib_merge(rc_keys, rc_subs, rc_masks)
         del r_keys, r_counts, r_sums
-    else:
+    if transport not in ("peer", "collective"):
         raise ValueError(f"unknown transport {transport!r}")
     owner.finalize()
     ph.mark("finalize")

@@ -7,6 +7,7 @@ the owner drains its inbox on its own stream.  torch.distributed is used once, t
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -27,6 +28,8 @@ class Inbox:
     def __init__(self, device: torch.device, dim: int, cap_rows: int, cap_contrib: int, shared: bool = True):
         self.device, self.dim, self.cap_rows, self.cap_contrib = device, int(dim), int(cap_rows), int(cap_contrib)
         self.bytes = inbox_bytes(dim, cap_rows, cap_contrib)
+        if shared and os.environ.get("VSM_PEER_DISABLE") == "1":  # e.g. containers that must not use CUDA IPC
+            raise RuntimeError("peer-memory exchange disabled by VSM_PEER_DISABLE=1")
         ptr = C.c_void_p()
         buf = (C.c_uint8 * 64)()
         N.check(N.lib.vsm_peer_alloc(device.index or 0, self.bytes, C.byref(ptr), buf if shared else None))
@@ -66,6 +69,10 @@ def drain(owner, inbox_ptr: int, world: int, cap_rows: int, cap_contrib: int, ep
     return int(n_rows.value), int(n_contrib.value)
 
 
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC / peer access does not work between the GPUs of this group (raised on EVERY rank)."""
+
+
 class PeerExchange:
     """The inboxes of a process group (one node, one process per GPU), mapped into this process."""
 
@@ -75,20 +82,36 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         self.cap_rows, self.cap_contrib = int(cap_rows), int(cap_contrib)
         self.epoch = 0
-        self.mine = Inbox(device, dim, cap_rows, cap_contrib, shared=True)
-        handles: List[Optional[bytes]] = [None] * self.world
-        dist.all_gather_object(handles, self.mine.handle, group=group)
         self.ptrs: List[int] = []
         self._opened: List[int] = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.ptrs.append(self.mine.ptr)
-                continue
-            p = C.c_void_p()
-            hb = (C.c_uint8 * 64).from_buffer_copy(h)
-            N.check(N.lib.vsm_peer_open(device.index or 0, hb, C.byref(p)))
-            self.ptrs.append(int(p.value))
-            self._opened.append(int(p.value))
+        self.mine = None
+        err = None
+        try:
+            self.mine = Inbox(device, dim, cap_rows, cap_contrib, shared=True)
+        except Exception as e:  # e.g. no CUDA IPC in this environment
+            err = e
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, None if self.mine is None else self.mine.handle, group=group)
+        if err is None and all(h is not None for h in handles):
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        self.ptrs.append(self.mine.ptr)
+                        continue
+                    p = C.c_void_p()
+                    hb = (C.c_uint8 * 64).from_buffer_copy(h)
+                    N.check(N.lib.vsm_peer_open(device.index or 0, hb, C.byref(p)))
+                    self.ptrs.append(int(p.value))
+                    self._opened.append(int(p.value))
+            except Exception as e:  # no peer access between some pair of GPUs
+                err = e
+        # every rank must reach the same verdict: one failure anywhere makes the exchange unusable everywhere
+        oks: List[Optional[bool]] = [None] * self.world
+        dist.all_gather_object(oks, err is None and all(h is not None for h in handles), group=group)
+        if not all(oks):
+            self.close()
+            raise PeerUnavailable(f"peer-memory exchange unavailable on rank(s) {[r for r, ok in enumerate(oks) if not ok]}"
+                                  + (f": {err}" if err is not None else ""))
 
     def push(self, dm) -> None:
         push(dm, self.ptrs, self.cap_rows, self.cap_contrib, self.epoch)
@@ -106,7 +129,8 @@ class PeerExchange:
             N.lib.vsm_peer_close(self.device.index or 0, C.c_void_p(p))
         self._opened = []
         dist.barrier(group=self.group)
-        self.mine.free()
+        if self.mine is not None:
+            self.mine.free()
 
 
 _EXCHANGES: dict = {}
