@@ -135,6 +135,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same, naming the registers an earlier tcgen05.ld fills: the compiler must not read them before this point
+__device__ __forceinline__ void tmem_ld_wait_for(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B (8-row x 128-byte atoms, 1024 bytes apart along M/N)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -188,6 +198,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bfull + 1);
   __shared__ float2 s_col[TN];  // per prompt column: (||q_p||, threshold T_p); padding columns can never pass
   __shared__ unsigned long long s_stage[4 * C::kMH][kWarpStage];  // candidates staged per epilogue warp
+  __shared__ uint32_t s_wcnt[4 * C::kMH];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_tiles = (a.n_rows + C::kTileRows - 1) / C::kTileRows;
@@ -274,69 +285,79 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int mh = (warp - 4) >> 2;  // which M=128 half of the tile
     // A candidate costs a slot in the global list.  Reserving it with a global atomic per hit stalls the warp for a
     // full round trip per candidate (measured: the epilogue of a 256-prompt tile took longer than its MMAs), so
-    // each warp stages its hits in shared memory (positions from a ballot, no atomics) and appends ~100 at a time.
+    // each warp stages its hits in shared memory (a shared-memory counter) and appends ~64 at a time.
     unsigned long long* wbuf = s_stage[warp - 4];
-    uint32_t wn = 0;  // staged entries (warp-uniform)
+    uint32_t* wcnt = &s_wcnt[warp - 4];  // staged entries of this warp
+    if (lane == 0) *wcnt = 0u;
+    __syncwarp();
     auto flush = [&]() {
+      __syncwarp();
+      const uint32_t wn = min(*wcnt, (uint32_t)kWarpStage);
       if (wn) {
-        __syncwarp();
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(a.pair_cnt, wn);
         base = __shfl_sync(0xffffffffu, base, 0);
         for (uint32_t i = lane; i < wn; i += 32)
           if (base + i < a.pair_cap) a.pairs[base + i] = wbuf[i];
-        wn = 0;
-        __syncwarp();
       }
+      __syncwarp();
+      if (lane == 0) *wcnt = 0u;
+      __syncwarp();
     };
     uint32_t acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const uint32_t row = tile * C::kTileRows + mh * kTileM + ew * 32 + lane;
       const uint32_t id = row * a.row_stride;
-      float inv = 0.f, fn = 0.f, nrm = 0.f;
+      float inv = 0.f, fn = 0.f;
       const bool valid = row < a.n_rows;
       if (valid) {
         const float cnt = (float)a.vcount[id];
-        nrm = a.vnorm[id];
+        const float nrm = a.vnorm[id];
         fn = __fdiv_rn(nrm, cnt);  // ||f_v||
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
-        if (a.normalize) fn = 1.0f;  // scored quantity is f/||f||: unit norm
+        if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;  // scored quantity is f/||f||: unit norm (NaN sums stay NaN)
       }
       const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
-      // rows with non-finite sums (NaN scores rank first in torch.topk) always take the exact per-column path
-      const bool special = !(fabsf(nrm) <= 3.402823466e38f) || !(fabsf(fn) <= 3.402823466e38f) || !(fabsf(inv) <= 3.402823466e38f);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * C::kMH + mh) * TN;
+      const int n_chunks = min(TN, (a.pb + 31) & ~31) / 32;  // columns beyond the pass's prompts are padding
+      // keep (v, p) iff  x = a(v,p)/count + margin_v * ||q_p|| - T_p  is not < 0 (a NaN passes, like torch.topk ranks it
+      // first).  Per score: one shared-memory read, two FMAs, one compare, one bit into the lane's hit mask.  Hits are
+      // rare (< 1e-3): the set bits are walked afterwards, each taking a slot of the warp's staging buffer.  The next
+      // chunk's accumulators are already on their way from tensor memory while this one is tested.
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        if (c0 >= a.pb) break;  // columns beyond the pass's prompts are padding
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        tmem_ld_wait();
-        // keep (v, p) iff  x = a(v,p)/count + margin_v * ||q_p|| - T_p  is not < 0.  Hits are rare (< 1e-3), so the
-        // 32 columns are first reduced to one maximum: 3 instructions and one shared-memory read per score
-        float mx = __int_as_float(0xff800000);
+      for (int c = 0; c < n_chunks; c += 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float2 c = s_col[c0 + j];
-          mx = fmaxf(mx, fmaf(__uint_as_float(r[j]), inv, fmaf(margin, c.x, -c.y)));
-        }
-        const bool go = valid && (special || mx >= 0.f);
-        if (__any_sync(0xffffffffu, go)) {
+        for (int h = 0; h < 2; ++h) {
+          if (c + h >= n_chunks) break;  // warp-uniform
+          tmem_ld_wait_for(r[h]);
+          if (c + h + 1 < n_chunks) tmem_ld32(taddr + (c + h + 1) * 32, r[h ^ 1]);
+          const int c0 = (c + h) * 32;
+          uint32_t hits = 0u;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float2 c = s_col[c0 + j];
-            const float x = fmaf(__uint_as_float(r[j]), inv, fmaf(margin, c.x, -c.y));
-            const bool hit = go && (c0 + j < a.pb) && !(x < 0.f);  // also keeps NaN
-            const unsigned v = __ballot_sync(0xffffffffu, hit);
-            if (v) {
-              if (hit)
-                wbuf[wn + __popc(v & ((1u << lane) - 1u))] = ((unsigned long long)(uint32_t)(a.p0 + c0 + j) << 32) | id;
-              wn += __popc(v);
-              if (wn > (uint32_t)(kWarpStage - 32)) flush();
+            const float2 col = s_col[c0 + j];
+            const float x = fmaf(__uint_as_float(r[h][j]), inv, fmaf(margin, col.x, -col.y));
+            hits |= (!(x < 0.f)) ? (1u << j) : 0u;
+          }
+          if (!valid) hits = 0u;
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const unsigned long long e = ((unsigned long long)(uint32_t)(a.p0 + c0 + j) << 32) | id;
+            const uint32_t pos = atomicAdd(wcnt, 1u);
+            if (pos < (uint32_t)kWarpStage) {
+              wbuf[pos] = e;
+            } else {  // staging buffer full (dense ties): straight to the list
+              const uint32_t g = atomicAdd(a.pair_cnt, 1u);
+              if (g < a.pair_cap) a.pairs[g] = e;
             }
           }
+          __syncwarp();
+          if (*wcnt > (uint32_t)(kWarpStage / 2)) flush();  // warp-uniform: every lane reads the same counter
         }
       }
       tc_fence_before();
