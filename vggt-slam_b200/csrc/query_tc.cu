@@ -44,12 +44,16 @@ constexpr int kWarpStage = 128;  // candidates an epilogue warp stages in shared
 template <int TN>
 struct Cfg {
   static constexpr bool kStream = TN > 64;                      // prompt slices travel with the voxel stages
-  static constexpr int kMH = kStream ? 2 : 1;                   // M=128 halves per tile
+  // (build with -DVSM_TC256_MH=1 for 128-voxel, double-buffered tiles at 256 prompts: measured the same 6.6 ms per call)
+#ifndef VSM_TC256_MH
+#define VSM_TC256_MH 2
+#endif
+  static constexpr int kMH = !kStream ? 1 : (TN == 256 ? VSM_TC256_MH : 2);  // M=128 halves per tile
   static constexpr int kTileRows = kMH * kTileM;
   static constexpr uint32_t kABytes = kMH * kHalfBytes;
   static constexpr uint32_t kBChunkBytes = TN * kChunkK * 4;    // one 32-channel slice of the prompt block
   static constexpr uint32_t kStageBytes = kABytes + (kStream ? kBChunkBytes : 0u);
-  static constexpr int kStages = !kStream ? 4 : (TN == 128 ? 4 : 3);
+  static constexpr int kStages = !kStream ? 4 : (TN == 128 ? 4 : (kMH == 2 ? 3 : 4));
   static constexpr int kAccBufs = (2 * kMH * TN <= 512) ? 2 : 1;  // accumulator sets in the 512 TMEM columns
   static constexpr int kTmemCols = kAccBufs * kMH * TN;
   static constexpr int kThreads = 128 + 128 * kMH;              // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4.. epilogue
@@ -517,7 +521,7 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   uint32_t* pair_cnt = sc.cand_cnt + P;
   const uint32_t pair_cap = (uint32_t)std::min<uint64_t>((uint64_t)P * sc.cap, 0xFFFFFFFFull);
   CUtensorMap map_a, map_b;
-  const uint32_t tile_rows = tile_n == 64 ? Cfg<64>::kTileRows : Cfg<256>::kTileRows;
+  const uint32_t tile_rows = tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows);
   VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, tile_rows, (uint64_t)stride * d));
   VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)tile_n));
   int n_sm = 148;
