@@ -509,14 +509,17 @@ struct Scratch {
 };
 
 // One level: tensor-core pass over the voxel rows 0, stride, 2*stride, ... (n_rows of them) with the thresholds in
-// sc.thr, exact re-scoring of the candidates, top-k.  *fell_back is set (and nothing written) when a candidate list
-// overflowed or came up short.
+// sc.thr, exact re-scoring of the candidates, top-k.  fell_back != null (the level that answers the query): the
+// candidate counts are read back (the level's one synchronisation) and *fell_back is set, nothing written, when a
+// list overflowed or came up short.  fell_back == null (a level that only produces thresholds): nothing is read back
+// -- whatever subset of candidates survived an overflow, the k-th best of their EXACT scores is still a valid lower
+// bound, and a list shorter than k yields NaN = "keep everything" downstream.
 static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize, uint32_t stride, uint32_t n_rows,
                     const Scratch& sc, int tile_n, size_t smem, int64_t* idx_dev, float* score_dev, bool* fell_back,
                     cudaStream_t s) {
   const int d = m->d;
   const int n_kchunks = d / kChunkK;
-  *fell_back = false;
+  if (fell_back) *fell_back = false;
   VSM_CUDA(cudaMemsetAsync(sc.cand_cnt, 0, (size_t)(P + 1) * 4, s));
   uint32_t* pair_cnt = sc.cand_cnt + P;
   const uint32_t pair_cap = (uint32_t)std::min<uint64_t>((uint64_t)P * sc.cap, 0xFFFFFFFFull);
@@ -558,17 +561,19 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   rescore_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
                                          normalize, sc.pairs, pair_cnt, pair_cap, sc.cand_cnt, sc.cap, sc.keys);
   VSM_LAUNCHED();
-  std::vector<uint32_t> h_cnt(P + 1);
-  VSM_TRY(read_back(m, h_cnt.data(), sc.cand_cnt, (size_t)(P + 1) * 4, s));  // the one synchronisation of a level
-  uint32_t mx = 0, mn = 0xFFFFFFFFu;
-  for (int p = 0; p < P; ++p) {
-    mx = std::max(mx, h_cnt[p]);
-    mn = std::min(mn, h_cnt[p]);
-  }
-  m->tc_last_candidates = mx;
-  if (h_cnt[P] > pair_cap || mx > sc.cap || mn < (uint32_t)k) {
-    *fell_back = true;  // a list overflowed (dense ties) -- or, impossibly, lost candidates
-    return VSM_OK;
+  if (fell_back) {
+    std::vector<uint32_t> h_cnt(P + 1);
+    VSM_TRY(read_back(m, h_cnt.data(), sc.cand_cnt, (size_t)(P + 1) * 4, s));  // the one synchronisation of a query
+    uint32_t mx = 0, mn = 0xFFFFFFFFu;
+    for (int p = 0; p < P; ++p) {
+      mx = std::max(mx, h_cnt[p]);
+      mn = std::min(mn, h_cnt[p]);
+    }
+    m->tc_last_candidates = mx;
+    if (h_cnt[P] > pair_cap || mx > sc.cap || mn < (uint32_t)k) {
+      *fell_back = true;  // a list overflowed (dense ties) -- or, impossibly, lost candidates
+      return VSM_OK;
+    }
   }
   return query_select_from_keys(m, sc.keys, sc.cand_cnt, P, (int)sc.cap, k, idx_dev, score_dev, s);
 }
@@ -642,14 +647,10 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
     // tensor-core launch instead of P/8 passes of the exact engine
     prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 0, sc.qnorm, sc.thr);
     VSM_LAUNCHED();
-    bool fell_back = false;
-    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_c, n_c, sc, tile_n, smem, sc.sidx, sc.ssc, &fell_back, s));
-    if (fell_back) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_c, n_c, sc.sidx, sc.ssc, s));
+    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_c, n_c, sc, tile_n, smem, sc.sidx, sc.ssc, nullptr, s));
     prompt_prep_kernel<<<(P + 63) / 64, 64, 0, s>>>(q_dev, P, d, sc.ssc, k, 1, sc.qnorm, sc.thr);
     VSM_LAUNCHED();
-    fell_back = false;
-    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_b, n_b, sc, tile_n, smem, sc.sidx, sc.ssc, &fell_back, s));
-    if (fell_back) VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_b, n_b, sc.sidx, sc.ssc, s));
+    VSM_TRY(tc_level(m, q_dev, P, k, normalize, stride_b, n_b, sc, tile_n, smem, sc.sidx, sc.ssc, nullptr, s));
     have_sample = 1;
   } else if (n_b >= (uint32_t)k && stride_b > 1) {
     VSM_TRY(query_exact_rows(m, q_dev, P, k, normalize, stride_b, n_b, sc.sidx, sc.ssc, s));
