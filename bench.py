@@ -11,7 +11,9 @@ the three outlier filters on) + finalisation.  Synthetic inputs (vsm.synth_devic
              finished map (centres + features) back device->host
   roofline   accumulate kernel: algorithmic bytes / CUDA-event time (events recorded inside libvsm on the
              launching stream) against MEASURED_PEAKS.json's HBM copy bandwidth
-  cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample, 1 core
+  cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample, 1 core (the path is
+                single-threaded numpy); cpu_baseline.parallel: as many independent copies as the host has cores
+                (up to 16), each on its own submap, started together -- an extra figure, not the baseline
 
 `--impl reference` times that CPU port alone (the reference arm).  N>1 (torchrun): every rank fuses its own
 20 submaps (weak scaling), then voxels are exchanged by key-hash owner with an NCCL all-to-all and merged.
@@ -58,6 +60,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-submaps", type=int, default=-1, help="-1: all")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one submap in the CPU sample")
+    ap.add_argument("--cpu-procs", type=int, default=min(os.cpu_count() or 1, 16),
+                    help="also run this many independent copies of the CPU port at once (cpu_baseline.parallel); 1: skip")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--query", action="store_true", help="also report query latency on the built map")
@@ -199,13 +203,61 @@ def cpu_run_once(sm, voxel_size):
     return out.n_points, dt
 
 
+_WORKER_SAMPLE = None
+
+
+def _cpu_worker_init(frames, height, width, dim, voxel_size, root):
+    """Spawned worker: its own sample submap (numpy generator), held in a global."""
+    global _WORKER_SAMPLE
+    for p in (root, os.path.join(root, "vggt-slam_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
+    from vsm import synth
+    from oracle import voxel_oracle as vo
+
+    s = synth.make_submap(1234, os.getpid() % 1000, S=frames, H=height, W=width, d=dim, mode="sl4", room=(12.0, 8.0, 3.0))
+    fids = [vo.frame_id_from_name(p) for p in s.frame_paths]
+    names = {str(f): p for f, p in zip(fids, s.frame_paths)}
+    _WORKER_SAMPLE = (vo.OracleSubmap(0, s.points, s.conf, vo.conf_threshold(s.conf, 25.0), s.emb, s.H_world_map, fids,
+                                      names, frames - 1), voxel_size)
+
+
+def _cpu_worker_run(_):
+    sm, vs = _WORKER_SAMPLE
+    return cpu_run_once(sm, vs)
+
+
+def cpu_parallel(args, procs):
+    """`procs` independent copies of the CPU port, each on its own sample submap, started together: what the host
+    reaches when the (single-threaded) reference path is simply run once per core."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs, initializer=_cpu_worker_init,
+                  initargs=(args.cpu_frames, args.height, args.width, args.dim, args.voxel_size, ROOT)) as pool:
+        pool.map(_cpu_worker_run, range(procs), chunksize=1)          # warm-up (page faults, imports)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker_run, range(procs), chunksize=1)
+        wall = time.perf_counter() - t0
+    n = sum(r[0] for r in res)
+    return {"procs": procs, "value": n / wall, "unit": UNIT, "wall_s": wall, "points": int(n)}
+
+
 def cpu_baseline(args):
     sm = cpu_sample_inputs(args)
     n, dt = cpu_run_once(sm, args.voxel_size)
-    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32, "
-                      f"{n} points fused in {dt:.1f} s by the numpy oracle (np.unique + np.add.at are single-threaded)",
-            "host_cpus": os.cpu_count()}
+    out = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32, "
+                     f"{n} points fused in {dt:.1f} s by the numpy oracle (np.unique + np.add.at are single-threaded)",
+           "host_cpus": os.cpu_count()}
+    if args.cpu_procs > 1:
+        try:
+            del sm
+            out["parallel"] = cpu_parallel(args, args.cpu_procs)
+        except Exception as e:  # an extra, never the headline
+            out["parallel"] = {"error": repr(e)}
+    return out
 
 
 def run_reference_arm(args):
@@ -231,6 +283,12 @@ def run_reference_arm(args):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.cpu_procs > 1:
+        try:
+            del sm
+            line["cpu_baseline"]["parallel"] = cpu_parallel(args, args.cpu_procs)
+        except Exception as e:
+            line["cpu_baseline"]["parallel"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 

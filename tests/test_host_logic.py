@@ -119,7 +119,7 @@ def test_lazy_containers():
 def test_bench_reference_arm_runs_on_cpu():
     """`bench.py --impl reference` times the oracle port and prints ONE json line with the contract's keys."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                          "--frames", "2", "--cpu-frames", "2", "--height", "28", "--width", "42", "--dim", "16", "--voxel-size", "0.5"],
+                          "--frames", "2", "--cpu-frames", "2", "--height", "28", "--width", "42", "--dim", "16", "--voxel-size", "0.5", "--cpu-procs", "2"],
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
@@ -128,6 +128,8 @@ def test_bench_reference_arm_runs_on_cpu():
     assert j["impl"] == "reference" and j["metric"] == "points fused/sec" and j["unit"] == "points/s"
     assert j["value"] > 0 and j["higher_is_better"] is True and j["gpu_launches"] == 0
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] == 1
+    par = j["cpu_baseline"]["parallel"]              # independent copies of the port, one per core (an extra figure)
+    assert par["procs"] >= 1 and par["value"] > 0 and par["unit"] == "points/s"
     assert j["e2e"] == {"value": j["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
