@@ -74,7 +74,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
+  uint32_t spins = 0;
   do {
+    if (++spins == 0x20000000u) __trap();  // minutes of polling: a protocol error must not hang the GPU
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -95,6 +97,60 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// ---- CTA pairs (cta_group::2): two SMs execute one MMA of M = 256; every barrier the MMA thread waits on lives in the
+// leader CTA (rank 0).  Shared-memory addresses of the two CTAs of a pair differ in bit 24: clearing it names the
+// leader's copy of a variable from either CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// both CTAs of the pair issue their own loads; the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T with M = 256: each CTA supplies its 128 rows of A and its half of B's rows
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrives, when the pair's MMAs issued so far are done, on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -161,8 +217,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return d;
 }
 // instruction descriptor: D=F32, A=B=TF32, both K-major, N=tile_n, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int tile_n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int tile_n, int tile_m = kTileM) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
 }
 
 struct TcArgs {
@@ -379,6 +435,198 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// ---- 256 prompts on CTA pairs ------------------------------------------------------------------------------------
+// One tile = 256 voxels x 256 prompts on TWO SMs: each CTA stages its 128 voxels and its 128 prompts (its half of
+// the prompt slice: half the L2 reads, half the shared-memory operand traffic per SM), the leader's elected thread
+// issues tcgen05.mma.cta_group::2 (M = 256), each CTA's tensor memory receives its 128 rows x 256 columns -- which
+// leaves room for TWO accumulator sets, so the epilogue of tile t overlaps the MMAs of tile t+1 again.
+namespace pairk {
+constexpr int kTN = 256;
+constexpr int kStages = 6;
+constexpr uint32_t kABytes = kHalfBytes;                    // my 128 voxels x 32 channels
+constexpr uint32_t kBBytes = (kTN / 2) * kChunkK * 4;       // my 128 prompts x 32 channels
+constexpr uint32_t kStageBytes = kABytes + kBBytes;         // 32 KB per CTA and stage
+constexpr int kThreads = 256;                               // warp 0 TMA, 1 MMA (leader), 2 TMEM alloc, 4..7 epilogue
+constexpr int kTmemCols = 2 * kTN;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
+}  // namespace pairk
+
+__global__ void __launch_bounds__(pairk::kThreads, 1)
+query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
+  using namespace pairk;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages] both producers -> leader's MMA thread (leader's copy is used)
+  uint64_t* empty = bars + kStages;      // [kStages] MMA -> the producer of this CTA
+  uint64_t* tfull = bars + 2 * kStages;  // [2] MMA -> the epilogue of this CTA
+  uint64_t* tempty = tfull + 2;          // [2] both epilogues -> leader's MMA thread (leader's copy is used)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tempty + 2);
+  __shared__ float2 s_col[kTN];
+  __shared__ unsigned long long s_stage[4][kWarpStage];
+  __shared__ uint32_t s_wcnt[4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t n_tiles = (a.n_rows + 2 * kTileM - 1) / (2 * kTileM);
+  const uint32_t pair0 = blockIdx.x >> 1, pair_step = gridDim.x >> 1;
+
+  for (int i = threadIdx.x; i < kTN; i += kThreads)
+    s_col[i] = i < a.pb ? make_float2(a.qnorm[i], a.thr[i]) : make_float2(0.f, __int_as_float(0x7f800000));
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 2);   // one arrive.expect_tx per producer of the pair
+      mbar_init(&empty[i], 1);  // the pair's commit, multicast to both CTAs
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // four epilogue warps in each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers and tensor memory exist before anything is signalled across
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer (both CTAs) =====
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = pair0; tile < n_tiles; tile += pair_step) {
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const uint32_t lfull = smem_u32(&full[stage]) & kPeerBitMask;
+        mbar_expect_tx_cluster(lfull, kStageBytes);
+        uint8_t* st = smem + (size_t)stage * kStageBytes;
+        tma_load_2d_pair(st, &map_a, lfull, kc * kChunkK, (int)(tile * 2 * kTileM + crank * kTileM));
+        tma_load_2d_pair(st + kABytes, &map_b, lfull, kc * kChunkK, (int)(crank * (kTN / 2)));
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && crank == 0) {
+    // ===== MMA issuer (leader CTA only) =====
+    constexpr uint32_t idesc = make_idesc(kTN, 2 * kTileM);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (uint32_t tile = pair0; tile < n_tiles; tile += pair_step) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator set
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * kTN;
+      for (int kc = 0; kc < a.n_kchunks; ++kc) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        uint8_t* st = smem + (size_t)stage * kStageBytes;
+        const uint64_t adesc = make_smem_desc(smem_u32(st));
+        const uint64_t bdesc = make_smem_desc(smem_u32(st + kABytes));
+#pragma unroll
+        for (int k = 0; k < kChunkK / 8; ++k)
+          mma_tf32_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        mma_commit_pair(&empty[stage], 3);  // both producers may refill this stage
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      mma_commit_pair(&tfull[acc], 3);  // both epilogues may read this accumulator set
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): as query_tc_kernel's, on this CTA's 128 rows =====
+    const int ew = warp & 3;
+    unsigned long long* wbuf = s_stage[warp - 4];
+    uint32_t* wcnt = &s_wcnt[warp - 4];
+    if (lane == 0) *wcnt = 0u;
+    __syncwarp();
+    auto flush = [&]() {
+      __syncwarp();
+      const uint32_t wn = min(*wcnt, (uint32_t)kWarpStage);
+      if (wn) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.pair_cnt, wn);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < wn; i += 32)
+          if (base + i < a.pair_cap) a.pairs[base + i] = wbuf[i];
+      }
+      __syncwarp();
+      if (lane == 0) *wcnt = 0u;
+      __syncwarp();
+    };
+    uint32_t acc = 0, acc_phase = 0;
+    for (uint32_t tile = pair0; tile < n_tiles; tile += pair_step) {
+      const uint32_t row = tile * 2 * kTileM + crank * kTileM + ew * 32 + lane;
+      const uint32_t id = row * a.row_stride;
+      float inv = 0.f, fn = 0.f;
+      const bool valid = row < a.n_rows;
+      if (valid) {
+        const float cnt = (float)a.vcount[id];
+        const float nrm = a.vnorm[id];
+        fn = __fdiv_rn(nrm, cnt);
+        inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
+        if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;
+      }
+      const float margin = 3.0f * 0.00390625f * fn;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kTN;
+      const int n_chunks = min(kTN, (a.pb + 31) & ~31) / 32;
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; c += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c + h >= n_chunks) break;
+          tmem_ld_wait_for(r[h]);
+          if (c + h + 1 < n_chunks) tmem_ld32(taddr + (c + h + 1) * 32, r[h ^ 1]);
+          const int c0 = (c + h) * 32;
+          uint32_t hits = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 col = s_col[c0 + j];
+            const float x = fmaf(__uint_as_float(r[h][j]), inv, fmaf(margin, col.x, -col.y));
+            hits |= (!(x < 0.f)) ? (1u << j) : 0u;
+          }
+          if (!valid) hits = 0u;
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const unsigned long long e = ((unsigned long long)(uint32_t)(a.p0 + c0 + j) << 32) | id;
+            const uint32_t pos = atomicAdd(wcnt, 1u);
+            if (pos < (uint32_t)kWarpStage) {
+              wbuf[pos] = e;
+            } else {
+              const uint32_t g = atomicAdd(a.pair_cnt, 1u);
+              if (g < a.pair_cap) a.pairs[g] = e;
+            }
+          }
+          __syncwarp();
+          if (*wcnt > (uint32_t)(kWarpStage / 2)) flush();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty[acc]) & kPeerBitMask);  // the leader's copy
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees tensor memory) while the peer may still use the pair's resources
+  if (warp == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------------------
 // ||sum_v||_2 per voxel id (one warp per row)
 __global__ void __launch_bounds__(256) row_norm_kernel(const float* __restrict__ vsum, uint32_t V, int d, float* __restrict__ out) {
@@ -524,13 +772,18 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   uint32_t* pair_cnt = sc.cand_cnt + P;
   const uint32_t pair_cap = (uint32_t)std::min<uint64_t>((uint64_t)P * sc.cap, 0xFFFFFFFFull);
   CUtensorMap map_a, map_b;
-  const uint32_t tile_rows = tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows);
-  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, tile_rows, (uint64_t)stride * d));
-  VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)tile_n));
+  static const bool use_pair = !(getenv("VSM_TC_PAIR") && getenv("VSM_TC_PAIR")[0] == '0');
+  const bool pair = tile_n == 256 && use_pair;  // 256 prompts: CTA pairs (cta_group::2)
+  const uint32_t tile_rows = pair ? 2 * kTileM
+                                  : (tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows));
+  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, pair ? kTileM : tile_rows, (uint64_t)stride * d));
+  VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)(pair ? tile_n / 2 : tile_n)));
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   const uint32_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
-  const int grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
+  const int grid = pair ? 2 * (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm / 2) : (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
+  if (pair)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairk::kSmemBytes));
   for (int p0 = 0; p0 < P; p0 += tile_n) {
     const int pb = std::min(tile_n, P - p0);
     pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, sc.qpad);
@@ -553,8 +806,23 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
       query_tc_kernel<64><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
     else if (tile_n == 128)
       query_tc_kernel<128><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
-    else
+    else if (!pair)
       query_tc_kernel<256><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
+    else {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(pairk::kThreads);
+      cfg.dynamicSmemBytes = pairk::kSmemBytes;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel, map_a, map_b, a));
+    }
     VSM_LAUNCHED();
   }
   // the list's length lives on the device: a fixed grid strides over it
