@@ -435,25 +435,29 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-// ---- 256 prompts on CTA pairs ------------------------------------------------------------------------------------
-// One tile = 256 voxels x 256 prompts on TWO SMs: each CTA stages its 128 voxels and its 128 prompts (its half of
+// ---- 128 / 256 prompts on CTA pairs ------------------------------------------------------------------------------------
+// One tile = 256 voxels x TN prompts on TWO SMs: each CTA stages its 128 voxels and TN/2 prompts (its half of
 // the prompt slice: half the L2 reads, half the shared-memory operand traffic per SM), the leader's elected thread
 // issues tcgen05.mma.cta_group::2 (M = 256), each CTA's tensor memory receives its 128 rows x 256 columns -- which
 // leaves room for TWO accumulator sets, so the epilogue of tile t overlaps the MMAs of tile t+1 again.
-namespace pairk {
-constexpr int kTN = 256;
-constexpr int kStages = 6;
-constexpr uint32_t kABytes = kHalfBytes;                    // my 128 voxels x 32 channels
-constexpr uint32_t kBBytes = (kTN / 2) * kChunkK * 4;       // my 128 prompts x 32 channels
-constexpr uint32_t kStageBytes = kABytes + kBBytes;         // 32 KB per CTA and stage
-constexpr int kThreads = 256;                               // warp 0 TMA, 1 MMA (leader), 2 TMEM alloc, 4..7 epilogue
-constexpr int kTmemCols = 2 * kTN;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
-}  // namespace pairk
+template <int TN>
+struct PairCfg {
+  static constexpr int kTN = TN;                                     // prompts per pass: 128 or 256
+  static constexpr uint32_t kABytes = kHalfBytes;                    // my 128 voxels x 32 channels
+  static constexpr uint32_t kBBytes = (TN / 2) * kChunkK * 4;        // my half of the prompts x 32 channels
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;         // 32 / 24 KB per CTA and stage
+  static constexpr int kStages = TN == 256 ? 6 : 8;
+  static constexpr int kThreads = 256;  // warp 0 TMA, 1 MMA (leader), 2 TMEM alloc, 4..7 epilogue
+  static constexpr int kTmemCols = 2 * TN;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
+};
 
-__global__ void __launch_bounds__(pairk::kThreads, 1)
+template <int TN>
+__global__ void __launch_bounds__(256, 1)
 query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
-  using namespace pairk;
+  using PC = PairCfg<TN>;
+  constexpr int kTN = PC::kTN, kStages = PC::kStages, kThreads = PC::kThreads, kTmemCols = PC::kTmemCols;
+  constexpr uint32_t kABytes = PC::kABytes, kStageBytes = PC::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
   uint64_t* full = bars;                 // [kStages] both producers -> leader's MMA thread (leader's copy is used)
@@ -773,7 +777,9 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   const uint32_t pair_cap = (uint32_t)std::min<uint64_t>((uint64_t)P * sc.cap, 0xFFFFFFFFull);
   CUtensorMap map_a, map_b;
   static const bool use_pair = !(getenv("VSM_TC_PAIR") && getenv("VSM_TC_PAIR")[0] == '0');
-  const bool pair = tile_n == 256 && use_pair;  // 256 prompts: CTA pairs (cta_group::2)
+  // 256 prompts: CTA pairs (cta_group::2).  At 128 prompts the pair kernel measured slower than the single-CTA one
+  // (4.71 vs 4.61 ms per call at 10 M voxels): that pass is closer to the HBM roof than to the tensor roof.
+  const bool pair = tile_n == 256 && use_pair;
   const uint32_t tile_rows = pair ? 2 * kTileM
                                   : (tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows));
   VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, pair ? kTileM : tile_rows, (uint64_t)stride * d));
@@ -782,8 +788,9 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   const uint32_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
   const int grid = pair ? 2 * (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm / 2) : (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
+  const size_t pair_smem = PairCfg<256>::kSmemBytes;
   if (pair)
-    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pairk::kSmemBytes));
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
   for (int p0 = 0; p0 < P; p0 += tile_n) {
     const int pb = std::min(tile_n, P - p0);
     pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, sc.qpad);
@@ -804,15 +811,15 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
     a.n_kchunks = n_kchunks;
     if (tile_n == 64)
       query_tc_kernel<64><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
-    else if (tile_n == 128)
+    else if (!pair && tile_n == 128)
       query_tc_kernel<128><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
     else if (!pair)
       query_tc_kernel<256><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
     else {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)grid);
-      cfg.blockDim = dim3(pairk::kThreads);
-      cfg.dynamicSmemBytes = pairk::kSmemBytes;
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = pair_smem;
       cfg.stream = s;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -821,7 +828,7 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel, map_a, map_b, a));
+      VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel<256>, map_a, map_b, a));
     }
     VSM_LAUNCHED();
   }
