@@ -13,8 +13,8 @@
 // TF32 drops mantissa bits, so the tensor-core scores only SELECT candidates, conservatively:
 //   1. thresholds: the exact fp32 engine scores a strided sample of the voxels; the k-th best sample score T_p is
 //      a lower bound of the k-th best score overall;
-//   2. the tensor-core pass keeps voxel v for prompt p if  a(v,p) + 3*eps(v,p) >= T_p  with
-//      eps = 2^-8 * ||f_v|| * ||q_p||  (>= the TF32 product error summed over d channels, Cauchy-Schwarz);
+//   2. the tensor-core pass keeps voxel v for prompt p if  a(v,p) + 1.5 * 2^-9 * ||f_v|| * ||q_p|| >= T_p  (2^-9 ||f|| ||q||
+//      bounds the TF32 product error summed over d channels, Cauchy-Schwarz; see kTf32Margin);
 //   3. the candidates are re-scored exactly in fp32 and the top-k taken with the same keys as engine 1.
 // The result is therefore identical to engine 1 (vggt_slam/semantic_voxel.py:97-116 semantics).  If a candidate
 // list overflows, the call falls back to engine 1.
@@ -37,6 +37,10 @@ constexpr int kTileM = 128;      // voxels per tile (MMA M)
 constexpr int kMaxTileN = 256;   // prompts per pass (MMA N): 64 (resident prompt block), 128 or 256 (streamed)
 constexpr int kChunkK = 32;      // fp32 channels per pipeline stage: 128 bytes = one swizzle row
 constexpr uint32_t kHalfBytes = kTileM * kChunkK * 4;  // 128 voxels x 32 channels: 16 KB
+// |a_tf32 . b_tf32 - a . b| <= sum |a_i b_i| (2 eps + eps^2) <= (2^-9 + 2^-20) ||a|| ||b||  for eps = 2^-10 (the tensor core
+// reads 10 explicit mantissa bits of each fp32 operand) -- Cauchy-Schwarz; the fp32 accumulation of d <= 1024 terms adds
+// less than 1e-4 ||a|| ||b||.  1.5 x 2^-9 leaves half of the bound as slack.
+constexpr float kTf32Margin = 1.5f * 0.001953125f;
 constexpr int kWarpStage = 128;  // candidates an epilogue warp stages in shared memory before one global append
 
 // TN prompts per pass.  Streamed prompt slices are re-read from L2 for every voxel tile, so a streamed tile takes
@@ -377,7 +381,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;  // scored quantity is f/||f||: unit norm (NaN sums stay NaN)
       }
-      const float margin = 3.0f * 0.00390625f * fn;  // 3 * 2^-8 * ||f_v||
+      const float margin = kTf32Margin * fn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * C::kMH + mh) * TN;
@@ -576,7 +580,7 @@ query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;
       }
-      const float margin = 3.0f * 0.00390625f * fn;
+      const float margin = kTf32Margin * fn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kTN;
