@@ -80,3 +80,42 @@ def test_engine2_on_fused_map_and_overflow_fallback():
     i2, s2 = dm.query(q[:12], top_k=3, engine=2)
     assert dm.query_stats()["fallbacks"] == 1
     assert torch.equal(i1, i2) and i1[0].tolist() == [0, 1, 2]      # ties: lower index first
+
+
+@pytest.mark.parametrize("P", [4, 200])
+def test_engine2_margin_covers_worst_case_tf32_truncation(P):
+    """Pins the selection margin (kTf32Margin).  Every fp32 value below has its 13 low mantissa bits set, so the
+    tensor core (which reads 10 mantissa bits) understates each product by 2^-10 .. 2^-9 relative, and the
+    voxels are parallel to the prompts, where Cauchy-Schwarz is tight.  70 000 voxels parallel to prompt p have norms
+    a relative 2e-6 apart, so their exact ranking is decided far below the TF32 error: a margin smaller than the
+    error would drop true top-k voxels; the engine must still agree with the exact engine."""
+    import torch
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    V, d, k = 140000, 128, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+
+    def low_bits_set(x):  # same sign and exponent, mantissa low 13 bits all ones
+        return (x.view(torch.int32) | 0x1FFF).view(torch.float32)
+
+    q = torch.randn((P, d), device="cuda", generator=g).abs() + 0.5       # all products positive
+    q = low_bits_set(q / q.norm(dim=1, keepdim=True))
+    owner = torch.arange(V, device="cuda") % min(P, 2)                      # half the voxels parallel to prompt 0, half to 1
+    scale = 1.0 + 2e-6 * torch.arange(V, device="cuda", dtype=torch.float32)
+    feats = low_bits_set(q[owner] * scale[:, None]).contiguous()
+    dm = vm.DeviceVoxelMap(0.05, d, N.F32, capacity=V)
+    dm.load_dense(torch.rand((V, 3), device="cuda", generator=g), feats)
+    i1, s1 = dm.query(q, top_k=k, engine=1)
+    i2, s2 = dm.query(q, top_k=k, engine=2)
+    assert dm.query_stats()["fallbacks"] == 0
+    assert torch.equal(i1, i2)
+    torch.testing.assert_close(s1, s2, rtol=1e-6, atol=0)
+    # the tensor-core scores really are that far off: float64 vs 10-bit operands
+    tf = lambda x: (x.view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    exact = (feats[:1000].double() * q[owner[:1000]].double()).sum(1)
+    trunc = (tf(feats[:1000]) * tf(q[owner[:1000]])).sum(1)
+    rel = ((exact - trunc) / exact).min().item()
+    assert rel > 2.0 ** -10   # per operand between 2^-11 (mantissa near 2) and 2^-10 (near 1): products lose 2^-10 .. 2^-9
+    dm.close()
