@@ -228,11 +228,33 @@ def _cpu_worker_run(_):
     return cpu_run_once(sm, vs)
 
 
+def release_host_memory():
+    """Drop what this process no longer needs on the host: garbage, torch's cache of pinned blocks."""
+    import gc
+
+    gc.collect()
+    try:
+        import torch
+
+        torch._C._host_emptyCache()
+    except Exception:
+        pass
+
+
 def cpu_parallel(args, procs):
     """`procs` independent copies of the CPU port, each on its own sample submap, started together: what the host
     reaches when the (single-threaded) reference path is simply run once per core."""
     import multiprocessing as mp
 
+    # a worker peaks at ~8 GB (float64 temporaries of the generator, gathered copies inside the oracle) per 4 frames of
+    # 518x294x512: never ask for more than half of what the host has free
+    try:
+        import psutil
+
+        per_worker = 2.0e9 + 14.0 * args.cpu_frames * args.height * args.width * args.dim
+        procs = max(1, min(procs, int(0.5 * psutil.virtual_memory().available / per_worker)))
+    except Exception:
+        pass
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs, initializer=_cpu_worker_init,
                   initargs=(args.cpu_frames, args.height, args.width, args.dim, args.voxel_size, ROOT)) as pool:
@@ -254,6 +276,7 @@ def cpu_baseline(args):
     if args.cpu_procs > 1:
         try:
             del sm
+            release_host_memory()
             out["parallel"] = cpu_parallel(args, args.cpu_procs)
         except Exception as e:  # an extra, never the headline
             out["parallel"] = {"error": repr(e)}
@@ -765,6 +788,9 @@ def main():
                "api": "GraphMap.build_semantic_voxel_map on pinned host arrays -> vsm_fuse_submap_host; "
                       "get_features()/get_centers_world() read the map back",
                "cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU (NVML)" if numa_cpus else "unchanged")}
+        # the pinned inputs (5 GB per submap) go back to the OS before anything else needs host memory
+        del e2e_step, gmh
+        release_host_memory()
 
     # ---- secondary measurements (BASELINE configs[3] and configs[4]), rank 0's GPU only, outside the timed step ----
     secondary = None
