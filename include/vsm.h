@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VSM_ABI_VERSION 2
+#define VSM_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VSM_API __attribute__((visibility("default")))
@@ -44,7 +44,7 @@ extern "C" {
 #define VSM_E_INVALID 1        /* bad argument (reference: ValueError / TypeError) */
 #define VSM_E_CUDA 2           /* CUDA runtime error, or no device */
 #define VSM_E_NOMEM 3          /* device allocation failed */
-#define VSM_E_COORD_RANGE 4    /* a finite voxel coordinate outside +-(2^20-1) */
+#define VSM_E_COORD_RANGE 4    /* a finite voxel coordinate outside +-(2^20-1) cells (option "coord_range_policy" 0) */
 #define VSM_E_NONFINITE_EMB 5  /* optimistic filter pass met a non-finite embedding row: map poisoned, redo with VSM_FUSE_EMB_PRECHECK */
 #define VSM_E_STATE 6          /* call not valid in the map's current state */
 #define VSM_E_TOO_MANY_FRAMES 7/* more than VSM_MAX_FRAMES frames in one submap */
@@ -107,6 +107,8 @@ typedef struct vsm_fuse_stats {
   int64_t n_map_voxels;    /* voxels in the map after the call */
   int64_t n_bad_emb_rows;  /* non-finite embedding rows met while accumulating */
   float bbox_lo[3], bbox_hi[3];
+  int64_t n_range_dropped; /* points dropped because a finite voxel coordinate lies outside +-(2^20-1) cells
+                              (only with vsm_set_option("coord_range_policy", 1); 0 otherwise) */
 } vsm_fuse_stats;
 
 /* ---- library ---------------------------------------------------------- */
@@ -115,7 +117,15 @@ VSM_API const char* vsm_last_error(void);
 /* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
 VSM_API int64_t vsm_launch_count(void);
 
-/* process-wide options: "select_mode" 0 default (= 1) / 1 three-pass radix select / 2 bracket select (sampled brackets,
+/* All maps of one device share a scratch workspace (world points, submap-local hash tables).  Calls may come from
+ * any stream: a call queued on a stream other than the previous borrower's first waits (on the device) for that
+ * borrower's kernels, so two maps fused on two streams serialise instead of corrupting each other.
+ *
+ * process-wide options: "prep_variant" bit mask of the preparation kernels (1 = a warp takes a 4x8 pixel patch, 2 = probe
+ * the frame mask before the atomic OR, 4 = select with merged one-block steps; default 5; results identical for every
+ * value); "coord_range_policy" 0 (default) = a finite point whose voxel coordinate cannot be packed fails the call with
+ * VSM_E_COORD_RANGE, 1 = such points are dropped and counted in vsm_fuse_stats.n_range_dropped (the reference accepts
+ * any int64 coordinate; +-(2^20-1) cells is +-21 km at 2 cm); "select_mode" 0 default (= 1) / 1 three-pass radix select / 2 bracket select (sampled brackets,
  * collect fused into the world-point kernel) for the bbox percentiles (identical results; tests force each); "overlap" 0/1 runs the accumulate kernel on a side stream beside the
  * next call's preparation kernels (current device).  Counters: "select_misses" = fuse calls repeated with the radix
  * select because the bracket select could not answer; "capacity_retries" = calls repeated after the map or the

@@ -49,7 +49,7 @@ def test_no_cpu_fallback(native):
 
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    assert native.lib.vsm_abi_version() == 2
+    assert native.lib.vsm_abi_version() == 3
     cfg = native.Config(0.05, 16, native.F32, 1024, -1, 0)
     h = C.c_void_p()
     rc = native.lib.vsm_map_create(C.byref(cfg), C.byref(h))

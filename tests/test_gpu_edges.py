@@ -107,7 +107,63 @@ def test_frame_limit_and_coordinate_range():
     with pytest.raises(OverflowError, match="outside"):
         dm.fuse(far, conf[:2].contiguous(), emb[:2].contiguous(), dm.make_params(2, 2, 2, 2, 1, 1.0, H, 1, 0))
     assert dm.num_voxels == n_before                          # the call was stopped before it touched the map
+    # coord_range_policy 1: the far point is dropped and counted, the other seven are fused
+    N.set_option("coord_range_policy", 1)
+    try:
+        st = dm.fuse(far, conf[:2].contiguous(), emb[:2].contiguous(), dm.make_params(2, 2, 2, 2, 1, 1.0, H, 1, 0))
+    finally:
+        N.set_option("coord_range_policy", 0)
+    assert st["n_range_dropped"] == 1 and st["n_fused"] == 7
     dm.finalize()
     _, _, counts, _ = dm.export_geometry()
-    assert int(counts.sum()) == 128 * 4
+    assert int(counts.sum()) == 128 * 4 + 7
     dm.close()
+
+
+def test_two_maps_on_two_streams_share_the_workspace_safely():
+    """Two maps of one device fused from two streams (queued calls, nothing collected in between): the shared
+    workspace is handed over in stream order, so both maps equal their single-stream builds."""
+    import torch
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    subs = [synth.make_submap(91, i, S=4, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.3 * i)
+            for i in range(4)]
+    dev = [_dev(s) for s in subs]
+    thr = [float(vm.conf_threshold(d[1], 25.0)) for d in dev]
+
+    def build(order):
+        maps = [vm.DeviceVoxelMap(0.05, 64, N.F32), vm.DeviceVoxelMap(0.05, 64, N.F32)]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()] if order == "two_streams" else [None, None]
+        torch.cuda.synchronize()
+        for i, (s, d) in enumerate(zip(subs, dev)):
+            which = i & 1
+            p = maps[which].make_params(4, 56, 84, 4, 1, thr[i], s.H_world_map, s.submap_id, N.FUSE_FILTERS)
+            if streams[which] is not None:
+                with torch.cuda.stream(streams[which]):
+                    maps[which].fuse_async(d[0], d[1], d[2], p)
+            else:
+                maps[which].fuse_async(d[0], d[1], d[2], p)
+        out = []
+        for which, mp in enumerate(maps):
+            if streams[which] is not None:
+                with torch.cuda.stream(streams[which]):
+                    mp.collect()
+                    mp.finalize()
+                    out.append((mp.export_packed_keys().cpu().numpy(), mp.export_geometry()[2].cpu().numpy(),
+                                mp.features_to_host()))
+            else:
+                mp.collect()
+                mp.finalize()
+                out.append((mp.export_packed_keys().cpu().numpy(), mp.export_geometry()[2].cpu().numpy(),
+                            mp.features_to_host()))
+            mp.close()
+        return out
+
+    want = build("one_stream")
+    for _ in range(3):
+        got = build("two_streams")
+        for (k0, c0, f0), (k1, c1, f1) in zip(want, got):
+            np.testing.assert_array_equal(k0, k1)
+            np.testing.assert_array_equal(c0, c1)
+            np.testing.assert_allclose(f0, f1, rtol=1e-5, atol=1e-6)

@@ -165,7 +165,7 @@ def test_fuse_submap_errors(vsm_mod):
     (22, 5, 42, 70, 512, "sim3", "painted"),
     (23, 3, 29, 41, 8, "se3", "normal"),   # odd sizes: unaligned tails
 ])
-def test_fuse_submap_oracle(vsm_mod, seed, S, H, W, d, mode, kind):
+def test_fuse_submap_oracle(vsm_mod, seed, S, H, W, d, mode, kind, kernel_variant):
     import torch
 
     s = synth.make_submap(seed, 2, S=S, H=H, W=W, d=d, mode=mode, emb_kind=kind, room=(3.0, 2.5, 2.0))
@@ -214,6 +214,19 @@ def fuse_overlap(request):
     N.set_option("overlap", 0)
 
 
+@pytest.fixture(params=[(0, 0), (5, 1), (7, 1)], ids=["row_kernels", "default_kernels", "mask_probe"])
+def kernel_variant(request):
+    """The preparation kernels with a warp per 32-pixel row run / per 4x8 patch (+ merged select steps, + frame-mask
+    probe) and the chunked / segment-owning accumulate kernel: every combination must give the reference's map."""
+    from vsm import _native as N
+
+    N.set_option("prep_variant", request.param[0])
+    N.set_option("acc_variant", request.param[1])
+    yield request.param
+    N.set_option("prep_variant", 5)
+    N.set_option("acc_variant", 1)
+
+
 def graph_from(vsm, subs, **kw):
     gm = vsm.GraphMap()
     for s in subs:
@@ -227,7 +240,7 @@ def graph_from(vsm, subs, **kw):
     ("s1_nodedup", dict(stride=1, deduplicate_contributors=False)),
 ])
 @pytest.mark.parametrize("streaming", [False, True])
-def test_build_global_golden(vsm_mod, tag, kw, streaming, select_mode):
+def test_build_global_golden(vsm_mod, tag, kw, streaming, select_mode, kernel_variant):
     z = gio.load("case_c_global_sl4.npz")
     gm = graph_from(vsm_mod, gio.inputs(z))
     m = gm.build_semantic_voxel_map(0.05, host_streaming=streaming, **kw)
@@ -276,7 +289,7 @@ def test_build_global_errors_and_empty(vsm_mod):
 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 @pytest.mark.parametrize("stride", [1, 3])
-def test_build_global_oracle(vsm_mod, dtype, stride, select_mode, fuse_overlap):
+def test_build_global_oracle(vsm_mod, dtype, stride, select_mode, fuse_overlap, kernel_variant):
     """Four overlapping submaps, SL(4), d=64, clean embeddings (single optimistic pass), device inputs."""
     subs = [synth.make_submap(31, i, S=5, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
                               first_frame_number=5 * i, n_loop_frames=(1 if i == 2 else 0)) for i in range(4)]
@@ -293,6 +306,27 @@ def test_build_global_oracle(vsm_mod, dtype, stride, select_mode, fuse_overlap):
     np.testing.assert_array_equal(counts.cpu().numpy(), want.counts)
     assert m.get_contributors() == want.contributors
     assert sum(st["n_fused"] for st in gm.last_build_stats) == want.n_points == int(want.counts.sum())
+
+
+@pytest.mark.parametrize("voxel_size", [0.012, 0.05, 0.4])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_segment_shapes_against_oracle(vsm_mod, voxel_size, dtype, kernel_variant):
+    """Voxel segments of ~1 row (1.2 cm voxels), tens of rows and thousands of rows (40 cm voxels: segments that run
+    through several 32-entry chunks) through both accumulate kernels, d = 256 (full rows: the owned-segment kernel),
+    fused twice so that the second pass meets voxels that are no longer new."""
+    subs = [synth.make_submap(47, i, S=3, H=56, W=84, d=256, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
+                              first_frame_number=3 * i) for i in range(3)]
+    with np.errstate(all="ignore"):
+        want = vo.build_global([gio.to_oracle_submap(s) for s in subs], voxel_size, exact_order=False)
+    gm = vsm_mod.GraphMap()
+    for s in subs:
+        gm.add_submap(to_submap(vsm_mod, s, emb=bf16_tensor(s.emb) if dtype == "bf16" else None, device_inputs=True))
+    m = gm.build_semantic_voxel_map(voxel_size)
+    np.testing.assert_array_equal(m.get_centers_world(), want.centers_world)
+    coords, _, counts, _ = m._dm.export_geometry()
+    np.testing.assert_array_equal(counts.cpu().numpy(), want.counts)
+    np.testing.assert_allclose(m.get_features(), want.features, rtol=RTOL, atol=ATOL)
+    assert m.get_contributors() == want.contributors
 
 
 def test_build_orders_agree(vsm_mod):

@@ -93,6 +93,34 @@ Workspace* workspace_for_device(int device) {
   return table[device];
 }
 
+WsLease::WsLease(Workspace* ws, cudaStream_t s) : ws_(ws), s_(s), status_(VSM_OK) {
+  ws_->mu.lock();
+  if (!ws_->ev_last_use && cudaEventCreateWithFlags(&ws_->ev_last_use, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("workspace: cannot create the stream-order event: %s", cudaGetErrorString(cudaGetLastError()));
+    status_ = VSM_E_CUDA;
+    return;
+  }
+  if (ws_->used && ws_->last_stream != s_) {
+    // the previous borrower's kernels (another stream) still own the buffers: order this stream behind them
+    if (cudaStreamWaitEvent(s_, ws_->ev_last_use, 0) != cudaSuccess || join_accumulates(ws_, s_) != VSM_OK) {
+      set_error("workspace: cannot order stream behind the previous borrower: %s", cudaGetErrorString(cudaGetLastError()));
+      status_ = VSM_E_CUDA;
+    }
+  }
+}
+
+WsLease::~WsLease() {
+  if (status_ == VSM_OK && ws_->ev_last_use) {
+    if (cudaEventRecord(ws_->ev_last_use, s_) == cudaSuccess) {
+      ws_->last_stream = s_;
+      ws_->used = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  ws_->mu.unlock();
+}
+
 int read_back(vsm_map* m, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
   if (m->pinned_bytes < bytes) {
     if (m->pinned) cudaFreeHost(m->pinned);
@@ -241,7 +269,7 @@ static int map_destroy_now(vsm_map* m) {
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
                          &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm,
-                         &m->q_tc,      &m->q_tc_cand};
+                         &m->q_tc,      &m->q_tc_cand,  &m->xch_tmp};
   for (auto* b : bufs) b->release();
   for (auto& f : m->fuses) f.point_gid.release();
   if (m->pinned) cudaFreeHost(m->pinned);

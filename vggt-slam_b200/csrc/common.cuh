@@ -45,7 +45,9 @@ extern int64_t g_launches;  // kernels launched by this library (vsm_launch_coun
   } while (0)
 
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
-static inline int grid_for(int64_t n, int block, int max_blocks = 148 * 16) {
+int sm_count();  // multiprocessors of the current device (cached per device; select.cu)
+static inline int grid_for(int64_t n, int block, int max_blocks = 0) {
+  if (max_blocks <= 0) max_blocks = sm_count() * 16;
   int64_t g = cdiv(n, block);
   if (g < 1) g = 1;
   if (g > max_blocks) g = max_blocks;

@@ -183,16 +183,14 @@ extern "C" int vsm_partials_pack(vsm_map* m, int32_t world, uint64_t* keys_dev, 
     set_error("vsm_partials_pack: null output");
     return VSM_E_INVALID;
   }
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-  VSM_TRY(m->ws->lv_off.ensure((size_t)V * 4, s));
+  VSM_TRY(m->xch_tmp.ensure((size_t)V * 4, s));
   owner_place_kernel<<<grid_for(V, 256), 256, 0, s>>>(m->vkey.as<unsigned long long>(), V, (uint32_t)world, base, cursor,
-                                                      m->ws->lv_off.as<uint32_t>());
+                                                      m->xch_tmp.as<uint32_t>());
   VSM_LAUNCHED();
   pack_rows_kernel<<<grid_for((int64_t)V * 32, 256), 256, 0, s>>>(
-      m->vkey.as<unsigned long long>(), m->vcount.as<uint32_t>(), m->vsum.as<float>(), m->ws->lv_off.as<uint32_t>(), V, m->d,
+      m->vkey.as<unsigned long long>(), m->vcount.as<uint32_t>(), m->vsum.as<float>(), m->xch_tmp.as<uint32_t>(), V, m->d,
       reinterpret_cast<unsigned long long*>(keys_dev), counts_dev, sums_dev);
   VSM_LAUNCHED();
-  VSM_CUDA(cudaStreamSynchronize(s));  // the shared workspace is released on return
   return VSM_OK;
 }
 
@@ -216,12 +214,11 @@ extern "C" int vsm_partials_merge(vsm_map* m, const uint64_t* keys_dev, const ui
   VSM_TRY(m->ctr.ensure(sizeof(FuseCounters), s));
   FuseCounters* ctr = m->ctr.as<FuseCounters>();
   VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters), s));
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-  VSM_TRY(m->ws->lv_gid.ensure((size_t)n * 4, s));
+  VSM_TRY(m->xch_tmp.ensure((size_t)n * 4, s));
   merge_keys_kernel<<<grid_for(n, 256), 256, 0, s>>>(global_store(m), reinterpret_cast<const unsigned long long*>(keys_dev),
-                                                     counts_dev, n, m->ws->lv_gid.as<int32_t>(), &ctr->internal_err);
+                                                     counts_dev, n, m->xch_tmp.as<int32_t>(), &ctr->internal_err);
   VSM_LAUNCHED();
-  merge_rows_kernel<<<grid_for(n * 32, 256), 256, 0, s>>>(m->ws->lv_gid.as<int32_t>(), sums_dev, n, m->d, m->vsum.as<float>());
+  merge_rows_kernel<<<grid_for(n * 32, 256), 256, 0, s>>>(m->xch_tmp.as<int32_t>(), sums_dev, n, m->d, m->vsum.as<float>());
   VSM_LAUNCHED();
   FuseCounters hc{};
   VSM_TRY(read_back(m, &hc, ctr, sizeof(FuseCounters), s));

@@ -16,10 +16,11 @@
 //                     + top-11-bit histograms of the three axes for the percentile select
 //   [filters]         radix-select passes 1,2 -> bbox; coarse-cell hash count -> isolation filter
 //   fine_insert       packed voxel key -> submap-local hash (count + frame mask), point -> slot
-//   post_insert       capacity check (abort flag), coarse table cleanup
-//   local_compact     dense local voxel ids, counts, segment offsets (warp-aggregated allocation)
-//   global_merge      one thread per DISTINCT voxel inserts into the global hash (V_sub, not N, probes)
+//   count_new_decide  exact capacity check; the last block sets the abort flag or reserves the log entries
+//   compact_merge     one thread per DISTINCT voxel (V_sub, not N): dense local id, segment of the sorted list,
+//                     insert into the global hash, counts, contributor log
 //   scatter           counting sort of the points by local voxel -> packed (voxel id, pixel) entries
+//   tables_cleanup    resets the touched slots of both submap-local tables
 //   accumulate        warps walk 32-entry chunks of the sorted list, sum embedding rows in fp32 registers
 //                     (FHADD.BF16) and flush with vector REDs at voxel boundaries
 #include <algorithm>
@@ -32,6 +33,11 @@ namespace vsm {
 
 constexpr uint32_t kFuseForceRadix = 1u << 30;  // internal flag: this call must use the three-pass radix select
 std::atomic<int> g_select_mode{0};              // 0 default (= 1), 1 radix, 2 bracket (vsm_set_option "select_mode")
+// preparation kernels (vsm_set_option "prep_variant"): bit 0 = a warp takes a 4x8 pixel patch instead of 32 pixels of a
+// row; bit 1 = read the frame-mask word before the atomic OR; bit 2 = select with merged one-block steps
+std::atomic<int> g_prep_variant{5};
+std::atomic<int> g_acc_variant{1};  // "acc_variant": 1 = segment-owning accumulate kernel (plain stores for new voxels), 0 = chunked
+std::atomic<int> g_range_policy{0};             // "coord_range_policy": 0 = fail the call (VSM_E_COORD_RANGE), 1 = drop + count
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
 std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
@@ -216,24 +222,60 @@ __global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm,
 // ---------------------------------------------------------------------------
 // submap-local hash: insert with warp-level key dedup
 // ---------------------------------------------------------------------------
-// Consecutive pixels mostly fall into the same voxel, so the lanes of a warp first
-// group equal keys (match.any) and only each group's leader touches the table, adding
-// the whole group's count with one atomic.
-__device__ __forceinline__ int table_claim(const LocalTable& t, unsigned long long key, uint32_t add,
+// Neighbouring pixels mostly fall into the same voxel, so the lanes of a warp first group equal keys (match.any) and
+// only each group's leader touches the table, adding the whole group's count with one atomic.  A warp takes a
+// 4 x 8 PATCH of one frame rather than 32 pixels of one image row: a 5 cm voxel covers a few pixels in BOTH image
+// directions, so a patch holds 2-3x fewer distinct keys than a row segment (fewer claims, fewer atomics); rows of a
+// patch are 8 pixels = 128 contiguous bytes of world points, so the loads stay sector-exact.
+constexpr int kPatchRows = 4, kPatchCols = 8;
+struct PixMap {
+  uint32_t n_px, H, W, tiles_x, tiles_per_frame;
+  uint32_t n_items;  // warp-iterations: patches (PATCH) or 32-pixel runs (linear)
+};
+static PixMap make_pixmap(int64_t n_px, int frames, int H, int W, bool patch) {
+  PixMap pm{};
+  pm.n_px = (uint32_t)n_px;
+  pm.H = (uint32_t)H;
+  pm.W = (uint32_t)W;
+  pm.tiles_x = (uint32_t)((W + kPatchCols - 1) / kPatchCols);
+  pm.tiles_per_frame = pm.tiles_x * (uint32_t)((H + kPatchRows - 1) / kPatchRows);
+  pm.n_items = patch ? (uint32_t)frames * pm.tiles_per_frame : (uint32_t)((n_px + 31) / 32);
+  return pm;
+}
+template <bool PATCH>
+__device__ __forceinline__ bool map_pixel(const PixMap& pm, uint32_t item, int lane, uint32_t& pix) {
+  if (PATCH) {
+    const uint32_t f = item / pm.tiles_per_frame;
+    const uint32_t r = item - f * pm.tiles_per_frame;
+    const uint32_t ty = r / pm.tiles_x, tx = r - ty * pm.tiles_x;
+    const uint32_t y = ty * kPatchRows + ((uint32_t)lane >> 3), x = tx * kPatchCols + ((uint32_t)lane & 7u);
+    pix = (f * pm.H + y) * pm.W + x;
+    return y < pm.H && x < pm.W;
+  }
+  pix = item * 32u + (uint32_t)lane;
+  return pix < pm.n_px;
+}
+
+constexpr int kOptMaskProbe = 1;  // read the frame-mask word before the atomic OR (most ORs would set a bit that is set)
+constexpr int kOptDropRange = 2;  // drop points whose finite voxel coordinate cannot be packed instead of failing the call
+
+// finds or claims the slot of `key` and adds `add` to its count; is_new: this call claimed it (the caller gives it
+// a place in the claim list)
+__device__ __forceinline__ int table_claim(const LocalTable& t, unsigned long long key, uint32_t add, bool& is_new,
                                            FuseCounters* ctr) {
   uint32_t h = (uint32_t)mix64(key) & t.cap_mask;
   for (uint32_t probes = 0; probes <= t.cap_mask; ++probes) {
-    unsigned long long cur = t.keys[h];
+    Slot* sl = t.slots + h;
+    unsigned long long cur = sl->key;
     if (cur == kEmptyKey) {
-      cur = atomicCAS(&t.keys[h], kEmptyKey, key);
+      cur = atomicCAS(&sl->key, kEmptyKey, key);
       if (cur == kEmptyKey) {
-        const uint32_t lid = atomicAdd(t.n_occ, 1u);
-        t.slot_list[lid] = h;
+        is_new = true;
         cur = key;
       }
     }
     if (cur == key) {
-      atomicAdd(&t.count[h], add);
+      atomicAdd(&sl->count, add);
       return (int)h;
     }
     h = (h + 1u) & t.cap_mask;
@@ -243,18 +285,33 @@ __device__ __forceinline__ int table_claim(const LocalTable& t, unsigned long lo
 }
 
 // all 32 lanes must call; inactive lanes pass active=false.  frame < 0: no frame mask.
-__device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, unsigned long long key, int frame,
+__device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, unsigned long long key, int frame, int opts,
                                            FuseCounters* ctr) {
+  const int lane = lane_id();
   const unsigned long long k = active ? key : kEmptyKey;
   const unsigned grp = __match_any_sync(0xffffffffu, k);
   const int leader = __ffs(grp) - 1;
   int slot = -1;
-  if (active && lane_id() == leader) slot = table_claim(t, key, (uint32_t)__popc(grp), ctr);
+  bool is_new = false;
+  if (active && lane == leader) slot = table_claim(t, key, (uint32_t)__popc(grp), is_new, ctr);
+  // the slots this warp claimed take consecutive places in the claim list: ONE atomic per warp on the shared counter
+  // (every new voxel used to add 1 to the same address -- ~350 k serialised atomics per submap at 2 cm voxels)
+  const unsigned newm = __ballot_sync(0xffffffffu, is_new);
+  if (newm) {
+    const int nl = __ffs(newm) - 1;
+    uint32_t base = 0;
+    if (lane == nl) base = atomicAdd(t.n_occ, (uint32_t)__popc(newm));
+    base = __shfl_sync(0xffffffffu, base, nl);
+    if (is_new) t.slot_list[base + (uint32_t)__popc(newm & ((1u << lane) - 1u))] = (uint32_t)slot;
+  }
   slot = __shfl_sync(0xffffffffu, slot, leader);
   if (frame >= 0) {
     const int lf = __shfl_sync(0xffffffffu, frame, leader);
-    if (active && slot >= 0 && (lane_id() == leader || frame != lf))
-      atomicOr(&t.mask[(size_t)slot * 2 + (frame >> 6)], 1ull << (frame & 63));
+    if (active && slot >= 0 && (lane == leader || frame != lf)) {
+      unsigned long long* mp = &t.slots[slot].mask[frame >> 6];
+      const unsigned long long bit = 1ull << (frame & 63);
+      if (!(opts & kOptMaskProbe) || (__ldcg(mp) & bit) == 0ull) atomicOr(mp, bit);
+    }
   }
   return active ? slot : -1;
 }
@@ -262,23 +319,34 @@ __device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, uns
 struct FilterArgs {
   const float4* pw;
   int32_t* pt_slot;
-  uint32_t n_px;
   uint32_t px_per_frame;
   uint32_t frame_base;
   float cell;  // coarse cell (bbox_coarse) or voxel size (fine)
   uint32_t min_pts;
+  int opts;
 };
 
+// a finite coordinate that cannot be packed: fail the call (default) or drop the point and count it
+__device__ __forceinline__ bool range_problem(bool rerr, int opts, FuseCounters* ctr) {
+  if (!rerr) return false;
+  atomicAdd((opts & kOptDropRange) ? &ctr->range_dropped : &ctr->range_err, 1u);
+  return (opts & kOptDropRange) != 0;
+}
+
 // filter 2 (inclusive percentile box, map.py:257-263) + count per coarse cell (map.py:271-275)
-__global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, LocalTable ta, FuseCounters* ctr) {
+template <bool PATCH>
+__global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, PixMap pm, LocalTable ta, FuseCounters* ctr) {
   const float lx = ctr->bounds[0], hx = ctr->bounds[1], ly = ctr->bounds[2], hy = ctr->bounds[3], lz = ctr->bounds[4],
               hz = ctr->bounds[5];
   unsigned n_in = 0;
-  const uint32_t n_round = (a.n_px + 31u) & ~31u;
-  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
+  const int lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
+    uint32_t pix;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
     bool act = false;
     unsigned long long key = kEmptyKey;
-    if (pix < a.n_px) {
+    if (inside) {
       const float4 p = a.pw[pix];
       const uint32_t f = __float_as_uint(p.w);
       if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) {
@@ -286,57 +354,66 @@ __global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, LocalTab
         if (act) {
           bool rerr = false;
           key = pack_key(p.x, p.y, p.z, a.cell, rerr);
-          if (rerr) atomicAdd(&ctr->range_err, 1u);
+          if (range_problem(rerr, a.opts, ctr)) act = false;
         }
       }
     }
-    const int slot = warp_insert(ta, act, key, -1, ctr);
-    if (pix < a.n_px) a.pt_slot[pix] = slot;
+    const int slot = warp_insert(ta, act, key, -1, a.opts, ctr);
+    if (inside) a.pt_slot[pix] = slot;
     n_in += act ? 1u : 0u;
   }
   for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
-  if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
+  if (lane == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
 }
 
 // filter 3 (cells with >= min_pts points, map.py:276-280) + fine voxel keys (map.py:351 / submap.py:282)
-template <bool FILTERS>
-__global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, LocalTable ta, LocalTable tb, FuseCounters* ctr) {
+template <bool FILTERS, bool PATCH>
+__global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, PixMap pm, LocalTable ta, LocalTable tb,
+                                                          FuseCounters* ctr) {
   unsigned n_in = 0;
-  const uint32_t n_round = (a.n_px + 31u) & ~31u;
-  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
+  const int lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
+    uint32_t pix;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
     bool act = false;
     unsigned long long key = kEmptyKey;
     int frame = 0;
-    if (pix < a.n_px) {
+    if (inside) {
       const float4 p = a.pw[pix];
       if (FILTERS) {
         const int sa = a.pt_slot[pix];
-        act = sa >= 0 && ta.count[sa] >= a.min_pts;
+        act = sa >= 0 && ta.slots[sa].count >= a.min_pts;
       } else {
         act = (__float_as_uint(p.w) & PF_SEL) != 0u;
       }
       if (act) {
         bool rerr = false;
         key = pack_key(p.x, p.y, p.z, a.cell, rerr);
-        if (rerr) atomicAdd(&ctr->range_err, 1u);
+        if (range_problem(rerr, a.opts, ctr)) act = false;
         frame = (int)(a.frame_base + pix / a.px_per_frame);
       }
     }
-    const int slot = warp_insert(tb, act, key, frame, ctr);
-    if (pix < a.n_px) a.pt_slot[pix] = slot;
+    const int slot = warp_insert(tb, act, key, frame, a.opts, ctr);
+    if (inside) a.pt_slot[pix] = slot;
     n_in += act ? 1u : 0u;
   }
   for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
-  if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_fused, (unsigned long long)n_in);
+  if (lane == 0 && n_in) atomicAdd(&ctr->n_fused, (unsigned long long)n_in);
 }
 
-// how many of this call's distinct voxels are not in the global map yet (read-only probe): the exact number the
-// capacity check needs, so that a call is only stopped when the map really has to grow
-__global__ void __launch_bounds__(256) count_new_kernel(LocalTable tb, GlobalStore g, FuseCounters* ctr) {
+// How many of this call's distinct voxels are not in the global map yet (read-only probe): the exact number the
+// capacity check needs, so that a call is only stopped when the map really has to grow.  The LAST block to finish
+// decides, on the device, whether the call may go on.  It may not if an error was flagged or if the map / contributor
+// log cannot take this call's voxels: nothing global has been touched yet, so the host can grow the map and simply
+// repeat the call.
+__global__ void __launch_bounds__(256) count_new_decide_kernel(LocalTable tb, GlobalStore g, FuseCounters* ctr,
+                                                               uint32_t* __restrict__ map_state /* [0] voxels, [1] log */,
+                                                               uint32_t vcap, uint32_t log_cap, uint32_t entry_cap) {
   const uint32_t n_occ = ctr->n_occ_b;
   unsigned n_new = 0;
   for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
-    const unsigned long long key = tb.keys[tb.slot_list[lid]];
+    const unsigned long long key = tb.slots[tb.slot_list[lid]].key;
     uint64_t h = mix64(key) & g.gmask;
     bool found = false;
     for (uint64_t probes = 0; probes <= g.gmask; ++probes) {
@@ -352,80 +429,46 @@ __global__ void __launch_bounds__(256) count_new_kernel(LocalTable tb, GlobalSto
   }
   for (int o = 16; o > 0; o >>= 1) n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
   if (lane_id() == 0 && n_new) atomicAdd(&ctr->n_new, n_new);
-}
-
-// After the inserts: reset the coarse table and decide, on the device, whether the call may go on.  It may not
-// if an error was flagged or if the map / contributor log cannot take this call's voxels: nothing global has
-// been touched yet, so the host can grow the map and simply repeat the call.
-__global__ void __launch_bounds__(256) post_insert_kernel(LocalTable ta, int has_ta, FuseCounters* ctr,
-                                                          uint32_t* __restrict__ map_state /* [0] voxels, [1] log */,
-                                                          uint32_t vcap, uint32_t log_cap, uint32_t entry_cap) {
-  if (has_ta) {
-    const uint32_t n_occ = *ta.n_occ;
-    for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
-      const uint32_t slot = ta.slot_list[lid];
-      ta.keys[slot] = kEmptyKey;
-      ta.count[slot] = 0u;
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const uint32_t n_occ = ctr->n_occ_b;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1) {
+    __threadfence();
+    const uint32_t total_new = atomicAdd(&ctr->n_new, 0u);
     const uint32_t log_n = map_state[1];
-    const bool fits = ((unsigned long long)map_state[0] + ctr->n_new <= vcap) &&
+    const bool fits = ((unsigned long long)map_state[0] + total_new <= vcap) &&
                       ((unsigned long long)log_n + n_occ <= log_cap) &&
                       (ctr->n_finite <= (unsigned long long)entry_cap || ctr->n_fused <= (unsigned long long)entry_cap);
     if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss || ctr->bad_index) {
       ctr->abort = 1u;
     } else {
       ctr->log_base = log_n;  // calls on one stream run one after the other: plain read-modify-write
+      ctr->vox_base = map_state[0];
       map_state[1] = log_n + n_occ;
     }
   }
 }
 
-// dense local ids (= position in the claim list), counts, and a segment of the sorted list per local voxel
-__global__ void __launch_bounds__(256) local_compact_kernel(LocalTable tb, FuseCounters* ctr, uint32_t* __restrict__ lv_cnt,
-                                                            uint32_t* __restrict__ lv_off,
-                                                            uint32_t* __restrict__ lv_cursor) {
-  if (ctr->abort) return;
-  const uint32_t n_occ = ctr->n_occ_b;
-  const uint32_t n_round = (n_occ + 31u) & ~31u;
-  const int lane = lane_id();
-  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
-    uint32_t cnt = 0, slot = 0;
-    if (lid < n_occ) {
-      slot = tb.slot_list[lid];
-      cnt = tb.count[slot];
-    }
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += up;
-    }
-    uint32_t base = 0;
-    if (lane == 31) base = atomicAdd(&ctr->seg_total, incl);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (lid < n_occ) {
-      lv_cnt[lid] = cnt;
-      lv_off[lid] = base + incl - cnt;
-      lv_cursor[lid] = 0u;
-      tb.lid[slot] = lid;
-    }
+__device__ __forceinline__ void slot_reset(Slot* sl) {
+  uint4* q = reinterpret_cast<uint4*>(sl);
+  q[0] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);  // key = kEmptyKey, count = 0, lid = 0
+  q[1] = make_uint4(0u, 0u, 0u, 0u);                    // frame mask
+}
+
+// leaves both submap-local tables clean for the next call (only the touched slots are visited)
+__global__ void __launch_bounds__(256) tables_cleanup_kernel(LocalTable ta, int has_ta, LocalTable tb) {
+  const uint32_t nb = *tb.n_occ;
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < nb; lid += gridDim.x * blockDim.x)
+    slot_reset(tb.slots + tb.slot_list[lid]);
+  if (has_ta) {
+    const uint32_t na = *ta.n_occ;
+    for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < na; lid += gridDim.x * blockDim.x)
+      slot_reset(ta.slots + ta.slot_list[lid]);
   }
 }
 
-__global__ void __launch_bounds__(256) table_cleanup_kernel(LocalTable t) {
-  const uint32_t n_occ = *t.n_occ;
-  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
-    const uint32_t slot = t.slot_list[lid];
-    t.keys[slot] = kEmptyKey;
-    t.count[slot] = 0u;
-    if (t.mask) {
-      t.mask[(size_t)slot * 2] = 0ull;
-      t.mask[(size_t)slot * 2 + 1] = 0ull;
-    }
-  }
+__global__ void __launch_bounds__(256) table_init_kernel(Slot* slots, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    slot_reset(slots + i);
 }
 
 // ---------------------------------------------------------------------------
@@ -446,26 +489,99 @@ __global__ void rehash_kernel(GlobalStore g, uint32_t n) {
   }
 }
 
-// one thread per distinct voxel of this call: global insert, counts, contributor log
-__global__ void __launch_bounds__(256) global_merge_kernel(LocalTable tb, GlobalStore g,
-                                                           const uint32_t* __restrict__ lv_cnt,
-                                                           int32_t* __restrict__ lv_gid, int32_t* __restrict__ log_gid,
-                                                           int32_t* __restrict__ log_sub,
-                                                           unsigned long long* __restrict__ log_mask, int32_t submap_id,
-                                                           FuseCounters* ctr) {
+// One thread per DISTINCT voxel of this call: dense local id (= place in the claim list), count, its segment of the
+// sorted list (warp scan + one atomic per warp), then the global insert, the map's point count and the contributor
+// log entry.  New voxels take consecutive ids per warp (one atomic on the map's voxel counter per warp).
+__global__ void __launch_bounds__(256) compact_merge_kernel(LocalTable tb, GlobalStore g, FuseCounters* ctr,
+                                                            uint32_t* __restrict__ lv_off, uint32_t* __restrict__ lv_cursor,
+                                                            int32_t* __restrict__ lv_gid, int32_t* __restrict__ log_gid,
+                                                            int32_t* __restrict__ log_sub,
+                                                            unsigned long long* __restrict__ log_mask, int32_t submap_id) {
   if (ctr->abort) return;
   const uint32_t n_occ = ctr->n_occ_b;
+  const uint32_t n_round = (n_occ + 31u) & ~31u;
   const size_t log_base = ctr->log_base;
-  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_occ; lid += gridDim.x * blockDim.x) {
-    const uint32_t slot = tb.slot_list[lid];
-    const unsigned long long key = tb.keys[slot];
-    const int gid = global_find_or_insert(g, key, &ctr->internal_err);
-    lv_gid[lid] = gid;
-    if (gid >= 0) atomicAdd(&g.vcount[gid], lv_cnt[lid]);
-    log_gid[log_base + lid] = gid;
-    log_sub[log_base + lid] = submap_id;
-    log_mask[2 * (log_base + lid)] = tb.mask[(size_t)slot * 2];
-    log_mask[2 * (log_base + lid) + 1] = tb.mask[(size_t)slot * 2 + 1];
+  const int lane = lane_id();
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
+    const bool on = lid < n_occ;
+    uint32_t cnt = 0, slot = 0;
+    unsigned long long key = kEmptyKey, m0 = 0ull, m1 = 0ull;
+    if (on) {
+      slot = tb.slot_list[lid];
+      const Slot* sl = tb.slots + slot;
+      key = sl->key;
+      cnt = sl->count;
+      m0 = sl->mask[0];
+      m1 = sl->mask[1];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(&ctr->seg_total, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    // global map: find, or claim the hash slot; claimed slots get their ids below
+    int gid = -1;
+    uint64_t hslot = 0;
+    bool claimed = false;
+    if (on) {
+      uint64_t h = mix64(key) & g.gmask;
+      bool done = false;
+      for (uint64_t probes = 0; probes <= g.gmask && !done; ++probes) {
+        unsigned long long cur = g.gkeys[h];
+        if (cur == kEmptyKey) {
+          cur = atomicCAS(&g.gkeys[h], kEmptyKey, key);
+          if (cur == kEmptyKey) {
+            claimed = true;
+            hslot = h;
+            done = true;
+            break;
+          }
+        }
+        if (cur == key) {
+          // published by an earlier call (or, if two streams raced, by a claimer that is about to publish)
+          while ((gid = reinterpret_cast<volatile int32_t*>(g.gids)[h]) == -1) {
+          }
+          done = true;
+          break;
+        }
+        h = (h + 1) & g.gmask;
+      }
+      if (!done) atomicAdd(&ctr->internal_err, 1u);
+    }
+    const unsigned newm = __ballot_sync(0xffffffffu, claimed);
+    if (newm) {
+      const int nl = __ffs(newm) - 1;
+      uint32_t id0 = 0;
+      if (lane == nl) id0 = atomicAdd(g.n_vox, (uint32_t)__popc(newm));
+      id0 = __shfl_sync(0xffffffffu, id0, nl);
+      if (claimed) {
+        const uint32_t id = id0 + (uint32_t)__popc(newm & ((1u << lane) - 1u));
+        if (id >= g.vcap) {
+          atomicAdd(&ctr->internal_err, 1u);
+          reinterpret_cast<volatile int32_t*>(g.gids)[hslot] = -2;  // release waiters; callers treat < 0 as failure
+        } else {
+          g.vkey[id] = key;
+          __threadfence();
+          reinterpret_cast<volatile int32_t*>(g.gids)[hslot] = (int32_t)id;
+          gid = (int)id;
+        }
+      }
+    }
+    if (on) {
+      lv_off[lid] = base + incl - cnt;
+      lv_cursor[lid] = 0u;
+      tb.slots[slot].lid = lid;
+      lv_gid[lid] = gid;
+      if (gid >= 0) atomicAdd(&g.vcount[gid], cnt);
+      log_gid[log_base + lid] = gid;
+      log_sub[log_base + lid] = submap_id;
+      log_mask[2 * (log_base + lid)] = m0;
+      log_mask[2 * (log_base + lid) + 1] = m1;
+    }
   }
 }
 
@@ -478,21 +594,24 @@ __device__ __forceinline__ unsigned long long make_entry(int gid, uint32_t pix) 
 }
 
 // counting sort of the fused points by local voxel.  Lanes with the same voxel claim a block of consecutive
-// positions with one atomic and keep their pixel order inside it; check-only pixels are appended behind.
+// positions with one atomic; check-only pixels are appended behind.
+template <bool PATCH>
 __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict__ pt_slot, const float4* __restrict__ pw,
-                                                      uint32_t n_px, LocalTable tb, const uint32_t* __restrict__ lv_off,
+                                                      PixMap pm, LocalTable tb, const uint32_t* __restrict__ lv_off,
                                                       uint32_t* __restrict__ lv_cursor,
                                                       const int32_t* __restrict__ lv_gid, int mark_checks,
                                                       unsigned long long* __restrict__ entries,
                                                       int32_t* __restrict__ point_gid, FuseCounters* ctr) {
   if (ctr->abort) return;
   const uint32_t n_fused = (uint32_t)ctr->n_fused;
-  const uint32_t n_round = (n_px + 31u) & ~31u;
   const int lane = lane_id();
-  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
-    const int slot = pix < n_px ? pt_slot[pix] : -1;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
+    uint32_t pix;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
+    const int slot = inside ? pt_slot[pix] : -1;
     const bool act = slot >= 0;
-    const uint32_t lid = act ? tb.lid[slot] : 0xFFFFFFFFu;
+    const uint32_t lid = act ? tb.slots[slot].lid : 0xFFFFFFFFu;
     const unsigned grp = __match_any_sync(0xffffffffu, lid);
     const int leader = __ffs(grp) - 1;
     uint32_t base = 0;
@@ -506,7 +625,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
     }
     if (mark_checks) {
       bool chk = false;
-      if (!act && pix < n_px) {
+      if (!act && inside) {
         const uint32_t f = __float_as_uint(pw[pix].w);
         chk = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
       }
@@ -518,7 +637,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
         if (chk) entries[n_fused + cbase + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = make_entry(-2, pix);
       }
     }
-    if (point_gid != nullptr && pix < n_px) point_gid[pix] = gid;
+    if (point_gid != nullptr && inside) point_gid[pix] = gid;
   }
 }
 
@@ -532,7 +651,7 @@ __global__ void __launch_bounds__(256) point_gid_kernel(const int32_t* __restric
     const int slot = pt_slot[pix];
     int g = -1;
     if (slot >= 0) {
-      g = lv_gid[tb.lid[slot]];
+      g = lv_gid[tb.slots[slot].lid];
     } else if (mark_checks) {
       const uint32_t f = __float_as_uint(pw[pix].w);
       if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) g = -2;
@@ -840,17 +959,196 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
   if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
 }
 
+// The voxel-sorted, full-row case with SEGMENT OWNERSHIP.  A voxel's points are one contiguous segment of the sorted
+// list; the kernel above cuts the list into 32-entry chunks, so a segment that straddles a chunk boundary is flushed
+// twice and every flush must be a RED (read-modify-write of the 2 KB sum row).  Here the warp of chunk c owns the
+// segments that START in its chunk and follows them into chunk c+1; only segments that run through a whole chunk are
+// still cut at chunk boundaries.  A whole segment of a voxel that is NEW to the map (id >= vox_base: its sum row has
+// never been touched) is flushed with plain 16-byte stores: no read of the row.  At 2 cm voxels (segments of ~12 rows,
+// most voxels new) that removes ~40 % of the flushes and the row fetch of nearly all the others.
+__device__ __forceinline__ void st_v4_f32(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <bool BF16, int VPL, bool CHECK>
+__global__ void __launch_bounds__(256, 2) accumulate_owned_kernel(AccArgs a) {  // launched with 2 CTAs per SM
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
+  constexpr int kNone = (int)0x80000000;  // "no entry": differs from every voxel id
+  if (a.ctr->abort) return;
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_entries = (int64_t)a.ctr->n_fused;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
+  const int vox_base = (int)a.ctr->vox_base;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const uint8_t* emb0 = a.emb - a.pix_base * a.row_bytes + (size_t)lane * 16;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  unsigned n_bad = 0;
+
+  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+    const int64_t base = chunk << 5;
+    // entries of this chunk and the next one, the first and last voxel id of the previous chunk
+    uint32_t p0 = 0, p1 = 0;
+    int g0 = kNone, g1 = kNone, gp_first = kNone, gp_last = kNone;
+    if (base + lane < n_entries) {
+      const unsigned long long e = a.entries[base + lane];
+      p0 = (uint32_t)e;
+      g0 = (int)(uint32_t)(e >> 32);
+    }
+    if (base + 32 + lane < n_entries) {
+      const unsigned long long e = a.entries[base + 32 + lane];
+      p1 = (uint32_t)e;
+      g1 = (int)(uint32_t)(e >> 32);
+    }
+    if (chunk > 0) {
+      gp_first = (int)(uint32_t)(a.entries[base - 32] >> 32);
+      gp_last = (int)(uint32_t)(a.entries[base - 1] >> 32);
+    }
+    const int g0_first = __shfl_sync(0xffffffffu, g0, 0), g0_last = __shfl_sync(0xffffffffu, g0, 31);
+    const int g1_first = __shfl_sync(0xffffffffu, g1, 0);
+    // lo: where this warp starts.  A segment that began inside the previous chunk belongs to that chunk's warp,
+    // unless it already fills the previous chunk from its first entry (a long segment is cut at every chunk start).
+    int lo = 0;
+    bool first_partial = false;  // the first segment continues one cut at `base`
+    if (chunk > 0 && g0_first == gp_last) {
+      if (g0_first == gp_first) {
+        first_partial = true;
+      } else {
+        const unsigned diff = __ballot_sync(0xffffffffu, g0 != g0_first);
+        lo = diff ? __ffs(diff) - 1 : 32;
+      }
+    }
+    // hi: where the next chunk's warp starts (the same rule, one chunk later)
+    int hi = 32;
+    bool last_partial = false;  // the last segment is cut at base + 32
+    if (base + 32 >= n_entries) {
+      hi = (int)(n_entries - base);
+    } else if (g1_first == g0_last) {
+      if (g1_first == g0_first) {
+        last_partial = true;
+      } else {
+        const unsigned diff = __ballot_sync(0xffffffffu, g1 != g1_first);
+        hi = 32 + (diff ? __ffs(diff) - 1 : 32);
+        if (!diff) last_partial = true;  // still running at base + 64: the warp two chunks on takes over there
+      }
+    }
+    if (lo >= hi) continue;
+
+    float acc[VPL * EPV];
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+    int cur = kNone;
+    bool cur_partial = first_partial;
+
+    auto flush = [&](bool partial) {
+      if (cur != kNone) {
+        bool ok = true;
+        if (CHECK) {
+          float t = 0.f;
+#pragma unroll
+          for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);  // NaN iff some accumulator is Inf/NaN
+          ok = !__any_sync(0xffffffffu, t != t);
+          if (!ok && lane == 0) ++n_bad;
+        }
+        if (ok) {
+          float* dst = vsum0 + (size_t)cur * d;
+          if (!partial && cur >= vox_base) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+              for (int q = 0; q < EPV / 4; ++q)
+                st_v4_f32(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
+                          acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+#pragma unroll
+              for (int q = 0; q < EPV / 4; ++q)
+                red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
+                           acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+    };
+
+    for (int j = lo; j < hi; j += U) {
+      uint4 rows[U][VPL];
+      int gids[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int idx = j + u;  // warp-uniform
+        const bool live = idx < hi;
+        const uint32_t pj = __shfl_sync(0xffffffffu, idx < 32 ? p0 : p1, idx & 31);
+        const int gj = __shfl_sync(0xffffffffu, idx < 32 ? g0 : g1, idx & 31);
+        gids[u] = live ? gj : kNone;
+        const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) rows[u][v] = live ? ld_stream_v4(row + v * 512) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      bool same = true;
+#pragma unroll
+      for (int u = 0; u < U; ++u) same &= (gids[u] == cur);
+      if (same) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (gids[u] == kNone) continue;  // warp-uniform: past the end of this warp's range
+          if (gids[u] != cur) {
+            flush(cur_partial);
+            cur_partial = false;
+            cur = gids[u];
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+        }
+      }
+    }
+    flush(cur_partial || last_partial);
+  }
+
+  if (CHECK) {
+    // check-only entries sit behind the fused ones: one warp per row, test the raw values
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+  }
+  if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+}
+
 template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
   const int block = 256;
   // The sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks.  Two CTAs
   // per SM (16 warps x 4 rows of 1 KB in flight) already saturate HBM (measured: same time as 3 or 6 per SM).
-  int grid = 148 * 2;
+  int grid = sm_count() * 2;
   if (!sorted) {
     const int64_t n_chunks = (a.n + 31) >> 5;
-    grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)148 * 6);
+    grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)sm_count() * 6);
   }
   const bool full = a.nvec == 32 * VPL;
+  if (sorted && full && a.emb_index == nullptr && g_acc_variant.load() == 1) {
+    if (check)
+      accumulate_owned_kernel<BF16, VPL, true><<<grid, block, 0, s>>>(a);
+    else
+      accumulate_owned_kernel<BF16, VPL, false><<<grid, block, 0, s>>>(a);
+    VSM_LAUNCHED();
+    return VSM_OK;
+  }
   if (sorted && full && a.emb_index != nullptr) {
     if (check)
       accumulate_kernel<BF16, VPL, true, true, true, true><<<grid, block, 0, s>>>(a);
@@ -1009,19 +1307,12 @@ int log_grow(vsm_map* m, int64_t need, cudaStream_t s) {
   return VSM_OK;
 }
 
-static int ensure_local_table(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& list, DevBuf* mask, uint64_t& cap,
-                              uint64_t need_cap, cudaStream_t s) {
+static int ensure_local_table(DevBuf& slots, DevBuf& list, uint64_t& cap, uint64_t need_cap, cudaStream_t s) {
   if (cap >= need_cap) return VSM_OK;
-  VSM_TRY(keys.ensure(need_cap * 8, s));
-  VSM_TRY(count.ensure(need_cap * 4, s));
-  VSM_TRY(lid.ensure(need_cap * 4, s));
-  VSM_TRY(list.ensure(need_cap / 2 * 4 + 64, s));
-  VSM_CUDA(cudaMemsetAsync(keys.p, 0xFF, need_cap * 8, s));
-  VSM_CUDA(cudaMemsetAsync(count.p, 0, need_cap * 4, s));
-  if (mask) {
-    VSM_TRY(mask->ensure(need_cap * 16, s));
-    VSM_CUDA(cudaMemsetAsync(mask->p, 0, need_cap * 16, s));
-  }
+  VSM_TRY(slots.ensure(need_cap * sizeof(Slot), s));
+  VSM_TRY(list.ensure(need_cap / 2 * 4 + 256, s));
+  table_init_kernel<<<grid_for((int64_t)need_cap, 256), 256, 0, s>>>(slots.as<Slot>(), need_cap);
+  VSM_LAUNCHED();
   cap = need_cap;
   return VSM_OK;
 }
@@ -1082,13 +1373,9 @@ static int ensure_stream_objects(vsm_map* m, size_t chunk_bytes) {
   return VSM_OK;
 }
 
-static LocalTable table_view(DevBuf& keys, DevBuf& count, DevBuf& lid, DevBuf& list, DevBuf* mask, uint64_t cap,
-                             uint32_t* n_occ) {
+static LocalTable table_view(DevBuf& slots, DevBuf& list, uint64_t cap, uint32_t* n_occ) {
   LocalTable t{};
-  t.keys = keys.as<unsigned long long>();
-  t.count = count.as<uint32_t>();
-  t.lid = lid.as<uint32_t>();
-  t.mask = mask ? mask->as<unsigned long long>() : nullptr;
+  t.slots = slots.as<Slot>();
   t.slot_list = list.as<uint32_t>();
   t.n_occ = n_occ;
   t.cap_mask = (uint32_t)(cap - 1);
@@ -1153,10 +1440,8 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   const uint64_t lcap = std::max<uint64_t>(next_pow2(2 * n_sel_max), 1024);
   VSM_TRY(ws->pw.ensure((size_t)n_px * 16, s));
   VSM_TRY(ws->pt_slot.ensure((size_t)n_px * 4, s));
-  VSM_TRY(ensure_local_table(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap, lcap, s));
-  if (filters)
-    VSM_TRY(ensure_local_table(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, lcap, s));
-  VSM_TRY(ws->lv_cnt.ensure((size_t)n_sel_max * 4, s));
+  VSM_TRY(ensure_local_table(ws->tb_slots, ws->tb_list, ws->tb_cap, lcap, s));
+  if (filters) VSM_TRY(ensure_local_table(ws->ta_slots, ws->ta_list, ws->ta_cap, lcap, s));
   VSM_TRY(ws->lv_off.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_cursor.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_gid.ensure((size_t)n_sel_max * 4, s));
@@ -1168,11 +1453,9 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_TRY(ws->sorted_pix[ab].ensure((size_t)n_sel_max * 8, s));  // packed entries
   }
 
-  LocalTable tb = table_view(ws->tb_keys, ws->tb_count, ws->tb_lid, ws->tb_list, &ws->tb_mask, ws->tb_cap,
-                             &ctr->n_occ_b);
+  LocalTable tb = table_view(ws->tb_slots, ws->tb_list, ws->tb_cap, &ctr->n_occ_b);
   LocalTable ta{};
-  if (filters)
-    ta = table_view(ws->ta_keys, ws->ta_count, ws->ta_lid, ws->ta_list, nullptr, ws->ta_cap, &ctr->n_occ_a);
+  if (filters) ta = table_view(ws->ta_slots, ws->ta_list, ws->ta_cap, &ctr->n_occ_a);
 
   if (emb_index != nullptr) {
     index_check_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(conf, emb_index, (uint32_t)n_px, p->conf_threshold, p->emb_rows, ctr);
@@ -1183,10 +1466,10 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_TRY(call.precheck_mask.ensure((size_t)n_px, s));
     const int nvec = (int)(row_bytes / 16);
     if (bf16)
-      emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
+      emb_row_mask_kernel<true><<<sm_count() * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
                                                         p->stride, p->conf_threshold, call.precheck_mask.as<uint8_t>());
     else
-      emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
+      emb_row_mask_kernel<false><<<sm_count() * 8, 256, 0, s>>>(conf, emb_dev, emb_index, p->emb_rows, row_bytes, nvec, n_px, p->H, p->W,
                                                          p->stride, p->conf_threshold, call.precheck_mask.as<uint8_t>());
     VSM_LAUNCHED();
     emb_ok = call.precheck_mask.as<uint8_t>();
@@ -1252,55 +1535,66 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   VSM_LAUNCHED();
 
   // ---- filters and the two submap-local tables -----------------------------------------------------------
+  const int variant = g_prep_variant.load();
+  const bool patch = (variant & 1) != 0;
   FilterArgs fa;
   fa.pw = ws->pw.as<float4>();
   fa.pt_slot = ws->pt_slot.as<int32_t>();
-  fa.n_px = (uint32_t)n_px;
   fa.px_per_frame = (uint32_t)px_per_frame;
   fa.frame_base = (uint32_t)p->frame_base;
   fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
-  const int grid = grid_for(n_px, 256);
+  fa.opts = ((variant & 2) ? kOptMaskProbe : 0) | (g_range_policy.load() == 1 ? kOptDropRange : 0);
+  const PixMap pm = make_pixmap(n_px, p->end_idx, p->H, p->W, patch);
+  const int grid = grid_for((int64_t)pm.n_items * 32, 256);
   if (filters) {
-    SelSrc src;
-    src.base = reinterpret_cast<const float*>(ws->pw.p);
-    src.stride = 4;
-    src.ncol = 3;
-    src.flag_off = 3;
-    src.flag_need = PF_SEL | PF_FINITE;
-    src.n_items = n_px;
     if (bracket) {
       bracket_resolve_kernel<<<kBrLists, 1024, 0, s>>>(br.bs, br.lists, br.cap, &ctr->n_finite, q0, q1, ctr->bounds,
                                                        &ctr->sel_miss);
       VSM_LAUNCHED();
+    } else if (variant & 4) {
+      VSM_TRY(run_percentiles_world_fast(sst, hist, ws->pw.as<float4>(), n_px, PF_SEL | PF_FINITE, q0, q1, ctr->bounds,
+                                         &ctr->n_finite, s));
     } else {
+      SelSrc src;
+      src.base = reinterpret_cast<const float*>(ws->pw.p);
+      src.stride = 4;
+      src.ncol = 3;
+      src.flag_off = 3;
+      src.flag_need = PF_SEL | PF_FINITE;
+      src.n_items = n_px;
       VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
     }
     fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
-    bbox_coarse_kernel<<<grid, 256, 0, s>>>(fa, ta, ctr);
+    if (patch)
+      bbox_coarse_kernel<true><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
+    else
+      bbox_coarse_kernel<false><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
     VSM_LAUNCHED();
     fa.cell = m->vs_f;
-    fine_insert_kernel<true><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
+    if (patch)
+      fine_insert_kernel<true, true><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
+    else
+      fine_insert_kernel<true, false><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
     VSM_LAUNCHED();
   } else {
     fa.cell = m->vs_f;
-    fine_insert_kernel<false><<<grid, 256, 0, s>>>(fa, ta, tb, ctr);
+    if (patch)
+      fine_insert_kernel<false, true><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
+    else
+      fine_insert_kernel<false, false><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
     VSM_LAUNCHED();
   }
-  const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)148 * 8 * 256), 256, 148 * 8);
-  count_new_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr);
-  VSM_LAUNCHED();
-  post_insert_kernel<<<148 * 2, 256, 0, s>>>(ta, filters ? 1 : 0, ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
-                                             (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
-                                             (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
+  const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)sm_count() * 8 * 256), 256, sm_count() * 8);
+  count_new_decide_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
+                                                (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
+                                                (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
   VSM_LAUNCHED();
 
   // ---- distinct voxels -> global map; points -> sorted entries ---------------------------------------------
-  local_compact_kernel<<<vgrid, 256, 0, s>>>(tb, ctr, ws->lv_cnt.as<uint32_t>(), ws->lv_off.as<uint32_t>(),
-                                             ws->lv_cursor.as<uint32_t>());
-  VSM_LAUNCHED();
-  global_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ws->lv_cnt.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
-                                            m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
-                                            m->log_mask.as<unsigned long long>(), p->submap_id, ctr);
+  compact_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, ws->lv_off.as<uint32_t>(),
+                                             ws->lv_cursor.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
+                                             m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
+                                             m->log_mask.as<unsigned long long>(), p->submap_id);
   VSM_LAUNCHED();
 
   FuseRecord& rec = m->fuses[call.fuse_index];
@@ -1322,12 +1616,18 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   aa.nvec = (int)(row_bytes / 16);
   aa.ctr = ctr;
   if (!pixel_order) {
-    scatter_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
-                                        ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
-                                        ws->lv_gid.as<int32_t>(), check ? 1 : 0,
-                                        ws->sorted_pix[ab].as<unsigned long long>(), point_gid, ctr);
+    if (patch)
+      scatter_kernel<true><<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), pm, tb,
+                                                ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
+                                                ws->lv_gid.as<int32_t>(), check ? 1 : 0,
+                                                ws->sorted_pix[ab].as<unsigned long long>(), point_gid, ctr);
+    else
+      scatter_kernel<false><<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), pm, tb,
+                                                 ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
+                                                 ws->lv_gid.as<int32_t>(), check ? 1 : 0,
+                                                 ws->sorted_pix[ab].as<unsigned long long>(), point_gid, ctr);
     VSM_LAUNCHED();
-    table_cleanup_kernel<<<vgrid, 256, 0, s>>>(tb);
+    tables_cleanup_kernel<<<vgrid, 256, 0, s>>>(ta, filters ? 1 : 0, tb);
     VSM_LAUNCHED();
     aa.emb = emb_dev;
     aa.pix_base = 0;
@@ -1347,10 +1647,10 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
       ws->acc_parity ^= 1;
     }
   } else {
-    point_gid_kernel<<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
-                                          ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
+    point_gid_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
+                                                         ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
     VSM_LAUNCHED();
-    table_cleanup_kernel<<<vgrid, 256, 0, s>>>(tb);
+    tables_cleanup_kernel<<<vgrid, 256, 0, s>>>(ta, filters ? 1 : 0, tb);
     VSM_LAUNCHED();
     aa.point_gid = point_gid;
     if (host == nullptr) {
@@ -1493,6 +1793,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     st.n_fused = (int64_t)c.n_fused;
     st.n_submap_voxels = c.n_occ_b;
     st.n_bad_emb_rows = (int64_t)c.n_bad_emb;
+    st.n_range_dropped = (int64_t)c.range_dropped;
     for (int i = 0; i < 3; ++i) {
       st.bbox_lo[i] = filters ? c.bounds[2 * i] : __builtin_nanf("");
       st.bbox_hi[i] = filters ? c.bounds[2 * i + 1] : __builtin_nanf("");
@@ -1563,7 +1864,8 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
 
 int fuse_collect_pending(vsm_map* m, cudaStream_t s) {
   if (m->pending.empty()) return VSM_OK;
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  WsLease ws_lock(m->ws, s);
+  VSM_TRY(ws_lock.status());
   return fuse_collect_locked(m, s, nullptr);
 }
 
@@ -1582,7 +1884,8 @@ extern "C" int vsm_fuse_submap_async(vsm_map* m, const float* pts_dev, const flo
     // keeps a per-call array alive in the record: fine, but nothing to gain from queueing
   }
   VSM_CUDA(cudaSetDevice(m->device));
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  WsLease ws_lock(m->ws, (cudaStream_t)stream);
+  VSM_TRY(ws_lock.status());
   return fuse_submit_locked(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p,
                             (cudaStream_t)stream);
 }
@@ -1594,7 +1897,8 @@ extern "C" int vsm_fuse_collect(vsm_map* m, vsm_fuse_stats* stats_host, int32_t 
     return VSM_E_INVALID;
   }
   VSM_CUDA(cudaSetDevice(m->device));
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  WsLease ws_lock(m->ws, (cudaStream_t)stream);
+  VSM_TRY(ws_lock.status());
   // calls that an earlier submit had to collect itself (full ring, contributor-log growth) come first
   std::vector<vsm_fuse_stats> out;
   out.swap(m->stats_backlog);
@@ -1616,7 +1920,8 @@ extern "C" int vsm_fuse_submap(vsm_map* m, const float* pts_dev, const float* co
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  WsLease ws_lock(m->ws, s);
+  VSM_TRY(ws_lock.status());
   VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
   VSM_TRY(fuse_submit_locked(m, pts_dev, conf_dev, (const uint8_t*)emb_dev, emb_ok_dev, nullptr, p, s));
   const int st = fuse_collect_locked(m, s, nullptr);
@@ -1638,7 +1943,8 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   }
   VSM_CUDA(cudaSetDevice(m->device));
   cudaStream_t s = (cudaStream_t)stream;
-  std::lock_guard<std::mutex> ws_lock(m->ws->mu);
+  WsLease ws_lock(m->ws, s);
+  VSM_TRY(ws_lock.status());
   VSM_TRY(fuse_collect_locked(m, s, &m->stats_backlog));
   const size_t n_px = (size_t)p->end_idx * p->H * p->W;
   VSM_TRY(m->stage_pts.ensure(std::max<size_t>(n_px * 12, 16), s));
@@ -1733,10 +2039,10 @@ extern "C" int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, c
   const int64_t row_bytes = (int64_t)m->d * m->esize;
   const int nvec = (int)(row_bytes / 16);
   if (m->cfg.emb_dtype == VSM_BF16)
-    emb_row_mask_kernel<true><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
+    emb_row_mask_kernel<true><<<sm_count() * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
                                                       p->W, p->stride, p->conf_threshold, out_mask_dev);
   else
-    emb_row_mask_kernel<false><<<148 * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
+    emb_row_mask_kernel<false><<<sm_count() * 8, 256, 0, s>>>(conf_dev, (const uint8_t*)emb_dev, p->emb_index_dev, p->emb_rows, row_bytes, nvec, n_px, p->H,
                                                        p->W, p->stride, p->conf_threshold, out_mask_dev);
   VSM_LAUNCHED();
   return VSM_OK;
@@ -1749,6 +2055,18 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "select_mode") && value >= 0 && value <= 2) {
     g_select_mode = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "prep_variant") && value >= 0 && value <= 7) {
+    g_prep_variant = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_variant") && (value == 0 || value == 1)) {
+    g_acc_variant = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
+    g_range_policy = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "overlap") && (value == 0 || value == 1)) {

@@ -360,14 +360,14 @@ extern "C" int vsm_partials_push(vsm_map* m, int32_t world, void* const* inbox_p
   const PeerPtrs peers = peer_ptrs(inbox_ptrs_host, world, L, (int)(epoch & 1));
   const uint32_t V = (uint32_t)m->n_vox;
   if (V) {
-    push_rows_kernel<<<grid_for(V, 256, 148 * 4), 256, 0, s>>>(m->vkey.as<unsigned long long>(), m->vcount.as<uint32_t>(),
+    push_rows_kernel<<<grid_for(V, 256, sm_count() * 4), 256, 0, s>>>(m->vkey.as<unsigned long long>(), m->vcount.as<uint32_t>(),
                                                                m->vsum.as<float>(), V, m->d, (uint32_t)world, peers,
                                                                (uint32_t)cap_rows, L.row_stride);
     VSM_LAUNCHED();
   }
   const uint32_t M = (uint32_t)m->log_n;
   if (M) {
-    push_contrib_kernel<<<grid_for(M, 256, 148 * 4), 256, 0, s>>>(m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
+    push_contrib_kernel<<<grid_for(M, 256, sm_count() * 4), 256, 0, s>>>(m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
                                                                   m->log_mask.as<unsigned long long>(),
                                                                   m->vkey.as<unsigned long long>(), M, (uint32_t)world, peers,
                                                                   (uint32_t)cap_contrib);
@@ -411,17 +411,16 @@ extern "C" int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_
   const unsigned long long timeout_ns = (unsigned long long)(std::max(timeout_s, 0.001) * 1e9);
   uint32_t rep[4] = {0, 0, 0, 0};
   {
-    std::lock_guard<std::mutex> ws_lock(m->ws->mu);
-    VSM_TRY(m->ws->lv_gid.ensure((size_t)cap_rows * 4, s));
+    VSM_TRY(m->xch_tmp.ensure((size_t)cap_rows * 4, s));
     inbox_wait_kernel<<<1, 1, 0, s>>>(hdr, (uint32_t)world, timeout_ns);
     VSM_LAUNCHED();
-    drain_keys_kernel<<<grid_for(cap_rows, 256, 148 * 8), 256, 0, s>>>(global_store(m), hdr, rows, L.row_stride, (uint32_t)cap_rows,
-                                                                       m->ws->lv_gid.as<int32_t>(), &ctr->internal_err);
+    drain_keys_kernel<<<grid_for(cap_rows, 256, sm_count() * 8), 256, 0, s>>>(global_store(m), hdr, rows, L.row_stride, (uint32_t)cap_rows,
+                                                                       m->xch_tmp.as<int32_t>(), &ctr->internal_err);
     VSM_LAUNCHED();
-    drain_rows_kernel<<<148 * 8, 256, 0, s>>>(hdr, rows, L.row_stride, (uint32_t)cap_rows, m->ws->lv_gid.as<int32_t>(), m->d,
+    drain_rows_kernel<<<sm_count() * 8, 256, 0, s>>>(hdr, rows, L.row_stride, (uint32_t)cap_rows, m->xch_tmp.as<int32_t>(), m->d,
                                               m->vsum.as<float>());
     VSM_LAUNCHED();
-    drain_contrib_kernel<<<grid_for(cap_contrib, 256, 148 * 8), 256, 0, s>>>(
+    drain_contrib_kernel<<<grid_for(cap_contrib, 256, sm_count() * 8), 256, 0, s>>>(
         global_store(m), hdr, contrib, (uint32_t)cap_contrib, m->d_n_vox.as<uint32_t>(),
         (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll), m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
         m->log_mask.as<unsigned long long>());

@@ -77,6 +77,15 @@ extern "C" int vsm_conf_threshold(const float* conf_dev, int64_t n, double perce
     return VSM_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
+  int dev = 0;
+  VSM_CUDA(cudaGetDevice(&dev));
+  Workspace* ws = workspace_for_device(dev);
+  if (!ws) {
+    set_error("vsm_conf_threshold: device ordinal %d not supported", dev);
+    return VSM_E_INVALID;
+  }
+  WsLease lease(ws, s);  // the select scratch is shared with the fuse calls of this device
+  VSM_TRY(lease.status());
   SelectState* st;
   uint32_t* hist;
   float* out_dev;

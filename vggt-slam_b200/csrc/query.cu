@@ -309,8 +309,7 @@ int query_exact_rows(vsm_map* m, const float* q_dev, int P, int k, int normalize
   const int d = m->d;
   int cap = 2 * kQBatch;
   while (cap < 2 * k) cap <<= 1;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const int n_sm = sm_count();
   const int n_batches = (int)((V + kQBatch - 1) / kQBatch);
   const int grid = std::max(1, std::min(n_batches, n_sm * 2));
   VSM_TRY(m->q_cand.ensure((size_t)P * grid * k * 8, s));

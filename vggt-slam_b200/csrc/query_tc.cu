@@ -788,8 +788,7 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
                                   : (tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows));
   VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, pair ? kTileM : tile_rows, (uint64_t)stride * d));
   VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)(pair ? tile_n / 2 : tile_n)));
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const int n_sm = sm_count();
   const uint32_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
   const int grid = pair ? 2 * (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm / 2) : (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
   const size_t pair_smem = PairCfg<256>::kSmemBytes;
@@ -837,7 +836,7 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
     VSM_LAUNCHED();
   }
   // the list's length lives on the device: a fixed grid strides over it
-  rescore_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
+  rescore_kernel<<<sm_count() * 8, 256, 0, s>>>(m->vsum.as<float>(), m->vcount.as<uint32_t>(), m->rank_of_id.as<uint32_t>(), q_dev, d,
                                          normalize, sc.pairs, pair_cnt, pair_cap, sc.cand_cnt, sc.cap, sc.keys);
   VSM_LAUNCHED();
   if (fell_back) {
@@ -889,7 +888,7 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
   sc.cap = 1u << 16;
   VSM_TRY(m->q_norm.ensure((size_t)std::max<uint32_t>(V, 1) * 4, s));
   if (!m->norms_valid) {
-    row_norm_kernel<<<148 * 8, 256, 0, s>>>(m->vsum.as<float>(), V, d, m->q_norm.as<float>());
+    row_norm_kernel<<<sm_count() * 8, 256, 0, s>>>(m->vsum.as<float>(), V, d, m->q_norm.as<float>());
     VSM_LAUNCHED();
     m->norms_valid = true;
   }

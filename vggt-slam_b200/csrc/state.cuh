@@ -28,15 +28,20 @@ struct DevBuf {
   }
 };
 
-// submap-local open-addressing table (device view)
+// submap-local open-addressing table (device view).  One slot is ONE 32-byte sector: a claim reads and updates a
+// single sector instead of one per array (the tables are sized for the pixel count, ~0.5 GB, and probed at random).
+struct alignas(32) Slot {
+  unsigned long long key;      // kEmptyKey when free
+  uint32_t count;              // points of the key in this call
+  uint32_t lid;                // dense local id (index into slot_list), set by the compact step
+  unsigned long long mask[2];  // frames of the submap that hit the voxel (fine table only)
+};
+static_assert(sizeof(Slot) == 32, "a table slot is one 32-byte sector");
 struct LocalTable {
-  unsigned long long* keys;  // kEmptyKey when free
-  uint32_t* count;           // points per key
-  uint32_t* lid;             // local dense id of the slot (index into slot_list)
-  unsigned long long* mask;  // 2 x u64 frame mask per slot (fine table only, else nullptr)
-  uint32_t* slot_list;       // occupied slots in claim order
-  uint32_t* n_occ;           // number of occupied slots (device counter)
-  uint32_t cap_mask;         // capacity - 1
+  Slot* slots;
+  uint32_t* slot_list;  // occupied slots in claim order
+  uint32_t* n_occ;      // number of occupied slots (device counter)
+  uint32_t cap_mask;    // capacity - 1
 };
 
 // device-resident counters of one fuse call (zeroed at the start of every call)
@@ -51,8 +56,10 @@ struct FuseCounters {
   uint32_t n_check;    // check-only entries appended behind the fused ones
   uint32_t log_base;   // first contributor-log entry of this call (allocated on the device)
   uint32_t bad_index;  // selected pixels whose embedding index lies outside the table
-  uint32_t pad1;
+  uint32_t ticket;     // blocks of the capacity-check kernel that have finished (the last one decides)
   float bounds[6];     // bbox filter bounds laid out [axis][lo,hi]
+  uint32_t vox_base;   // voxels in the map before this call: ids >= vox_base are new, their sum rows are still zero
+  uint32_t range_dropped;  // points dropped because a finite voxel coordinate cannot be packed ("coord_range_policy" 1)
 };
 
 // radix-select state (device)
@@ -67,6 +74,7 @@ struct SelectState {
   uint32_t nan_count[4];
   int n_targets;
   int targets_per_col;
+  int alias[kSelMaxTargets];               // lowest target of the same column with the same prefix (fast select)
 };
 
 // a fuse call that has been queued on the stream and not yet collected
@@ -102,9 +110,14 @@ struct Workspace {
   std::mutex mu;
   DevBuf pw;        // float4[N_px]
   DevBuf pt_slot;   // int32[N_px]
-  DevBuf ta_keys, ta_count, ta_lid, ta_list;           // coarse table
-  DevBuf tb_keys, tb_count, tb_lid, tb_list, tb_mask;  // fine table
+  DevBuf ta_slots, ta_list;  // coarse table
+  DevBuf tb_slots, tb_list;  // fine table
   uint64_t ta_cap = 0, tb_cap = 0;
+  // Stream order of the borrowers: every use of the workspace ends with an event on the borrower's stream; a borrower
+  // on ANOTHER stream waits for it first (two maps of one device fused on different streams share these buffers).
+  cudaEvent_t ev_last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
   DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
   DevBuf sorted_pix[2], sorted_gid;
   DevBuf sel_bracket;  // scratch of the one-pass percentile select
@@ -122,6 +135,22 @@ struct Workspace {
   bool overlap = false;
 };
 Workspace* workspace_for_device(int device);
+
+// Borrows the device workspace for work queued on stream `s`: takes the mutex, makes `s` wait for the previous
+// borrower's kernels if they ran on a different stream, and on release records the end of this use on `s`.
+class WsLease {
+ public:
+  WsLease(Workspace* ws, cudaStream_t s);
+  ~WsLease();
+  int status() const { return status_; }
+  WsLease(const WsLease&) = delete;
+  WsLease& operator=(const WsLease&) = delete;
+
+ private:
+  Workspace* ws_;
+  cudaStream_t s_;
+  int status_;
+};
 }  // namespace vsm
 
 struct vsm_map {
@@ -181,6 +210,7 @@ struct vsm_map {
   vsm::DevBuf ck_keys, ck_val;
   uint64_t ck_cap = 0;
   bool ck_built = false;
+  vsm::DevBuf xch_tmp;  // exchange scratch (owner offsets of a pack, voxel ids of a merge / drain): per map, not shared
   // query scratch
   vsm::DevBuf q_cand, q_tmp, q_norm;
   vsm::DevBuf q_tc, q_tc_cand;     // tensor-core engine: thresholds / padded prompts; candidate ids + keys
@@ -208,6 +238,10 @@ int run_percentiles(SelectState* st, uint32_t* hist, const SelSrc& src, int npct
 int select_reset(SelectState* st, uint32_t* hist, cudaStream_t s);
 int run_percentiles_after_hist0(SelectState* st, uint32_t* hist, const SelSrc& src, int npct, float q0, float q1,
                                 float* out_dev, const unsigned long long* n_dev, cudaStream_t s);
+// the same for the world-point layout, with the one-block steps merged (plan + pick, pick, pick + lerp) and targets
+// that share a prefix histogrammed once: 5 launches instead of 8
+int run_percentiles_world_fast(SelectState* st, uint32_t* hist, const float4* pw, int64_t n_items, uint32_t flag_need,
+                               float q0, float q1, float* out_dev, const unsigned long long* n_dev, cudaStream_t s);
 // process-wide scratch per device: select state, histograms, 16 result floats
 int select_scratch(SelectState** st, uint32_t** hist, float** out);
 int map_grow(vsm_map* m, int64_t need_voxels, cudaStream_t s);

@@ -42,12 +42,13 @@ class FuseParams(C.Structure):
 class FuseStats(C.Structure):
     _fields_ = [("n_conf", C.c_int64), ("n_finite", C.c_int64), ("n_bbox", C.c_int64), ("n_fused", C.c_int64),
                 ("n_submap_voxels", C.c_int64), ("n_map_voxels", C.c_int64), ("n_bad_emb_rows", C.c_int64),
-                ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3)]
+                ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3), ("n_range_dropped", C.c_int64)]
 
     def as_dict(self):
         return {"n_conf": self.n_conf, "n_finite": self.n_finite, "n_bbox": self.n_bbox, "n_fused": self.n_fused,
                 "n_submap_voxels": self.n_submap_voxels, "n_map_voxels": self.n_map_voxels,
-                "n_bad_emb_rows": self.n_bad_emb_rows, "bbox_lo": list(self.bbox_lo), "bbox_hi": list(self.bbox_hi)}
+                "n_bad_emb_rows": self.n_bad_emb_rows, "bbox_lo": list(self.bbox_lo), "bbox_hi": list(self.bbox_hi),
+                "n_range_dropped": self.n_range_dropped}
 
 
 class Profile(C.Structure):

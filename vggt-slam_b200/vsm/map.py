@@ -95,6 +95,40 @@ class GraphMap:
             for frame_id, pointcloud, mask in zip(frame_ids, pointclouds, conf_masks):
                 np.savez(f"{file_name}/{frame_id}.npz", pointcloud=pointcloud, mask=mask)
 
+    def save_frame_outputs(self, output_dir, ignore_loop_closure_frames=True):
+        """Per-frame world point map, confidence mask, world extrinsic and intrinsic as {output_dir}/{stem}.npz
+        (map.py:106-151): same keys, same file names (frame name stem, else str(frame id)), same skips (submaps
+        without points or transform; a length mismatch between point maps and extrinsics).  The point maps come
+        from vsm_transform_points; the extrinsics are Submap.get_all_poses_world's (host, SLAM back end)."""
+        os.makedirs(output_dir, exist_ok=True)
+        for submap in self.ordered_submaps_by_key():
+            if submap.pointclouds is None or submap.H_world_map is None:
+                continue
+            end_idx = _shape(submap.pointclouds)[0]
+            if ignore_loop_closure_frames and (submap.last_non_loop_frame_index is not None):
+                end_idx = min(end_idx, submap.last_non_loop_frame_index + 1)
+            pointclouds, frame_ids, conf_masks = submap.get_points_list_in_world_frame(
+                ignore_loop_closure_frames=ignore_loop_closure_frames)
+            extrinsics_world = submap.get_all_poses_world(ignore_loop_closure_frames=ignore_loop_closure_frames)
+            intrinsics = submap.vggt_intrinscs
+            if intrinsics is None:
+                intrinsics = [None] * len(pointclouds)
+            if len(pointclouds) != len(extrinsics_world):
+                print(f"Skipping submap {submap.get_id()} due to length mismatch: "
+                      f"{len(pointclouds)} point maps vs {len(extrinsics_world)} extrinsics.")
+                continue
+            frame_names = getattr(submap, "frame_names", None)
+            for idx in range(min(end_idx, len(pointclouds))):
+                if frame_names is not None and idx < len(frame_names):
+                    stem, _ = os.path.splitext(str(frame_names[idx]))
+                    filename = f"{stem}.npz"
+                else:
+                    frame_id = frame_ids[idx] if frame_ids is not None else idx
+                    filename = f"{str(frame_id)}.npz"
+                np.savez(os.path.join(output_dir, filename), point_map_world=pointclouds[idx],
+                         conf_mask=conf_masks[idx], extrinsic_world=extrinsics_world[idx],
+                         intrinsic=intrinsics[idx] if intrinsics is not None else None)
+
     # -- a7: global semantic voxel map (map.py:170-381) -----------------------------
     def build_semantic_voxel_map(self, voxel_size: float, stride: int = 1, ignore_loop_closure_frames: bool = True,
                                  deduplicate_contributors: bool = True, use_torch: bool = True,
@@ -163,8 +197,14 @@ class GraphMap:
             self.last_profile = dm.profile()
         return dm, fused, frame_name_maps
 
+    # Queued device-path calls keep their input tensors alive until they are collected.  For dense embeddings that
+    # arrive as HOST arrays the tensor is a full device copy (5-10 GB per submap at the benchmark's shape): collect
+    # once this many bytes of such copies are queued instead of letting up to 64 calls pile up.
+    MAX_QUEUED_COPY_BYTES = 24 << 30
+
     def _fuse_all(self, dm, todo, stride, ignore_loop, flags, host_streaming, fused, frame_name_maps):
         queued = []
+        queued_copy_bytes = 0
 
         def index_is_set(sm):
             return getattr(sm, "semantic_index", None) is not None
@@ -222,9 +262,19 @@ class GraphMap:
                 stats = dm.fuse_host(pts_h, conf_h, emb_h, params)
             else:
                 # queue the call; all queued calls are collected with one synchronisation below
-                dm.fuse_async(submap._device("points"), submap._device("conf"),
-                              submap.embeddings_on_device(cache=index is not None), params,
-                              keep_alive=index)
+                emb_dev = submap.embeddings_on_device(cache=index is not None)
+                if on_host and index is None:
+                    nbytes = emb_dev.numel() * emb_dev.element_size()
+                    try:
+                        budget = min(self.MAX_QUEUED_COPY_BYTES, torch.cuda.mem_get_info()[0] // 2 + queued_copy_bytes)
+                    except Exception:
+                        budget = self.MAX_QUEUED_COPY_BYTES
+                    if queued_copy_bytes and queued_copy_bytes + nbytes > budget:
+                        flush()
+                        queued_copy_bytes = 0
+                    queued_copy_bytes += nbytes
+                dm.fuse_async(submap._device("points"), submap._device("conf"), emb_dev, params, keep_alive=index)
+                del emb_dev
                 stats = None
             queued.append((stats, {"fuse_index": dm.fuse_calls - 1, "submap": submap, "S": S, "H": H, "W": W,
                                    "end_idx": end_idx, "sid": sid}))

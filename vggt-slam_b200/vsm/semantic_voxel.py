@@ -218,14 +218,22 @@ class SemanticVoxelMap:
         q = np.asarray(qe, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
-        try:
-            idx, sc = self._dm.query(q, top_k=top_k, normalize=normalize, engine=engine)
-        except ValueError as e:
-            if "exceeds" in str(e):
-                raise RuntimeError("selected index k out of range") from e
-            raise
-        idx = idx.cpu().numpy()
-        return idx, self._voxel_coords[idx], sc.cpu().numpy()
+        if int(top_k) > N.MAX_TOPK:
+            raise ValueError(f"top_k={top_k} exceeds the library limit VSM_MAX_TOPK={N.MAX_TOPK}")
+        # vsm_query scores at most VSM_MAX_PROMPTS prompts per call: larger batches go block by block (the
+        # reference loops one prompt at a time and has no limit, voxel_evaluators.py:61)
+        idx_blocks, sc_blocks = [], []
+        for p0 in range(0, max(q.shape[0], 1), N.MAX_PROMPTS):
+            try:
+                idx, sc = self._dm.query(q[p0:p0 + N.MAX_PROMPTS], top_k=top_k, normalize=normalize, engine=engine)
+            except ValueError as e:
+                if "exceeds" in str(e):
+                    raise RuntimeError("selected index k out of range") from e
+                raise
+            idx_blocks.append(idx.cpu().numpy())
+            sc_blocks.append(sc.cpu().numpy())
+        idx = np.concatenate(idx_blocks, axis=0)
+        return idx, self._voxel_coords[idx], np.concatenate(sc_blocks, axis=0)
 
     def query_with_embedding(self, qe: np.ndarray, top_k: int = 1, normalize: bool = False):
         """One prompt, the reference's return types: (list[int], (k,3) int64 array, list[float])."""

@@ -158,6 +158,27 @@ class Submap:
     def get_all_retrieval_vectors(self):
         return self.retrieval_vectors
 
+    def get_all_poses_world(self, ignore_loop_closure_frames=False):
+        """World camera poses of the frames (submap.py:91-104): the projection K @ inv(pose)[:3] @ inv(H_world_map) is
+        decomposed (cv2.decomposeProjectionMatrix) into rotation and camera centre.  Host code of the SLAM back end,
+        kept because GraphMap.save_frame_outputs writes its result next to the point maps."""
+        import cv2
+
+        poses_in = np.asarray(self.poses)
+        K = np.asarray(self.vggt_intrinscs)
+        projection_mat_list = K @ np.linalg.inv(poses_in)[:, 0:3, :] @ np.linalg.inv(np.asarray(self.H_world_map))
+        poses = []
+        for index, projection_mat in enumerate(projection_mat_list):
+            cal, rot, trans = cv2.decomposeProjectionMatrix(projection_mat)[0:3]
+            trans = trans / trans[3, 0]
+            pose = np.eye(4)
+            pose[0:3, 0:3] = np.linalg.inv(rot)
+            pose[0:3, 3] = trans[0:3, 0]
+            poses.append(pose)
+            if ignore_loop_closure_frames and index == self.last_non_loop_frame_index:
+                break
+        return np.stack(poses, axis=0)
+
     def get_frame_pointcloud(self, pose_index):
         return self.pointclouds[pose_index]
 
