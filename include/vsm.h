@@ -143,6 +143,11 @@ VSM_API int vsm_map_destroy(vsm_map* m);
 VSM_API int vsm_map_cache_release(void);
 VSM_API int vsm_map_clear(vsm_map* m, void* stream);
 VSM_API int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream);
+/* room for `entries` contributor-log entries (one per fuse call and voxel, or per received contributor record) */
+VSM_API int vsm_map_reserve_log(vsm_map* m, int64_t entries, void* stream);
+/* vsm_map_clear without the host waiting: the resets are queued on `stream` behind whatever still reads the map there
+ * (an exchange push).  Only valid when no fuse call is pending; ordering against other streams is the caller's. */
+VSM_API int vsm_map_clear_async(vsm_map* m, void* stream);
 
 /* ---- a1: Submap.add_all_points' np.percentile(conf, pct) (submap.py:38) --
  * numpy-2 'linear' method on float32 data (index arithmetic in float32).  Synchronises. */
@@ -211,6 +216,8 @@ VSM_API int vsm_embedding_row_mask(const vsm_map* m, const float* conf_dev, cons
 /* sorts the voxel keys lexicographically (np.unique(axis=0) order), builds rank maps and the contributor CSR. Synchronises. */
 VSM_API int vsm_finalize(vsm_map* m, void* stream);
 VSM_API int vsm_num_voxels(const vsm_map* m, int64_t* out_host);
+/* contributor-log entries held (one per collected fuse call and voxel it touched, plus merged / drained records) */
+VSM_API int vsm_num_log_entries(const vsm_map* m, int64_t* out_host);
 /* sorted order; any pointer may be NULL.  coords int64[V*3] true keys, centers float[V*3] = (coords+0.5)*vs,
  * counts int64[V], recon_coords int64[V*3] = floor(centers/vs - 0.5) (semantic_voxel.py:62-66, lossy) */
 VSM_API int vsm_export_geometry(const vsm_map* m, int64_t* coords_dev, float* centers_dev, int64_t* counts_dev,
@@ -228,6 +235,12 @@ VSM_API int vsm_export_point_index(const vsm_map* m, int32_t fuse_index, int32_t
 
 /* a loaded map (SemanticVoxelMap.load_from_directory, semantic_voxel.py:150-165): rows are taken in file order */
 VSM_API int vsm_map_load_dense(vsm_map* m, const float* centers_dev, const float* features_dev, int64_t V, void* stream);
+
+/* The same load in row blocks, for files larger than the device can hold twice: begin sizes the map for V rows, rows
+ * copies rows [r0, r0+n_rows) (centres float[n_rows*3], features float[n_rows*d], device pointers), vsm_finalize ends it. */
+VSM_API int vsm_map_load_begin(vsm_map* m, int64_t V, void* stream);
+VSM_API int vsm_map_load_rows(vsm_map* m, int64_t r0, int64_t n_rows, const float* centers_dev, const float* features_dev,
+                              void* stream);
 
 /* ---- a12: position -> voxel index (semantic_voxel.py:68-80) -------------- *
  * compat != 0 reproduces the reference's table keyed by the lossy reconstructed coordinates
@@ -278,9 +291,51 @@ VSM_API int vsm_partials_push(vsm_map* m, int32_t world, void* const* inbox_ptrs
                       int64_t epoch, void* stream);
 VSM_API int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib, int64_t epoch,
                        double timeout_s, int64_t* n_rows_host, int64_t* n_contrib_host, uint32_t* flags_host, void* stream);
+/* The two halves of vsm_partials_drain for exchanges that run BESIDE fusion (rounds of a long build: the exchange of
+ * round r on one stream while round r+1 is fused on another).  _async queues the wait + merge on `stream` and returns;
+ * the map must already have room for what can arrive (vsm_map_reserve, vsm_map_reserve_log): it is not grown.
+ * _collect synchronises `stream`, reads the report of slot `report_slot` (0..3, one per drain in flight), updates the
+ * map's voxel count and maps overflow / timeout to the same status codes as vsm_partials_drain. */
+VSM_API int vsm_partials_drain_async(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib,
+                                     int64_t epoch, double timeout_s, int32_t report_slot, void* stream);
+VSM_API int vsm_partials_drain_collect(vsm_map* m, int32_t report_slot, int64_t* n_rows_host, int64_t* n_contrib_host,
+                                       uint32_t* flags_host, void* stream);
 
 /* sorted packed keys of this map's voxels (uint64[V]); pack/unpack helpers for global ranking across owners */
 VSM_API int vsm_export_packed_keys(const vsm_map* m, uint64_t* keys_dev, void* stream);
+
+/* global index of this shard's keys among the keys of all shards (disjoint, each sorted): all_keys_dev is the
+ * all-gather buffer, shard r = all_keys_dev[r*shard_stride .. r*shard_stride + shard_sizes_host[r]); ranks_dev int64[n_mine] */
+VSM_API int vsm_global_ranks(const uint64_t* my_keys_dev, int64_t n_mine, const uint64_t* all_keys_dev, int64_t shard_stride,
+                             const int64_t* shard_sizes_host, int32_t world, int64_t* ranks_dev, void* stream);
+
+/* ---- f3: scoring of the projective RANSAC hypotheses (h_solve.py:16-41, 150-160) -------------------------------- *
+ * H_dev float[B*16] row-major 4x4 hypotheses, X1_dev / X2_dev float[N*3]: counts_dev[b] = #{n : ||(H_b [X1_n;1])_xyz / w
+ * - X2_n||_2 < threshold} in float32 arithmetic; best_dev int32[2] = (argmax, its count), first maximum wins like
+ * torch.argmax.  best_idx_host / best_count_host may be NULL (then the call does not synchronise). */
+VSM_API int vsm_ransac_score(const float* H_dev, const float* X1_dev, const float* X2_dev, int64_t N, int32_t B,
+                             float threshold, int32_t* counts_dev, int32_t* best_dev, int32_t* best_idx_host,
+                             int32_t* best_count_host, void* stream);
+
+/* ---- f4: occupancy grid of a point cloud (get_occupancy.py:130-179 build_occupancy_from_pointcloud) ------------- *
+ * pts_dev float[n*3].  Cells in np.unique(axis=0) order: centers_dev float[cells*3], blocked_dev uint8[cells],
+ * keys_dev int64[cells*2], minz_dev float[cells]; outputs may be NULL.  n_cells_host receives the number of cells
+ * (call with cap_cells = 0 and NULL outputs to size the arrays; VSM_E_NOMEM if cap_cells is too small), n_kept_host
+ * the points that survived the finite / ceiling filters.  Synchronises. */
+VSM_API int vsm_occupancy_build(const float* pts_dev, int64_t n, double voxel_size, double ceiling_z, double height_thresh,
+                                int64_t cap_cells, float* centers_dev, uint8_t* blocked_dev, int64_t* keys_dev,
+                                float* minz_dev, int64_t* n_cells_host, int64_t* n_kept_host, void* stream);
+
+/* ---- f2: producer hand-off (solver.py:249-263, 301, 337-340, 478-480) on the device ------------------------------ *
+ * vsm_unproject_depth: depth (S,H,W) float32, cam_to_world double[S*12] (row-major 3x4 [R|t], the closed-form inverse
+ * of the extrinsic), intrinsic float[S*9] -> world points (S,H,W,3), float32 or float64 (vggt.utils.geometry's
+ * unproject_depth_map_to_point_map restated; that dependency is not vendored upstream: parity unpinned).
+ * vsm_images_to_colors: images (S,3,H,W) float32 in [0,1] -> colors (S,H,W,3) uint8 = (img * 255).astype(uint8).
+ * vsm_scale_points: p *= scale over n_floats floats (product in float64, stored float32, as numpy's in-place op). */
+VSM_API int vsm_unproject_depth(const float* depth_dev, const double* cam_to_world_dev, const float* intrinsic_dev, int32_t S,
+                                int32_t H, int32_t W, void* out_dev, int out_f64, void* stream);
+VSM_API int vsm_images_to_colors(const float* images_dev, int32_t S, int32_t H, int32_t W, uint8_t* colors_dev, void* stream);
+VSM_API int vsm_scale_points(float* pts_dev, int64_t n_floats, double scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,8 @@ for i in range(n_sub):
 torch.cuda.synchronize()
 print(f"{'voxel':>6} {'prep':>5} {'acc':>4} {'fuse ms/submap':>15} {'accumulate ms':>14} {'prep ms':>8} {'voxels':>9}")
 for vs in (0.05, 0.02):
-    for prep, acc in ((0, 0), (1, 0), (4, 0), (5, 0), (7, 0), (5, 1), (7, 1)):
+    for prep, acc in ((0, 0), (1, 0), (4, 0), (5, 0)):
         N.set_option("prep_variant", prep)
-        N.set_option("acc_variant", acc)
         hint = 1 << 18
         for _ in range(3):
             m = gm.build_semantic_voxel_map(vs, capacity_hint=hint, profile=True)
@@ -38,4 +37,3 @@ for vs in (0.05, 0.02):
         print(f"{vs:6.2f} {prep:5d} {acc:4d} {f:15.4f} {a:14.4f} {f - a:8.4f} {m._dm.num_voxels:9d}", flush=True)
         del m
 N.set_option("prep_variant", 5)
-N.set_option("acc_variant", 1)

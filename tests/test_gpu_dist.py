@@ -157,3 +157,97 @@ def test_peer_inbox_overflow_and_timeout_are_reported():
     om.close()
     dm.close()
     small.free()
+
+
+def test_rounds_with_queued_drains_equal_single_map():
+    """The streaming exchange of a long build, every 'rank' on this GPU: per round each rank fuses a few submaps into
+    a local map, pushes it, clears it without waiting (vsm_map_clear_async) and every owner QUEUES its drain
+    (vsm_partials_drain_async); the reports are collected once, at the end.  Union of the owner shards == one map."""
+    import torch
+    import vsm
+    from vsm import peer
+    from vsm import voxel_map as vm
+    from vsm.map import wrap_device_map
+
+    world, rounds, per_round = 2, 3, 2
+    dev = torch.device("cuda", 0)
+    subs = [synth.make_submap(73, i, S=3, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
+                              first_frame_number=3 * i) for i in range(world * rounds * per_round)]
+    single = _local_map(vsm, subs, 0.05).build_semantic_voxel_map(0.05)
+    s_keys = single._dm.export_packed_keys().cpu().numpy()
+    s_counts = single._dm.export_geometry()[2].cpu().numpy()
+    cap_rows, cap_contrib = len(s_keys) + 8, 4 * len(s_keys)
+    inboxes = [peer.Inbox(dev, 64, cap_rows, cap_contrib, shared=False) for _ in range(world)]
+    ptrs = [b.ptr for b in inboxes]
+    owners = [vm.DeviceVoxelMap(0.05, 64, 0, capacity=len(s_keys) + 1024) for _ in range(world)]
+    for o in owners:
+        o.reserve_log(rounds * world * cap_contrib)
+    locals_ = [vm.DeviceVoxelMap(0.05, 64, 0, capacity=1 << 15) for _ in range(world)]
+    fused_all, names = [], {}
+    for r in range(rounds):
+        for k in range(world):
+            mine = subs[k::world][r * per_round:(r + 1) * per_round]
+            gm = _local_map(vsm, mine, 0.05)
+            _, fused, nm = gm.fuse_into_device_map(0.05, dm=locals_[k], submaps=gm.usable_submaps())
+            fused_all += fused
+            names.update(nm)
+            assert locals_[k].num_log_entries == sum(s["n_submap_voxels"] for s in gm.last_build_stats)
+            peer.push(locals_[k], ptrs, cap_rows, cap_contrib, r)
+            locals_[k].clear_async()
+            assert locals_[k].num_voxels == 0
+        for o in range(world):
+            peer.drain_async(owners[o], ptrs[o], world, cap_rows, cap_contrib, r, slot=0, timeout_s=5.0)
+    got = [peer.drain_collect(o, slot=0) for o in owners]
+    assert sum(g[0] for g in got) >= len(s_keys)
+    for o in owners:
+        o.finalize()
+    all_keys = np.concatenate([o.export_packed_keys().cpu().numpy() for o in owners])
+    assert len(np.unique(all_keys)) == len(all_keys) == len(s_keys)
+    order = np.argsort(all_keys.view(np.uint64), kind="stable")
+    np.testing.assert_array_equal(all_keys[order], s_keys)
+    np.testing.assert_array_equal(np.concatenate([o.export_geometry()[2].cpu().numpy() for o in owners])[order], s_counts)
+    np.testing.assert_allclose(np.concatenate([o.features_to_host() for o in owners])[order], single.get_features(),
+                               rtol=1e-3, atol=1e-5)
+    contribs = []
+    for o in owners:
+        contribs += wrap_device_map(o, fused_all, names, 0.05).get_contributors().tolist()
+    assert [contribs[i] for i in order] == single.get_contributors().tolist()
+    # an owner without room reports it at the collect instead of growing behind the host's back
+    tiny = vm.DeviceVoxelMap(0.05, 64, 0, capacity=1024)
+    gm = _local_map(vsm, subs[:2], 0.05)
+    dm, _, _ = gm.fuse_into_device_map(0.05)
+    assert dm.num_voxels > 1024
+    peer.push(dm, [ptrs[0]], cap_rows, cap_contrib, rounds)
+    peer.drain_async(tiny, ptrs[0], 1, cap_rows, cap_contrib, rounds, slot=1, timeout_s=5.0)
+    with pytest.raises(MemoryError):
+        peer.drain_collect(tiny, slot=1)
+    for m in owners + locals_ + [tiny, dm]:
+        m.close()
+    for b in inboxes:
+        b.free()
+
+
+def test_global_ranks_kernel():
+    """vsm_global_ranks against numpy: disjoint sorted shards of unequal length, padded like the all-gather buffer."""
+    import ctypes as C
+
+    import torch
+    from vsm import _native as N
+
+    rng = np.random.default_rng(3)
+    keys = np.unique(rng.integers(0, 1 << 62, size=200_000, dtype=np.int64))
+    owner = rng.integers(0, 3, size=keys.size)
+    shards = [np.sort(keys[owner == r]) for r in range(3)]
+    shards.append(np.zeros(0, np.int64))  # an empty shard
+    stride = max(len(s) for s in shards)
+    buf = np.full((4, stride), np.iinfo(np.int64).max, dtype=np.int64)
+    for r, sh in enumerate(shards):
+        buf[r, :len(sh)] = sh
+    allk = torch.from_numpy(buf).cuda()
+    sizes = (C.c_int64 * 4)(*[len(s) for s in shards])
+    for r, sh in enumerate(shards):
+        mine = torch.from_numpy(sh).cuda()
+        out = torch.empty_like(mine)
+        N.check(N.lib.vsm_global_ranks(C.c_void_p(mine.data_ptr()), len(sh), C.c_void_p(allk.data_ptr()), stride, sizes, 4,
+                                       C.c_void_p(out.data_ptr()), None))
+        np.testing.assert_array_equal(out.cpu().numpy(), np.searchsorted(keys, sh))

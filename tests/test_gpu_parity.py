@@ -214,17 +214,15 @@ def fuse_overlap(request):
     N.set_option("overlap", 0)
 
 
-@pytest.fixture(params=[(0, 0), (5, 1), (7, 1)], ids=["row_kernels", "default_kernels", "mask_probe"])
+@pytest.fixture(params=[0, 5, 7], ids=["row_kernels", "default_kernels", "mask_probe"])
 def kernel_variant(request):
     """The preparation kernels with a warp per 32-pixel row run / per 4x8 patch (+ merged select steps, + frame-mask
-    probe) and the chunked / segment-owning accumulate kernel: every combination must give the reference's map."""
+    probe): every combination must give the reference's map."""
     from vsm import _native as N
 
-    N.set_option("prep_variant", request.param[0])
-    N.set_option("acc_variant", request.param[1])
+    N.set_option("prep_variant", request.param)
     yield request.param
     N.set_option("prep_variant", 5)
-    N.set_option("acc_variant", 1)
 
 
 def graph_from(vsm, subs, **kw):
@@ -312,8 +310,7 @@ def test_build_global_oracle(vsm_mod, dtype, stride, select_mode, fuse_overlap, 
 @pytest.mark.parametrize("dtype", ["f32", "bf16"])
 def test_segment_shapes_against_oracle(vsm_mod, voxel_size, dtype, kernel_variant):
     """Voxel segments of ~1 row (1.2 cm voxels), tens of rows and thousands of rows (40 cm voxels: segments that run
-    through several 32-entry chunks) through both accumulate kernels, d = 256 (full rows: the owned-segment kernel),
-    fused twice so that the second pass meets voxels that are no longer new."""
+    through several 32-entry chunks of the sorted list), d = 256 (full rows: the hot loop of the accumulate kernel)."""
     subs = [synth.make_submap(47, i, S=3, H=56, W=84, d=256, mode="sl4", room=(2.4, 1.8, 1.2), start=0.2 * i,
                               first_frame_number=3 * i) for i in range(3)]
     with np.errstate(all="ignore"):

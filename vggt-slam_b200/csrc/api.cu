@@ -269,7 +269,7 @@ static int map_destroy_now(vsm_map* m) {
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
                          &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm,
-                         &m->q_tc,      &m->q_tc_cand,  &m->xch_tmp};
+                         &m->q_tc,      &m->q_tc_cand,  &m->xch_tmp,   &m->drain_report};
   for (auto* b : bufs) b->release();
   for (auto& f : m->fuses) f.point_gid.release();
   if (m->pinned) cudaFreeHost(m->pinned);
@@ -329,6 +329,50 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
   return VSM_OK;
 }
 
+// vsm_map_clear without the host waiting: the resets are queued on `stream` behind whatever still reads the map there
+// (an exchange push, an export).  Only valid when no fuse call is pending; the caller orders other streams itself.
+extern "C" int vsm_map_clear_async(vsm_map* m, void* stream) {
+  if (!m) {
+    set_error("null map");
+    return VSM_E_INVALID;
+  }
+  if (!m->pending.empty()) {
+    set_error("vsm_map_clear_async: the map has uncollected fuse calls");
+    return VSM_E_STATE;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  VSM_CUDA(cudaMemsetAsync(m->gkeys.p, 0xFF, m->gcap * 8, s));
+  VSM_CUDA(cudaMemsetAsync(m->gids.p, 0xFF, m->gcap * 4, s));
+  const size_t used = std::min<size_t>((size_t)m->vcap, (size_t)m->n_vox);
+  if (used) {
+    VSM_CUDA(cudaMemsetAsync(m->vcount.p, 0, used * 4, s));
+    VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, used * (size_t)m->d * 4, s));
+  }
+  VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, 2 * sizeof(uint32_t), s));
+  m->stats_backlog.clear();
+  m->n_vox = 0;
+  m->log_n = 0;
+  m->last_n_occ = 0;
+  for (auto& f : m->fuses) f.point_gid.release();
+  m->fuses.clear();
+  m->finalized = false;
+  m->norms_valid = false;
+  m->dense_loaded = false;
+  m->ck_built = false;
+  m->csr_entries = 0;
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_reserve_log(vsm_map* m, int64_t entries, void* stream) {
+  if (!m || entries < 0) {
+    set_error("vsm_map_reserve_log: bad arguments");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  return log_grow(m, entries, (cudaStream_t)stream);
+}
+
 extern "C" int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream) {
   if (!m) {
     set_error("null map");
@@ -336,6 +380,15 @@ extern "C" int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream)
   }
   VSM_CUDA(cudaSetDevice(m->device));
   return map_grow(m, voxel_capacity, (cudaStream_t)stream);
+}
+
+extern "C" int vsm_num_log_entries(const vsm_map* m, int64_t* out_host) {
+  if (!m || !out_host) {
+    set_error("null argument");
+    return VSM_E_INVALID;
+  }
+  *out_host = m->log_n;
+  return VSM_OK;
 }
 
 extern "C" int vsm_num_voxels(const vsm_map* m, int64_t* out_host) {

@@ -398,10 +398,11 @@ extern "C" int vsm_export_packed_keys(const vsm_map* m, uint64_t* keys_dev, void
   return VSM_OK;
 }
 
-extern "C" int vsm_map_load_dense(vsm_map* m, const float* centers_dev, const float* features_dev, int64_t V,
-                                  void* stream) {
-  if (!m || V < 0 || (V > 0 && (!centers_dev || !features_dev))) {
-    set_error("vsm_map_load_dense: bad arguments");
+// A loaded map (semantic_voxel.py:150-165) arrives in chunks so that a 50 M-voxel file is never resident twice:
+// begin (sizes the map), rows (any number of row blocks, straight into the sum rows), end (= finalisation).
+extern "C" int vsm_map_load_begin(vsm_map* m, int64_t V, void* stream) {
+  if (!m || V < 0 || V >= ((int64_t)1 << 31)) {
+    set_error("vsm_map_load_begin: bad arguments");
     return VSM_E_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -411,15 +412,95 @@ extern "C" int vsm_map_load_dense(vsm_map* m, const float* centers_dev, const fl
   m->n_vox = V;
   if (V) {
     VSM_TRY(m->dense_centers.ensure((size_t)V * 12, s));
-    VSM_CUDA(cudaMemcpyAsync(m->dense_centers.p, centers_dev, (size_t)V * 12, cudaMemcpyDeviceToDevice, s));
-    VSM_CUDA(cudaMemcpyAsync(m->vsum.p, features_dev, (size_t)V * m->d * 4, cudaMemcpyDeviceToDevice, s));
     fill_u32_kernel<<<grid_for(V, 256), 256, 0, s>>>(m->vcount.as<uint32_t>(), 1u, V);
     VSM_LAUNCHED();
     const uint32_t v32 = (uint32_t)V;
     VSM_CUDA(cudaMemcpyAsync(m->d_n_vox.p, &v32, 4, cudaMemcpyHostToDevice, s));
     VSM_CUDA(cudaStreamSynchronize(s));
   }
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_load_rows(vsm_map* m, int64_t r0, int64_t n_rows, const float* centers_dev, const float* features_dev,
+                                 void* stream) {
+  if (!m || !m->dense_loaded || m->finalized || r0 < 0 || n_rows < 0 || r0 + n_rows > m->n_vox ||
+      (n_rows > 0 && (!centers_dev || !features_dev))) {
+    set_error("vsm_map_load_rows: bad row block, or no vsm_map_load_begin before it");
+    return m && (!m->dense_loaded || m->finalized) ? VSM_E_STATE : VSM_E_INVALID;
+  }
+  if (n_rows == 0) return VSM_OK;
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  VSM_CUDA(cudaMemcpyAsync(m->dense_centers.as<float>() + 3 * r0, centers_dev, (size_t)n_rows * 12,
+                           cudaMemcpyDeviceToDevice, s));
+  VSM_CUDA(cudaMemcpyAsync(m->vsum.as<float>() + (size_t)r0 * m->d, features_dev, (size_t)n_rows * m->d * 4,
+                           cudaMemcpyDeviceToDevice, s));
+  return VSM_OK;
+}
+
+extern "C" int vsm_map_load_dense(vsm_map* m, const float* centers_dev, const float* features_dev, int64_t V,
+                                  void* stream) {
+  if (!m || V < 0 || (V > 0 && (!centers_dev || !features_dev))) {
+    set_error("vsm_map_load_dense: bad arguments");
+    return VSM_E_INVALID;
+  }
+  VSM_TRY(vsm_map_load_begin(m, V, stream));
+  VSM_TRY(vsm_map_load_rows(m, 0, V, centers_dev, features_dev, stream));
   return vsm_finalize(m, stream);
+}
+
+// ---- global voxel index of an owner shard ------------------------------------------------------------
+// Every rank holds the sorted keys of ALL ranks (all-gathered, 8 bytes per voxel) and ranks its own keys among them:
+// shards are disjoint, so the global index of a key is the number of smaller keys, one binary search per shard.
+namespace vsm {
+struct ShardSizes {
+  long long n[64];
+};
+__global__ void __launch_bounds__(256) global_rank_kernel(const unsigned long long* __restrict__ mine, int64_t n_mine,
+                                                          const unsigned long long* __restrict__ all, long long stride,
+                                                          ShardSizes sz, int world, int64_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_mine; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = mine[i];
+    long long rank = 0;
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* shard = all + (size_t)r * stride;
+      long long lo = 0, hi = sz.n[r];
+      while (lo < hi) {  // first position whose key is >= k
+        const long long mid = (lo + hi) >> 1;
+        if (shard[mid] < k)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      rank += lo;
+    }
+    out[i] = rank;
+  }
+}
+}  // namespace vsm
+
+extern "C" int vsm_global_ranks(const uint64_t* my_keys_dev, int64_t n_mine, const uint64_t* all_keys_dev,
+                                int64_t shard_stride, const int64_t* shard_sizes_host, int32_t world, int64_t* ranks_dev,
+                                void* stream) {
+  if (n_mine < 0 || world < 1 || world > 64 || !shard_sizes_host || shard_stride < 0 ||
+      (n_mine > 0 && (!my_keys_dev || !all_keys_dev || !ranks_dev))) {
+    set_error("vsm_global_ranks: bad arguments (world <= 64)");
+    return VSM_E_INVALID;
+  }
+  if (n_mine == 0) return VSM_OK;
+  ShardSizes sz{};
+  for (int r = 0; r < world; ++r) {
+    if (shard_sizes_host[r] < 0 || shard_sizes_host[r] > shard_stride) {
+      set_error("vsm_global_ranks: shard %d holds %lld keys, stride %lld", r, (long long)shard_sizes_host[r], (long long)shard_stride);
+      return VSM_E_INVALID;
+    }
+    sz.n[r] = shard_sizes_host[r];
+  }
+  global_rank_kernel<<<grid_for(n_mine, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned long long*>(my_keys_dev), n_mine, reinterpret_cast<const unsigned long long*>(all_keys_dev),
+      (long long)shard_stride, sz, world, ranks_dev);
+  VSM_LAUNCHED();
+  return VSM_OK;
 }
 
 extern "C" int vsm_lookup(vsm_map* m, const float* pos_dev, int64_t M, int64_t* idx_dev, int compat, void* stream) {

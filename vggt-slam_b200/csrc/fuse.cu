@@ -36,7 +36,6 @@ std::atomic<int> g_select_mode{0};              // 0 default (= 1), 1 radix, 2 b
 // preparation kernels (vsm_set_option "prep_variant"): bit 0 = a warp takes a 4x8 pixel patch instead of 32 pixels of a
 // row; bit 1 = read the frame-mask word before the atomic OR; bit 2 = select with merged one-block steps
 std::atomic<int> g_prep_variant{5};
-std::atomic<int> g_acc_variant{1};  // "acc_variant": 1 = segment-owning accumulate kernel (plain stores for new voxels), 0 = chunked
 std::atomic<int> g_range_policy{0};             // "coord_range_policy": 0 = fail the call (VSM_E_COORD_RANGE), 1 = drop + count
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
@@ -228,9 +227,31 @@ __global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm,
 // directions, so a patch holds 2-3x fewer distinct keys than a row segment (fewer claims, fewer atomics); rows of a
 // patch are 8 pixels = 128 contiguous bytes of world points, so the loads stay sector-exact.
 constexpr int kPatchRows = 4, kPatchCols = 8;
+// unsigned division by a runtime constant as multiply-high + shift (exact for all 32-bit numerators the kernels use:
+// checked on the host for the largest one) -- the index arithmetic below runs once per warp-iteration and lane
+struct FastDiv {
+  uint32_t d, mul, shift;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d <= 1u) return f;  // handled as a special case
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;  // ceil(log2 d)
+  f.shift = l - 1u;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << l) - d)) / d) + 1ull);  // round-up method (Granlund-Montgomery, n < 2^32)
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv_u32(uint32_t n, const FastDiv& f) {
+  if (f.d <= 1u) return n;
+  const uint32_t t = __umulhi(n, f.mul);
+  return (t + ((n - t) >> 1)) >> f.shift;
+}
+
 struct PixMap {
   uint32_t n_px, H, W, tiles_x, tiles_per_frame;
   uint32_t n_items;  // warp-iterations: patches (PATCH) or 32-pixel runs (linear)
+  uint32_t px_per_frame;
+  FastDiv div_tpf, div_tx, div_ppf;
 };
 static PixMap make_pixmap(int64_t n_px, int frames, int H, int W, bool patch) {
   PixMap pm{};
@@ -240,19 +261,26 @@ static PixMap make_pixmap(int64_t n_px, int frames, int H, int W, bool patch) {
   pm.tiles_x = (uint32_t)((W + kPatchCols - 1) / kPatchCols);
   pm.tiles_per_frame = pm.tiles_x * (uint32_t)((H + kPatchRows - 1) / kPatchRows);
   pm.n_items = patch ? (uint32_t)frames * pm.tiles_per_frame : (uint32_t)((n_px + 31) / 32);
+  pm.px_per_frame = (uint32_t)(H * W);
+  pm.div_tpf = make_fastdiv(pm.tiles_per_frame);
+  pm.div_tx = make_fastdiv(pm.tiles_x);
+  pm.div_ppf = make_fastdiv(pm.px_per_frame);
   return pm;
 }
+// pixel of (warp-iteration, lane) and the index of its frame inside this call
 template <bool PATCH>
-__device__ __forceinline__ bool map_pixel(const PixMap& pm, uint32_t item, int lane, uint32_t& pix) {
+__device__ __forceinline__ bool map_pixel(const PixMap& pm, uint32_t item, int lane, uint32_t& pix, uint32_t& frame) {
   if (PATCH) {
-    const uint32_t f = item / pm.tiles_per_frame;
+    const uint32_t f = fdiv_u32(item, pm.div_tpf);
     const uint32_t r = item - f * pm.tiles_per_frame;
-    const uint32_t ty = r / pm.tiles_x, tx = r - ty * pm.tiles_x;
+    const uint32_t ty = fdiv_u32(r, pm.div_tx), tx = r - ty * pm.tiles_x;
     const uint32_t y = ty * kPatchRows + ((uint32_t)lane >> 3), x = tx * kPatchCols + ((uint32_t)lane & 7u);
     pix = (f * pm.H + y) * pm.W + x;
+    frame = f;
     return y < pm.H && x < pm.W;
   }
   pix = item * 32u + (uint32_t)lane;
+  frame = fdiv_u32(pix, pm.div_ppf);
   return pix < pm.n_px;
 }
 
@@ -319,7 +347,6 @@ __device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, uns
 struct FilterArgs {
   const float4* pw;
   int32_t* pt_slot;
-  uint32_t px_per_frame;
   uint32_t frame_base;
   float cell;  // coarse cell (bbox_coarse) or voxel size (fine)
   uint32_t min_pts;
@@ -342,8 +369,8 @@ __global__ void __launch_bounds__(256) bbox_coarse_kernel(FilterArgs a, PixMap p
   const int lane = lane_id();
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
-    uint32_t pix;
-    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
+    uint32_t pix, frame_unused;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix, frame_unused);
     bool act = false;
     unsigned long long key = kEmptyKey;
     if (inside) {
@@ -374,8 +401,8 @@ __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, PixMap p
   const int lane = lane_id();
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
-    uint32_t pix;
-    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
+    uint32_t pix, fidx;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix, fidx);
     bool act = false;
     unsigned long long key = kEmptyKey;
     int frame = 0;
@@ -391,7 +418,7 @@ __global__ void __launch_bounds__(256) fine_insert_kernel(FilterArgs a, PixMap p
         bool rerr = false;
         key = pack_key(p.x, p.y, p.z, a.cell, rerr);
         if (range_problem(rerr, a.opts, ctr)) act = false;
-        frame = (int)(a.frame_base + pix / a.px_per_frame);
+        frame = (int)(a.frame_base + fidx);
       }
     }
     const int slot = warp_insert(tb, act, key, frame, a.opts, ctr);
@@ -607,8 +634,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const int32_t* __restrict_
   const int lane = lane_id();
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
-    uint32_t pix;
-    const bool inside = map_pixel<PATCH>(pm, item, lane, pix);
+    uint32_t pix, frame_unused;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix, frame_unused);
     const int slot = inside ? pt_slot[pix] : -1;
     const bool act = slot >= 0;
     const uint32_t lid = act ? tb.slots[slot].lid : 0xFFFFFFFFu;
@@ -959,177 +986,6 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
   if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
 }
 
-// The voxel-sorted, full-row case with SEGMENT OWNERSHIP.  A voxel's points are one contiguous segment of the sorted
-// list; the kernel above cuts the list into 32-entry chunks, so a segment that straddles a chunk boundary is flushed
-// twice and every flush must be a RED (read-modify-write of the 2 KB sum row).  Here the warp of chunk c owns the
-// segments that START in its chunk and follows them into chunk c+1; only segments that run through a whole chunk are
-// still cut at chunk boundaries.  A whole segment of a voxel that is NEW to the map (id >= vox_base: its sum row has
-// never been touched) is flushed with plain 16-byte stores: no read of the row.  At 2 cm voxels (segments of ~12 rows,
-// most voxels new) that removes ~40 % of the flushes and the row fetch of nearly all the others.
-__device__ __forceinline__ void st_v4_f32(float* p, float a, float b, float c, float d) {
-  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-template <bool BF16, int VPL, bool CHECK>
-__global__ void __launch_bounds__(256, 2) accumulate_owned_kernel(AccArgs a) {  // launched with 2 CTAs per SM
-  constexpr int EPV = RowVec<BF16>::EPV;
-  constexpr int U = (VPL <= 2) ? 4 : 2;  // rows in flight per warp
-  constexpr int kNone = (int)0x80000000;  // "no entry": differs from every voxel id
-  if (a.ctr->abort) return;
-  const int lane = lane_id();
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t n_entries = (int64_t)a.ctr->n_fused;
-  const int64_t n_chunks = (n_entries + 31) >> 5;
-  const int vox_base = (int)a.ctr->vox_base;
-  const uint32_t rb = (uint32_t)a.row_bytes;
-  const uint8_t* emb0 = a.emb - a.pix_base * a.row_bytes + (size_t)lane * 16;
-  float* const vsum0 = a.vsum + (size_t)lane * EPV;
-  const uint32_t d = (uint32_t)a.d;
-  unsigned n_bad = 0;
-
-  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
-    const int64_t base = chunk << 5;
-    // entries of this chunk and the next one, the first and last voxel id of the previous chunk
-    uint32_t p0 = 0, p1 = 0;
-    int g0 = kNone, g1 = kNone, gp_first = kNone, gp_last = kNone;
-    if (base + lane < n_entries) {
-      const unsigned long long e = a.entries[base + lane];
-      p0 = (uint32_t)e;
-      g0 = (int)(uint32_t)(e >> 32);
-    }
-    if (base + 32 + lane < n_entries) {
-      const unsigned long long e = a.entries[base + 32 + lane];
-      p1 = (uint32_t)e;
-      g1 = (int)(uint32_t)(e >> 32);
-    }
-    if (chunk > 0) {
-      gp_first = (int)(uint32_t)(a.entries[base - 32] >> 32);
-      gp_last = (int)(uint32_t)(a.entries[base - 1] >> 32);
-    }
-    const int g0_first = __shfl_sync(0xffffffffu, g0, 0), g0_last = __shfl_sync(0xffffffffu, g0, 31);
-    const int g1_first = __shfl_sync(0xffffffffu, g1, 0);
-    // lo: where this warp starts.  A segment that began inside the previous chunk belongs to that chunk's warp,
-    // unless it already fills the previous chunk from its first entry (a long segment is cut at every chunk start).
-    int lo = 0;
-    bool first_partial = false;  // the first segment continues one cut at `base`
-    if (chunk > 0 && g0_first == gp_last) {
-      if (g0_first == gp_first) {
-        first_partial = true;
-      } else {
-        const unsigned diff = __ballot_sync(0xffffffffu, g0 != g0_first);
-        lo = diff ? __ffs(diff) - 1 : 32;
-      }
-    }
-    // hi: where the next chunk's warp starts (the same rule, one chunk later)
-    int hi = 32;
-    bool last_partial = false;  // the last segment is cut at base + 32
-    if (base + 32 >= n_entries) {
-      hi = (int)(n_entries - base);
-    } else if (g1_first == g0_last) {
-      if (g1_first == g0_first) {
-        last_partial = true;
-      } else {
-        const unsigned diff = __ballot_sync(0xffffffffu, g1 != g1_first);
-        hi = 32 + (diff ? __ffs(diff) - 1 : 32);
-        if (!diff) last_partial = true;  // still running at base + 64: the warp two chunks on takes over there
-      }
-    }
-    if (lo >= hi) continue;
-
-    float acc[VPL * EPV];
-#pragma unroll
-    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
-    int cur = kNone;
-    bool cur_partial = first_partial;
-
-    auto flush = [&](bool partial) {
-      if (cur != kNone) {
-        bool ok = true;
-        if (CHECK) {
-          float t = 0.f;
-#pragma unroll
-          for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);  // NaN iff some accumulator is Inf/NaN
-          ok = !__any_sync(0xffffffffu, t != t);
-          if (!ok && lane == 0) ++n_bad;
-        }
-        if (ok) {
-          float* dst = vsum0 + (size_t)cur * d;
-          if (!partial && cur >= vox_base) {
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-#pragma unroll
-              for (int q = 0; q < EPV / 4; ++q)
-                st_v4_f32(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
-                          acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int v = 0; v < VPL; ++v)
-#pragma unroll
-              for (int q = 0; q < EPV / 4; ++q)
-                red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1],
-                           acc[v * EPV + 4 * q + 2], acc[v * EPV + 4 * q + 3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
-    };
-
-    for (int j = lo; j < hi; j += U) {
-      uint4 rows[U][VPL];
-      int gids[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int idx = j + u;  // warp-uniform
-        const bool live = idx < hi;
-        const uint32_t pj = __shfl_sync(0xffffffffu, idx < 32 ? p0 : p1, idx & 31);
-        const int gj = __shfl_sync(0xffffffffu, idx < 32 ? g0 : g1, idx & 31);
-        gids[u] = live ? gj : kNone;
-        const uint8_t* row = emb0 + (unsigned long long)pj * rb;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) rows[u][v] = live ? ld_stream_v4(row + v * 512) : make_uint4(0u, 0u, 0u, 0u);
-      }
-      bool same = true;
-#pragma unroll
-      for (int u = 0; u < U; ++u) same &= (gids[u] == cur);
-      if (same) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (gids[u] == kNone) continue;  // warp-uniform: past the end of this warp's range
-          if (gids[u] != cur) {
-            flush(cur_partial);
-            cur_partial = false;
-            cur = gids[u];
-          }
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
-        }
-      }
-    }
-    flush(cur_partial || last_partial);
-  }
-
-  if (CHECK) {
-    // check-only entries sit behind the fused ones: one warp per row, test the raw values
-    const int64_t n_check = (int64_t)a.ctr->n_check;
-    for (int64_t i = warp; i < n_check; i += n_warps) {
-      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
-      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
-      bool bad = false;
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
-      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
-    }
-  }
-  if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
-}
-
 template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
   const int block = 256;
@@ -1141,14 +997,6 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)sm_count() * 6);
   }
   const bool full = a.nvec == 32 * VPL;
-  if (sorted && full && a.emb_index == nullptr && g_acc_variant.load() == 1) {
-    if (check)
-      accumulate_owned_kernel<BF16, VPL, true><<<grid, block, 0, s>>>(a);
-    else
-      accumulate_owned_kernel<BF16, VPL, false><<<grid, block, 0, s>>>(a);
-    VSM_LAUNCHED();
-    return VSM_OK;
-  }
   if (sorted && full && a.emb_index != nullptr) {
     if (check)
       accumulate_kernel<BF16, VPL, true, true, true, true><<<grid, block, 0, s>>>(a);
@@ -1540,7 +1388,6 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   FilterArgs fa;
   fa.pw = ws->pw.as<float4>();
   fa.pt_slot = ws->pt_slot.as<int32_t>();
-  fa.px_per_frame = (uint32_t)px_per_frame;
   fa.frame_base = (uint32_t)p->frame_base;
   fa.min_pts = (uint32_t)std::max(p->coarse_min_points, 0);
   fa.opts = ((variant & 2) ? kOptMaskProbe : 0) | (g_range_policy.load() == 1 ? kOptDropRange : 0);
@@ -2059,10 +1906,6 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "prep_variant") && value >= 0 && value <= 7) {
     g_prep_variant = (int)value;
-    return VSM_OK;
-  }
-  if (!strcmp(key, "acc_variant") && (value == 0 || value == 1)) {
-    g_acc_variant = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {

@@ -245,16 +245,17 @@ __global__ void __launch_bounds__(256) drain_contrib_kernel(GlobalStore g, const
 
 // last kernel of a drain: report, advance the map's log length, and reset this half of the inbox for its next use
 __global__ void drain_finish_kernel(InboxHeader* hdr, uint32_t cap_contrib, uint32_t* map_state, uint32_t log_cap,
-                                    const uint32_t* hash_err, uint32_t* report /* [n_rows, n_contrib, flags, n_vox] */) {
+                                    const uint32_t* hash_err, uint32_t* report /* [n_rows, n_contrib, flags, n_vox, hash err, log n] */) {
   uint32_t flags = hdr->flags;
   if (*hash_err) flags |= kInboxHashErr;
   const uint32_t n_contrib = min(hdr->n_contrib, cap_contrib);
   if ((unsigned long long)map_state[1] + n_contrib > log_cap) flags |= kInboxContribOverflow;
-  report[0] = hdr->n_rows;
-  report[1] = hdr->n_contrib;
-  report[2] = flags;
+  report[0] += hdr->n_rows;  // reports accumulate over the drains queued since the slot was last collected
+  report[1] += hdr->n_contrib;
+  report[2] |= flags;
   map_state[1] = min(map_state[1] + n_contrib, log_cap);
   report[3] = map_state[0];
+  report[5] = map_state[1];  // (report[4] is the hash-error counter itself)
   hdr->n_rows = 0u;
   hdr->n_contrib = 0u;
   hdr->flags = 0u;
@@ -378,30 +379,22 @@ extern "C" int vsm_partials_push(vsm_map* m, int32_t world, void* const* inbox_p
   return VSM_OK;
 }
 
-extern "C" int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib,
-                                  int64_t epoch, double timeout_s, int64_t* n_rows_host, int64_t* n_contrib_host,
-                                  uint32_t* flags_host, void* stream) {
-  if (!m || !inbox || world < 1 || world > kMaxWorld || cap_rows < 1 || cap_contrib < 1 || epoch < 0) {
-    set_error("vsm_partials_drain: bad arguments");
-    return VSM_E_INVALID;
-  }
-  if (m->dense_loaded) {
-    set_error("vsm_partials_drain: dense-loaded maps cannot be merged into");
-    return VSM_E_STATE;
-  }
-  VSM_CUDA(cudaSetDevice(m->device));
-  cudaStream_t s = (cudaStream_t)stream;
-  VSM_TRY(fuse_collect_pending(m, s));
+// Queue one drain on `stream` without waiting for it: the device waits for `world` signals, inserts the received
+// records into the map and writes a 4-word report into report slot `slot` (0..3).  The map must already have room
+// (vsm_map_reserve / vsm_map_reserve_log): nothing about the inbox contents is known on the host, and a drain that
+// runs out of room is reported by the collect, not grown for.
+static int drain_enqueue(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib, int64_t epoch,
+                         double timeout_s, int slot, bool fresh_report, cudaStream_t s) {
   m->finalized = false;
   m->ck_built = false;
   m->norms_valid = false;
-  // room for everything the inbox can hold: nothing about its contents is known on the host yet
-  VSM_TRY(map_grow(m, m->n_vox + cap_rows, s));
-  VSM_TRY(log_grow(m, m->log_n + cap_contrib, s));
-  VSM_TRY(m->ctr.ensure(sizeof(FuseCounters) + 16, s));
-  FuseCounters* ctr = m->ctr.as<FuseCounters>();
-  uint32_t* report = reinterpret_cast<uint32_t*>(ctr + 1);
-  VSM_CUDA(cudaMemsetAsync(ctr, 0, sizeof(FuseCounters) + 16, s));
+  if (!m->drain_report.p) {
+    VSM_TRY(m->drain_report.ensure(4 * 32, s));
+    VSM_CUDA(cudaMemsetAsync(m->drain_report.p, 0, 4 * 32, s));
+  }
+  VSM_TRY(m->xch_tmp.ensure((size_t)cap_rows * 4, s));
+  uint32_t* report = m->drain_report.as<uint32_t>() + 8 * slot;  // [n_rows, n_contrib, flags, n_vox | hash err, log n, -, -]
+  if (fresh_report) VSM_CUDA(cudaMemsetAsync(report, 0, 32, s));
   const InboxLayout L = inbox_layout(m->d, cap_rows, cap_contrib);
   const int half = (int)(epoch & 1);
   uint8_t* base = reinterpret_cast<uint8_t*>(inbox);
@@ -409,31 +402,32 @@ extern "C" int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_
   const uint8_t* rows = base + L.rows_off[half];
   const uint8_t* contrib = base + L.contrib_off[half];
   const unsigned long long timeout_ns = (unsigned long long)(std::max(timeout_s, 0.001) * 1e9);
-  uint32_t rep[4] = {0, 0, 0, 0};
-  {
-    VSM_TRY(m->xch_tmp.ensure((size_t)cap_rows * 4, s));
-    inbox_wait_kernel<<<1, 1, 0, s>>>(hdr, (uint32_t)world, timeout_ns);
-    VSM_LAUNCHED();
-    drain_keys_kernel<<<grid_for(cap_rows, 256, sm_count() * 8), 256, 0, s>>>(global_store(m), hdr, rows, L.row_stride, (uint32_t)cap_rows,
-                                                                       m->xch_tmp.as<int32_t>(), &ctr->internal_err);
-    VSM_LAUNCHED();
-    drain_rows_kernel<<<sm_count() * 8, 256, 0, s>>>(hdr, rows, L.row_stride, (uint32_t)cap_rows, m->xch_tmp.as<int32_t>(), m->d,
-                                              m->vsum.as<float>());
-    VSM_LAUNCHED();
-    drain_contrib_kernel<<<grid_for(cap_contrib, 256, sm_count() * 8), 256, 0, s>>>(
-        global_store(m), hdr, contrib, (uint32_t)cap_contrib, m->d_n_vox.as<uint32_t>(),
-        (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll), m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
-        m->log_mask.as<unsigned long long>());
-    VSM_LAUNCHED();
-    drain_finish_kernel<<<1, 1, 0, s>>>(hdr, (uint32_t)cap_contrib, m->d_n_vox.as<uint32_t>(),
-                                        (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll), &ctr->internal_err, report);
-    VSM_LAUNCHED();
-    VSM_TRY(read_back(m, rep, report, sizeof(rep), s));  // the one synchronisation of an exchange
-  }
-  uint32_t state[2] = {0, 0};
-  VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
-  m->n_vox = std::min<int64_t>(state[0], m->vcap);
-  m->log_n = state[1];
+  uint32_t* hash_err = report + 4;
+  inbox_wait_kernel<<<1, 1, 0, s>>>(hdr, (uint32_t)world, timeout_ns);
+  VSM_LAUNCHED();
+  drain_keys_kernel<<<grid_for(cap_rows, 256, sm_count() * 8), 256, 0, s>>>(global_store(m), hdr, rows, L.row_stride,
+                                                                            (uint32_t)cap_rows, m->xch_tmp.as<int32_t>(), hash_err);
+  VSM_LAUNCHED();
+  drain_rows_kernel<<<sm_count() * 8, 256, 0, s>>>(hdr, rows, L.row_stride, (uint32_t)cap_rows, m->xch_tmp.as<int32_t>(), m->d,
+                                                   m->vsum.as<float>());
+  VSM_LAUNCHED();
+  drain_contrib_kernel<<<grid_for(cap_contrib, 256, sm_count() * 8), 256, 0, s>>>(
+      global_store(m), hdr, contrib, (uint32_t)cap_contrib, m->d_n_vox.as<uint32_t>(),
+      (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll), m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
+      m->log_mask.as<unsigned long long>());
+  VSM_LAUNCHED();
+  drain_finish_kernel<<<1, 1, 0, s>>>(hdr, (uint32_t)cap_contrib, m->d_n_vox.as<uint32_t>(),
+                                      (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll), hash_err, report);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
+static int drain_collect(vsm_map* m, int slot, int32_t world, double timeout_s, int64_t cap_rows, int64_t cap_contrib,
+                         int64_t* n_rows_host, int64_t* n_contrib_host, uint32_t* flags_host, cudaStream_t s) {
+  uint32_t rep[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  VSM_TRY(read_back(m, rep, m->drain_report.as<uint32_t>() + 8 * slot, sizeof(rep), s));  // synchronises the stream
+  m->n_vox = std::min<int64_t>(rep[3], m->vcap);
+  m->log_n = rep[5];
   if (n_rows_host) *n_rows_host = rep[0];
   if (n_contrib_host) *n_contrib_host = rep[1];
   if (flags_host) *flags_host = rep[2];
@@ -442,13 +436,67 @@ extern "C" int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_
     return VSM_E_STATE;
   }
   if (rep[2] & kInboxHashErr) {
-    set_error("internal: global hash overflow while draining the inbox");
-    return VSM_E_INTERNAL;
+    set_error("vsm_partials_drain: the map ran out of voxel capacity (%lld) while draining: reserve more", (long long)m->vcap);
+    return VSM_E_NOMEM;
   }
   if (rep[2] & (kInboxRowOverflow | kInboxContribOverflow)) {
-    set_error("vsm_partials_drain: inbox too small (%u rows for %lld slots, %u contributor entries for %lld slots)", rep[0],
-              (long long)cap_rows, rep[1], (long long)cap_contrib);
+    set_error("vsm_partials_drain: inbox too small, or contributor log full (%u rows for %lld slots, %u contributor entries "
+              "for %lld slots, log capacity %lld)", rep[0], (long long)cap_rows, rep[1], (long long)cap_contrib,
+              (long long)m->log_cap);
     return VSM_E_NOMEM;
   }
   return VSM_OK;
+}
+
+static int drain_check_args(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib, int64_t epoch) {
+  if (!m || !inbox || world < 1 || world > kMaxWorld || cap_rows < 1 || cap_contrib < 1 || epoch < 0) {
+    set_error("vsm_partials_drain: bad arguments");
+    return VSM_E_INVALID;
+  }
+  if (m->dense_loaded) {
+    set_error("vsm_partials_drain: dense-loaded maps cannot be merged into");
+    return VSM_E_STATE;
+  }
+  return VSM_OK;
+}
+
+extern "C" int vsm_partials_drain(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib,
+                                  int64_t epoch, double timeout_s, int64_t* n_rows_host, int64_t* n_contrib_host,
+                                  uint32_t* flags_host, void* stream) {
+  VSM_TRY(drain_check_args(m, inbox, world, cap_rows, cap_contrib, epoch));
+  VSM_CUDA(cudaSetDevice(m->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  VSM_TRY(fuse_collect_pending(m, s));
+  // room for everything the inbox can hold: nothing about its contents is known on the host yet
+  VSM_TRY(map_grow(m, m->n_vox + cap_rows, s));
+  VSM_TRY(log_grow(m, m->log_n + cap_contrib, s));
+  VSM_TRY(drain_enqueue(m, inbox, world, cap_rows, cap_contrib, epoch, timeout_s, 0, true, s));
+  return drain_collect(m, 0, world, timeout_s, cap_rows, cap_contrib, n_rows_host, n_contrib_host, flags_host, s);
+}
+
+extern "C" int vsm_partials_drain_async(vsm_map* m, void* inbox, int32_t world, int64_t cap_rows, int64_t cap_contrib,
+                                        int64_t epoch, double timeout_s, int32_t report_slot, void* stream) {
+  VSM_TRY(drain_check_args(m, inbox, world, cap_rows, cap_contrib, epoch));
+  if (report_slot < 0 || report_slot > 3) {
+    set_error("vsm_partials_drain_async: report slot must be 0..3");
+    return VSM_E_INVALID;
+  }
+  if (!m->pending.empty()) {
+    set_error("vsm_partials_drain_async: the map has uncollected fuse calls");
+    return VSM_E_STATE;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  return drain_enqueue(m, inbox, world, cap_rows, cap_contrib, epoch, timeout_s, report_slot, false, (cudaStream_t)stream);
+}
+
+extern "C" int vsm_partials_drain_collect(vsm_map* m, int32_t report_slot, int64_t* n_rows_host, int64_t* n_contrib_host,
+                                          uint32_t* flags_host, void* stream) {
+  if (!m || report_slot < 0 || report_slot > 3 || !m->drain_report.p) {
+    set_error("vsm_partials_drain_collect: no drain was queued with this report slot");
+    return VSM_E_INVALID;
+  }
+  VSM_CUDA(cudaSetDevice(m->device));
+  const int st = drain_collect(m, report_slot, 0, 0.0, 0, 0, n_rows_host, n_contrib_host, flags_host, (cudaStream_t)stream);
+  cudaMemsetAsync(m->drain_report.as<uint32_t>() + 8 * report_slot, 0, 32, (cudaStream_t)stream);  // the slot starts over
+  return st;
 }

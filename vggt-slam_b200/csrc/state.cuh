@@ -210,6 +210,7 @@ struct vsm_map {
   vsm::DevBuf ck_keys, ck_val;
   uint64_t ck_cap = 0;
   bool ck_built = false;
+  vsm::DevBuf drain_report;  // 4 report slots of queued drains (vsm_partials_drain_async)
   vsm::DevBuf xch_tmp;  // exchange scratch (owner offsets of a pack, voxel ids of a merge / drain): per map, not shared
   // query scratch
   vsm::DevBuf q_cand, q_tmp, q_norm;

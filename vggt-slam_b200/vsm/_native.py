@@ -104,6 +104,19 @@ SIGNATURES = {
     "vsm_partials_push": (C.c_int, [_vp, _i32, _P(_vp), _i64, _i64, _i64, _vp]),
     "vsm_partials_drain": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _f64, _P(_i64), _P(_i64), _P(C.c_uint32), _vp]),
     "vsm_export_packed_keys": (C.c_int, [_vp, _vp, _vp]),
+    "vsm_num_log_entries": (C.c_int, [_vp, _P(_i64)]),
+    "vsm_map_reserve_log": (C.c_int, [_vp, _i64, _vp]),
+    "vsm_map_clear_async": (C.c_int, [_vp, _vp]),
+    "vsm_partials_drain_async": (C.c_int, [_vp, _vp, _i32, _i64, _i64, _i64, _f64, _i32, _vp]),
+    "vsm_partials_drain_collect": (C.c_int, [_vp, _i32, _P(_i64), _P(_i64), _P(C.c_uint32), _vp]),
+    "vsm_map_load_begin": (C.c_int, [_vp, _i64, _vp]),
+    "vsm_map_load_rows": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "vsm_global_ranks": (C.c_int, [_vp, _i64, _vp, _i64, _P(_i64), _i32, _vp, _vp]),
+    "vsm_ransac_score": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _P(_i32), _P(_i32), _vp]),
+    "vsm_occupancy_build": (C.c_int, [_vp, _i64, _f64, _f64, _f64, _i64, _vp, _vp, _vp, _vp, _P(_i64), _P(_i64), _vp]),
+    "vsm_unproject_depth": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, C.c_int, _vp]),
+    "vsm_images_to_colors": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "vsm_scale_points": (C.c_int, [_vp, _i64, _f64, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -51,21 +51,41 @@ def merge_topk(idx: torch.Tensor, score: torch.Tensor, k: int) -> Tuple[torch.Te
     return torch.gather(idx_s, 1, order2), torch.gather(sc_s, 1, order2)
 
 
+def _global_ranks_torch(my_sorted_keys: torch.Tensor, bufs, sizes) -> torch.Tensor:
+    """CPU tensors only (the gloo plumbing test): one searchsorted per shard."""
+    ranks = torch.zeros_like(my_sorted_keys)
+    for r, b in enumerate(bufs):
+        ranks += torch.searchsorted(b[: sizes[r]], my_sorted_keys)  # keys smaller than mine on rank r
+    return ranks
+
+
 def global_ranks(my_sorted_keys: torch.Tensor, group=None) -> Tuple[torch.Tensor, int]:
-    """Global index of each of my (sorted, unique, disjoint across ranks) keys in the order of ALL keys."""
+    """Global index of each of my (sorted, unique, disjoint across ranks) keys in the order of ALL keys: the sorted
+    keys of every shard are all-gathered (8 bytes per voxel) and ONE kernel ranks mine among them (vsm_global_ranks:
+    a binary search per shard)."""
     world = dist.get_world_size(group)
     n = torch.tensor([my_sorted_keys.numel()], dtype=torch.int64, device=my_sorted_keys.device)
     sizes = [torch.empty_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = [int(s) for s in torch.cat(sizes).cpu().tolist()]
     mx = max(max(sizes), 1)
     pad = torch.full((mx,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=my_sorted_keys.device)
     pad[: my_sorted_keys.numel()] = my_sorted_keys
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    ranks = torch.zeros_like(my_sorted_keys)
-    for r, b in enumerate(bufs):
-        ranks += torch.searchsorted(b[: sizes[r]], my_sorted_keys)  # keys smaller than mine on rank r
+    if not my_sorted_keys.is_cuda:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+        return _global_ranks_torch(my_sorted_keys, bufs, sizes), int(sum(sizes))
+    import ctypes as C
+
+    from . import _native as N
+
+    allk = torch.empty((world * mx,), dtype=torch.int64, device=my_sorted_keys.device)
+    dist.all_gather_into_tensor(allk, pad, group=group)
+    ranks = torch.empty_like(my_sorted_keys)
+    sz = (C.c_int64 * world)(*sizes)
+    N.check(N.lib.vsm_global_ranks(C.c_void_p(my_sorted_keys.data_ptr()), int(my_sorted_keys.numel()),
+                                   C.c_void_p(allk.data_ptr()), int(mx), sz, world, C.c_void_p(ranks.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream(my_sorted_keys.device).cuda_stream)))
     return ranks, int(sum(sizes))
 
 
@@ -182,6 +202,55 @@ def _sizes_all(values, group, device) -> np.ndarray:
     return torch.stack(out).cpu().numpy()
 
 
+def _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs=None):
+    """Tail of a sharded build: finalise the owner shard, learn every rank's frame ids (contributor lists name frames
+    of remote submaps too), wrap the shard and rank its voxels among all shards."""
+    from .map import wrap_device_map
+
+    world = dist.get_world_size(group)
+    owner.finalize()
+    ph.mark("finalize")
+    # frame ids of every submap, from every rank (contributor lists name frames of remote submaps too)
+    mine = {int(f["submap"].get_id()): (list(f["submap"].frame_ids), dict(f["submap"].frame_id_to_name or {}))
+            for f in fused}
+    # The pickled all-gather costs ~1 ms: skip it while no rank's frame ids have changed since the last build.  Every
+    # rank sees the same vector of per-rank signatures (all-gathered with the sizes), so all ranks decide alike.
+    my_sig = _names_signature(fused)
+    if names_sigs is None:
+        names_sigs = tuple(int(x) for x in _sizes_all([my_sig], group, dev)[:, 0])
+    else:
+        names_sigs = tuple(int(x) for x in names_sigs)
+    cache_key = (id(group) if group is not None else 0, dev.index)
+    cached = _NAMES_CACHE.get(cache_key)
+    if cached is not None and cached[0] == names_sigs and cached[1] == my_sig:
+        everyone = cached[2]
+    else:
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine, group=group)
+        _NAMES_CACHE[cache_key] = (names_sigs, my_sig, everyone)
+    frame_ids, all_names = {}, {}
+    for part in everyone:
+        for sid, (ids, nm) in part.items():
+            frame_ids[sid] = ids
+            all_names[str(sid)] = nm
+
+    class _SubmapStub:
+        def __init__(self, sid, ids):
+            self._sid, self.frame_ids = sid, ids
+
+        def get_id(self):
+            return self._sid
+
+    fused_all = [{"submap": _SubmapStub(sid, ids)} for sid, ids in frame_ids.items()]
+    ph.mark("names")
+    local = wrap_device_map(owner, fused_all, all_names, voxel_size, True, False) if owner.num_voxels else None
+    ph.mark("wrap")
+    gidx, n_global = global_ranks(owner.export_packed_keys(), group)
+    ph.mark("ranks")
+    ph.report()
+    return ShardedVoxelMap(local, owner, gidx, n_global, group)
+
+
 def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_closure_frames: bool = True,
                   capacity_hint: Optional[int] = None, host_streaming: Optional[bool] = None, profile: bool = False,
                   group=None, transport: str = "auto"):
@@ -261,44 +330,196 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         del r_keys, r_counts, r_sums
     if transport not in ("peer", "collective"):
         raise ValueError(f"unknown transport {transport!r}")
-    owner.finalize()
-    ph.mark("finalize")
-    # frame ids of every submap, from every rank (contributor lists name frames of remote submaps too)
-    mine = {int(f["submap"].get_id()): (list(f["submap"].frame_ids), dict(f["submap"].frame_id_to_name or {}))
-            for f in fused}
-    # The pickled all-gather costs ~1 ms: skip it while no rank's frame ids have changed since the last build.  Every
-    # rank sees the same vector of per-rank signatures (all-gathered with the sizes), so all ranks decide alike.
-    my_sig = _names_signature(fused)
-    if names_sigs is None:
-        names_sigs = tuple(int(x) for x in _sizes_all([my_sig], group, dev)[:, 0])
+    return _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs), stats
+
+
+_XCHG_STREAMS: dict = {}
+
+
+def _exchange_stream(dev) -> "torch.cuda.Stream":
+    st = _XCHG_STREAMS.get(dev.index)
+    if st is None:
+        st = _XCHG_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def build_sharded_streaming(graph_map, voxel_size: float, round_submaps: int, stride: int = 1,
+                            ignore_loop_closure_frames: bool = True, owner_capacity: Optional[int] = None,
+                            round_capacity: Optional[int] = None, profile: bool = False, group=None,
+                            timings: Optional[dict] = None):
+    """Collective multi-GPU build for LONG trajectories (BASELINE configs[2]): the rank's submaps are fused in rounds of
+    `round_submaps`; the voxels of round r are pushed to their owners over NVLink peer memory and merged there on an
+    exchange stream WHILE round r+1 is being fused on the main stream (two local maps alternate; a drained local map is
+    cleared on the exchange stream).  The local map therefore never holds more than a round, the inboxes are sized for
+    one round, and the exchange is off the critical path except for the last round.  Peer memory only (no collective
+    fallback: a long trajectory does not fit the pack -> all-to-all -> merge route's staging buffers).
+
+    owner_capacity / round_capacity: voxels the owner shard / one round's local map must hold (estimated from the
+    first round when omitted; too small a value fails loudly with MemoryError at the final collect).
+    Returns (ShardedVoxelMap, this rank's per-submap fuse stats)."""
+    from . import peer
+    from . import voxel_map as vm
+    from .map import wrap_device_map
+
+    world = dist.get_world_size(group)
+    if round_submaps < 1:
+        raise ValueError("round_submaps must be >= 1")
+    todo = graph_map.usable_submaps()
+    if not todo:
+        raise RuntimeError("build_sharded_streaming: this rank has no submap to fuse")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    xs = _exchange_stream(dev)
+    d, code = int(todo[0].semantic_embeddings.shape[-1]), todo[0].embedding_dtype_code()
+    n_rounds = (len(todo) + round_submaps - 1) // round_submaps
+    t_r = torch.tensor([n_rounds], dtype=torch.int64, device=dev)
+    dist.all_reduce(t_r, op=dist.ReduceOp.MAX, group=group)
+    n_rounds = int(t_r.item())
+    ph = _Phases(dev)
+    locals_ = [None, None]
+    free_ev = [None, None]
+    owner, ex = None, None
+    stats_all, fused_all, names = [], [], {}
+    prof = None
+    pushed_rows = pushed_contrib = 0
+    for r in range(n_rounds):
+        chunk = todo[r * round_submaps:(r + 1) * round_submaps]
+        b = r & 1
+        if locals_[b] is None:
+            locals_[b] = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=round_capacity or (1 << 18))
+        L = locals_[b]
+        if free_ev[b] is not None:
+            main.wait_event(free_ev[b])  # the push of round r-2 has read this map and it has been cleared
+        if chunk:
+            _, fused, nm = graph_map.fuse_into_device_map(voxel_size, stride, ignore_loop_closure_frames, True, None,
+                                                          False, profile, dm=L, submaps=chunk)
+            st = graph_map.last_build_stats
+            stats_all += st
+            fused_all += fused
+            names.update(nm)
+            if profile and graph_map.last_profile is not None:
+                prof = dict(graph_map.last_profile) if prof is None else {k: prof[k] + v for k, v in graph_map.last_profile.items()}
+        n_log = L.num_log_entries
+        pushed_rows += L.num_voxels
+        pushed_contrib += n_log
+        ev = torch.cuda.Event()
+        ev.record(main)
+        if r == 0:
+            # the first round sizes the inboxes and, unless the caller knows better, the owner shard
+            sizes = _sizes_all([L.num_voxels, n_log], group, dev)
+            tot_v, tot_c = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+            need_rows = int(1.5 * tot_v / world) + (1 << 16)
+            need_contrib = int(1.5 * tot_c / world) + (1 << 16)
+            ex = peer.exchange_for(dev, d, need_rows, need_contrib, group)
+            cap = owner_capacity or (int(1.3 * tot_v * n_rounds / world) + (1 << 16))
+            owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=cap, device=dev)
+            owner.reserve_log(int(1.3 * tot_c * n_rounds / world) + (1 << 16))
+            torch.cuda.synchronize(dev)  # the owner's allocation (zeroed rows) is complete before any stream uses it
+        with torch.cuda.stream(xs):
+            xs.wait_event(ev)
+            ex.push(L)
+            L.clear_async()
+            free_ev[b] = torch.cuda.Event()
+            free_ev[b].record(xs)
+            ex.drain_async(owner, slot=0)
+    ph.mark("rounds")
+    with torch.cuda.stream(xs):
+        got_rows, got_contrib = peer.drain_collect(owner, slot=0)  # synchronises the exchange stream; errors surface here
+    main.wait_stream(xs)
+    ph.mark("last_exchange")
+    for L in locals_:
+        if L is not None:
+            L.close()
+    graph_map.last_build_stats = stats_all
+    graph_map.last_profile = prof
+    shard = _finish_shard(owner, fused_all, voxel_size, group, dev, ph)
+    if timings is not None:
+        timings.update({"rounds": n_rounds, "pushed_rows": int(pushed_rows), "pushed_contrib": int(pushed_contrib),
+                        "received_rows": int(got_rows), "received_contrib": int(got_contrib),
+                        "inbox_rows": int(ex.cap_rows), "row_bytes": 16 + 4 * d,
+                        "phases_ms": {ph.marks[i][0]: 1e3 * (ph.marks[i][1] - ph.marks[i - 1][1])
+                                      for i in range(1, len(ph.marks))} if ph.on else None})
+    return shard, stats_all
+
+
+def shard_invariants(shard: "ShardedVoxelMap", stats, group=None) -> dict:
+    """Collective, cheap at any size: sum of the per-voxel counts over all shards == points fused by all ranks; the
+    shards' sizes add up to the global voxel count; the global indices are a permutation (sum and sum of squares)."""
+    dm = shard._dm
+    dev = dm.device
+    V = dm.num_voxels
+    counts = dm.export_geometry(coords=False, centers=False, counts=True, recon=False)[2] if V else torch.zeros(0, dtype=torch.int64, device=dev)
+    g = shard.global_index.to(torch.float64)
+    t = torch.tensor([float(counts.sum().item()) if V else 0.0, float(sum(s["n_fused"] for s in stats)), float(V),
+                      float(g.sum().item()) if V else 0.0, float((g * g).sum().item()) if V else 0.0],
+                     dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    n = float(shard.n_global)
+    out = {"points_in_voxels": int(t[0].item()), "points_fused": int(t[1].item()), "voxels": int(t[2].item()),
+           "n_global": int(shard.n_global)}
+    out["counts_conserved"] = out["points_in_voxels"] == out["points_fused"]
+    out["shards_cover_map"] = out["voxels"] == out["n_global"]
+    out["indices_are_a_permutation"] = bool(abs(t[3].item() - n * (n - 1) / 2) < 0.5 and
+                                            abs(t[4].item() - (n - 1) * n * (2 * n - 1) / 6) <= 1e-9 * max(t[4].item(), 1.0))
+    out["ok"] = bool(out["counts_conserved"] and out["shards_cover_map"] and out["indices_are_a_permutation"])
+    return out
+
+
+def parity_check(make_submap, n_submaps: int, voxel_size: float, dim: int, group=None, round_submaps: Optional[int] = None,
+                 top_k: int = 5) -> dict:
+    """Collective correctness check of the multi-GPU build, small enough to run before a benchmark: `n_submaps`
+    submaps (``make_submap(i) -> vsm.Submap``, a pure function of i) are built sharded over the group -- one-shot
+    exchange, or streaming rounds when `round_submaps` is given -- and rank 0 also builds ALL of them on its own GPU;
+    the union of the shards must equal that map: keys, counts, contributors bit-exact, features to 1e-3, and the
+    sharded query must return the single-GPU query's indices.  Returns a report dict ("ok": bool) on every rank."""
+    from .map import GraphMap
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gm = GraphMap()
+    for i in range(rank, n_submaps, world):
+        gm.add_submap(make_submap(i))
+    if round_submaps:
+        sh, stats = build_sharded_streaming(gm, voxel_size, round_submaps, group=group)
     else:
-        names_sigs = tuple(int(x) for x in names_sigs)
-    cache_key = (id(group) if group is not None else 0, dev.index)
-    cached = _NAMES_CACHE.get(cache_key)
-    if cached is not None and cached[0] == names_sigs and cached[1] == my_sig:
-        everyone = cached[2]
-    else:
-        everyone = [None] * world
-        dist.all_gather_object(everyone, mine, group=group)
-        _NAMES_CACHE[cache_key] = (names_sigs, my_sig, everyone)
-    frame_ids, all_names = {}, {}
-    for part in everyone:
-        for sid, (ids, nm) in part.items():
-            frame_ids[sid] = ids
-            all_names[str(sid)] = nm
-
-    class _SubmapStub:
-        def __init__(self, sid, ids):
-            self._sid, self.frame_ids = sid, ids
-
-        def get_id(self):
-            return self._sid
-
-    fused_all = [{"submap": _SubmapStub(sid, ids)} for sid, ids in frame_ids.items()]
-    ph.mark("names")
-    local = wrap_device_map(owner, fused_all, all_names, voxel_size, True, False) if owner.num_voxels else None
-    ph.mark("wrap")
-    gidx, n_global = global_ranks(owner.export_packed_keys(), group)
-    ph.mark("ranks")
-    ph.report()
-    return ShardedVoxelMap(local, owner, gidx, n_global, group), stats
+        sh, stats = build_sharded(gm, voxel_size, group=group)
+    inv = shard_invariants(sh, stats, group)
+    dm = sh._dm
+    V = dm.num_voxels
+    keys = dm.export_packed_keys().cpu().numpy() if V else np.zeros(0, np.int64)
+    counts = dm.export_geometry(coords=False, centers=False, counts=True, recon=False)[2].cpu().numpy() if V else np.zeros(0, np.int64)
+    feats = dm.features_to_host() if V else np.zeros((0, dim), np.float32)
+    contribs = sh.local.get_contributors().tolist() if sh.local is not None else []
+    gidx = sh.global_index.cpu().numpy()
+    rng = np.random.default_rng(5)
+    Q = rng.normal(size=(4, dim)).astype(np.float32)
+    Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+    qi, qs = sh.query_with_embeddings(Q, top_k=top_k)
+    parts = [None] * world
+    dist.all_gather_object(parts, (keys, counts, feats, contribs, gidx), group=group)
+    report = {"world": world, "submaps": n_submaps, "mode": "streaming" if round_submaps else "one-shot", "invariants": inv}
+    if rank == 0:
+        gm1 = GraphMap()
+        for i in range(n_submaps):
+            gm1.add_submap(make_submap(i))
+        single = gm1.build_semantic_voxel_map(voxel_size)
+        sdm = single._dm
+        s_keys = sdm.export_packed_keys().cpu().numpy()
+        s_counts = sdm.export_geometry(coords=False, centers=False, counts=True, recon=False)[2].cpu().numpy()
+        all_gidx = np.concatenate([p[4] for p in parts])
+        order = np.argsort(all_gidx, kind="stable")
+        report["voxels"] = int(len(s_keys))
+        report["keys"] = bool(len(all_gidx) == len(s_keys) and np.array_equal(np.sort(all_gidx), np.arange(len(s_keys)))
+                              and np.array_equal(np.concatenate([p[0] for p in parts])[order], s_keys))
+        report["counts"] = bool(report["keys"] and np.array_equal(np.concatenate([p[1] for p in parts])[order], s_counts))
+        f_all = np.concatenate([p[2] for p in parts])[order] if report["keys"] else None
+        f_ref = single.get_features()
+        report["features_rtol"] = 1e-3
+        report["features"] = bool(report["keys"] and np.allclose(f_all, f_ref, rtol=1e-3, atol=1e-5))
+        allc = sum([p[3] for p in parts], [])
+        report["contributors"] = bool(report["keys"] and [allc[i] for i in order] == single.get_contributors().tolist())
+        si, _, ss = single.query_with_embeddings(Q, top_k=top_k)
+        report["query"] = bool(np.array_equal(qi, si) and np.allclose(qs, ss, rtol=1e-3, atol=1e-6))
+        report["ok"] = bool(inv["ok"] and all(report[k] for k in ("keys", "counts", "features", "contributors", "query")))
+    box = [report]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]

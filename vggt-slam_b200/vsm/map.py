@@ -150,17 +150,25 @@ class GraphMap:
         dm.finalize()
         return wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contributors, exact_coords)
 
+    def usable_submaps(self):
+        """The submaps build_semantic_voxel_map fuses (map.py:196-203 skips the others), in key order."""
+        return [sm for sm in self.ordered_submaps_by_key()
+                if getattr(sm, "semantic_embeddings", None) is not None and sm.pointclouds is not None
+                and sm.conf is not None and sm.conf_threshold is not None and sm.H_world_map is not None]
+
     def fuse_into_device_map(self, voxel_size, stride=1, ignore_loop_closure_frames=True,
-                             deduplicate_contributors=True, capacity_hint=None, host_streaming=None, profile=False):
+                             deduplicate_contributors=True, capacity_hint=None, host_streaming=None, profile=False,
+                             dm=None, submaps=None):
         """The per-submap loop of build_semantic_voxel_map: returns (DeviceVoxelMap or None, fused-call records,
-        frame_name_maps) before finalisation (the multi-GPU build exchanges voxels at this point)."""
+        frame_name_maps) before finalisation (the multi-GPU build exchanges voxels at this point).
+        ``submaps``: fuse only these (a round of the streaming multi-GPU build); ``dm``: fuse into this map."""
         if voxel_size <= 0.0:
             raise ValueError("voxel_size must be > 0")
         if stride < 1:
             raise ValueError("stride must be >= 1")
         vm.require_cuda()
         todo = []
-        for submap in self.ordered_submaps_by_key():
+        for submap in (self.ordered_submaps_by_key() if submaps is None else submaps):
             if getattr(submap, "semantic_embeddings", None) is None:
                 continue
             if submap.pointclouds is None or submap.conf is None or submap.conf_threshold is None:
@@ -172,10 +180,11 @@ class GraphMap:
         self.last_build_stats = []
         self.last_profile = None
         if not todo:
-            return None, [], frame_name_maps
+            return dm, [], frame_name_maps
         d = _shape(todo[0].semantic_embeddings)[-1]
         code = todo[0].embedding_dtype_code()
-        dm = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=capacity_hint or (1 << 18))
+        if dm is None:
+            dm = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=capacity_hint or (1 << 18))
         if profile:
             dm.profile_enable(True)
         flags = N.FUSE_FILTERS | (0 if deduplicate_contributors else N.FUSE_KEEP_POINT_INDEX)

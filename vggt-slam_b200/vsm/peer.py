@@ -69,6 +69,26 @@ def drain(owner, inbox_ptr: int, world: int, cap_rows: int, cap_contrib: int, ep
     return int(n_rows.value), int(n_contrib.value)
 
 
+def drain_async(owner, inbox_ptr: int, world: int, cap_rows: int, cap_contrib: int, epoch: int, slot: int = 0,
+                timeout_s: float = 30.0) -> None:
+    """vsm_partials_drain_async on the current stream (the owner map must have room: reserve / reserve_log)."""
+    from .voxel_map import _stream_ptr
+
+    N.check(N.lib.vsm_partials_drain_async(owner._h, C.c_void_p(int(inbox_ptr)), int(world), int(cap_rows), int(cap_contrib),
+                                           int(epoch), float(timeout_s), int(slot), _stream_ptr(owner.device)))
+
+
+def drain_collect(owner, slot: int = 0):
+    """vsm_partials_drain_collect: synchronises the current stream; (rows, contributor entries) received by the drains
+    queued on `slot` since its last collect."""
+    from .voxel_map import _stream_ptr
+
+    n_rows, n_contrib, flags = C.c_int64(0), C.c_int64(0), C.c_uint32(0)
+    N.check(N.lib.vsm_partials_drain_collect(owner._h, int(slot), C.byref(n_rows), C.byref(n_contrib), C.byref(flags),
+                                             _stream_ptr(owner.device)))
+    return int(n_rows.value), int(n_contrib.value)
+
+
 class PeerUnavailable(RuntimeError):
     """CUDA IPC / peer access does not work between the GPUs of this group (raised on EVERY rank)."""
 
@@ -120,6 +140,10 @@ class PeerExchange:
         out = drain(owner, self.mine.ptr, self.world, self.cap_rows, self.cap_contrib, self.epoch, timeout_s)
         self.epoch += 1
         return out
+
+    def drain_async(self, owner, slot: int = 0, timeout_s: float = 30.0) -> None:
+        drain_async(owner, self.mine.ptr, self.world, self.cap_rows, self.cap_contrib, self.epoch, slot, timeout_s)
+        self.epoch += 1
 
     def close(self) -> None:
         """Collective: nobody may unmap or free while a peer could still be writing."""

@@ -32,7 +32,7 @@ def _rot(axis, angle: float) -> np.ndarray:
 
 
 def box_room_frames_device(gen: torch.Generator, S: int, H: int, W: int, room, noise: float, start: float,
-                           device: torch.device):
+                           device: torch.device, step: float = 0.08):
     room_t = torch.tensor(room, dtype=torch.float64, device=device)
     fx = 0.8 * W
     u = (torch.arange(W, dtype=torch.float64, device=device) - (W - 1) / 2.0) / fx
@@ -44,7 +44,7 @@ def box_room_frames_device(gen: torch.Generator, S: int, H: int, W: int, room, n
     cams = []
     room_np = np.asarray(room, dtype=np.float64)
     for s in range(S):
-        t = start + 0.08 * s
+        t = start + step * s
         centre = room_np * (0.5 + 0.22 * np.array([math.cos(t), math.sin(1.3 * t), 0.3 * math.sin(0.7 * t)]))
         R = _rot([0.0, 0.0, 1.0], 0.9 * t + 0.3) @ _rot([1.0, 0.0, 0.0], -math.pi / 2 + 0.15 * math.sin(t))
         cams.append((R, centre))
@@ -97,6 +97,40 @@ def make_submap_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: 
     elif mode == "se3":
         Hm[3, :] = [0.0, 0.0, 0.0, 1.0]
     paths = [f"left_{first_frame_number + i:06d}.png" for i in range(S)]
+    return DeviceSubmapData(submap_id, pts, conf, emb, Hm.astype(np.float64), paths, S - 1)
+
+
+def make_trajectory_submap_device(seed: int, submap_id: int, S: int = 32, H: int = 294, W: int = 518, d: int = 512,
+                                   room=(8.0, 6.0, 3.0), step: float = 0.2, noise: float = 0.005,
+                                   emb_dtype: torch.dtype = torch.bfloat16,
+                                   device: Optional[torch.device] = None, with_emb: bool = True,
+                                   emb_from: Optional[torch.Tensor] = None) -> DeviceSubmapData:
+    """Submap `submap_id` of the LONG-TRAJECTORY workload (BASELINE configs[2]): a corridor of rooms chained
+    along x, one room per submap (room i spans x in [i*Lx, (i+1)*Lx]); neighbouring rooms share a wall plane, so
+    consecutive submaps overlap there and the voxel count of the map grows linearly with the number of submaps.
+    Everything is a function of (seed, submap_id) only: any rank can regenerate any submap, nothing depends on how the
+    submaps are sharded.  ``emb_from``: reuse an existing embedding tensor (the benchmark keeps a small pool of 5 GB
+    embedding arrays instead of one per submap: the values do not influence which voxels a point falls into)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 1000003 + 7919 * submap_id + 17)
+    pts, M_room_local = box_room_frames_device(gen, S, H, W, room, noise, 0.37 * submap_id, device, step)
+    u = torch.rand((2, S, H, W), dtype=torch.float32, device=device, generator=gen).clamp_min_(1e-12)
+    conf = (1.0 - 2.0 * (torch.log(u[0]) + torch.log(u[1]))).contiguous()
+    del u
+    emb = emb_from
+    if emb is None and with_emb:
+        emb = torch.empty((S, H, W, d), dtype=emb_dtype, device=device)
+        for s in range(S):
+            emb[s] = torch.randn((H, W, d), dtype=torch.float32, device=device, generator=gen).to(torch.bfloat16).to(emb_dtype)
+    T = np.eye(4)
+    T[0, 3] = float(room[0]) * submap_id  # the room's place in the corridor
+    rng = np.random.default_rng([seed, submap_id, 3])
+    G = synth.random_sl4(np.random.default_rng([seed, 987654321]))
+    Hm = G @ T @ M_room_local
+    Hm = Hm @ (np.eye(4) + 1e-4 * rng.normal(size=(4, 4)))
+    Hm = Hm / abs(np.linalg.det(Hm)) ** 0.25
+    paths = [f"left_{submap_id * S + i:07d}.png" for i in range(S)]
     return DeviceSubmapData(submap_id, pts, conf, emb, Hm.astype(np.float64), paths, S - 1)
 
 

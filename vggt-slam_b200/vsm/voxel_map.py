@@ -89,10 +89,25 @@ class DeviceVoxelMap:
     def reserve(self, n_voxels: int) -> None:
         N.check(N.lib.vsm_map_reserve(self._h, int(n_voxels), _stream_ptr(self.device)))
 
+    def reserve_log(self, n_entries: int) -> None:
+        N.check(N.lib.vsm_map_reserve_log(self._h, int(n_entries), _stream_ptr(self.device)))
+
+    def clear_async(self) -> None:
+        """vsm_map_clear_async on the CURRENT stream: queued behind what still reads the map there, no host wait."""
+        N.check(N.lib.vsm_map_clear_async(self._h, _stream_ptr(self.device)))
+        self.fuse_calls = 0
+
     @property
     def num_voxels(self) -> int:
         out = C.c_int64()
         N.check(N.lib.vsm_num_voxels(self._h, C.byref(out)))
+        return int(out.value)
+
+    @property
+    def num_log_entries(self) -> int:
+        """Contributor-log entries held (one per fuse call and voxel): what an exchange push sends besides the rows."""
+        out = C.c_int64()
+        N.check(N.lib.vsm_num_log_entries(self._h, C.byref(out)))
         return int(out.value)
 
     # -- fusion -----------------------------------------------------------
