@@ -214,7 +214,7 @@ def test_rounds_with_queued_drains_equal_single_map():
     assert [contribs[i] for i in order] == single.get_contributors().tolist()
     # an owner without room reports it at the collect instead of growing behind the host's back
     tiny = vm.DeviceVoxelMap(0.05, 64, 0, capacity=1024)
-    gm = _local_map(vsm, subs[:2], 0.05)
+    gm = _local_map(vsm, subs[:8], 0.05)
     dm, _, _ = gm.fuse_into_device_map(0.05)
     assert dm.num_voxels > 1024
     peer.push(dm, [ptrs[0]], cap_rows, cap_contrib, rounds)

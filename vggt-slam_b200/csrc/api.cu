@@ -312,6 +312,7 @@ extern "C" int vsm_map_clear(vsm_map* m, void* stream) {
     }
   }
   VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, 2 * sizeof(uint32_t), s));
+  if (m->drain_report.p) VSM_CUDA(cudaMemsetAsync(m->drain_report.p, 0, m->drain_report.bytes, s));
   for (auto& c : m->pending) c.precheck_mask.release();
   m->pending.clear();
   m->stats_backlog.clear();
@@ -350,6 +351,7 @@ extern "C" int vsm_map_clear_async(vsm_map* m, void* stream) {
     VSM_CUDA(cudaMemsetAsync(m->vsum.p, 0, used * (size_t)m->d * 4, s));
   }
   VSM_CUDA(cudaMemsetAsync(m->d_n_vox.p, 0, 2 * sizeof(uint32_t), s));
+  if (m->drain_report.p) VSM_CUDA(cudaMemsetAsync(m->drain_report.p, 0, m->drain_report.bytes, s));
   m->stats_backlog.clear();
   m->n_vox = 0;
   m->log_n = 0;

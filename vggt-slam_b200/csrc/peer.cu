@@ -390,7 +390,7 @@ static int drain_enqueue(vsm_map* m, void* inbox, int32_t world, int64_t cap_row
   m->norms_valid = false;
   if (!m->drain_report.p) {
     VSM_TRY(m->drain_report.ensure(4 * 32, s));
-    VSM_CUDA(cudaMemsetAsync(m->drain_report.p, 0, 4 * 32, s));
+    VSM_CUDA(cudaMemsetAsync(m->drain_report.p, 0, m->drain_report.bytes, s));
   }
   VSM_TRY(m->xch_tmp.ensure((size_t)cap_rows * 4, s));
   uint32_t* report = m->drain_report.as<uint32_t>() + 8 * slot;  // [n_rows, n_contrib, flags, n_vox | hash err, log n, -, -]
@@ -432,7 +432,10 @@ static int drain_collect(vsm_map* m, int slot, int32_t world, double timeout_s, 
   if (n_contrib_host) *n_contrib_host = rep[1];
   if (flags_host) *flags_host = rep[2];
   if (rep[2] & kInboxTimeout) {
-    set_error("vsm_partials_drain: timed out after %.1f s waiting for %d senders", timeout_s, world);
+    if (world > 0)
+      set_error("vsm_partials_drain: timed out after %.1f s waiting for %d senders", timeout_s, world);
+    else
+      set_error("vsm_partials_drain: a queued drain timed out waiting for its senders");
     return VSM_E_STATE;
   }
   if (rep[2] & kInboxHashErr) {
