@@ -8,15 +8,21 @@ the three outlier filters on) + finalisation.  Synthetic inputs (vsm.synth_devic
   value      whole-job points fused / s with inputs resident in HBM (device tensors in the Submaps)
   e2e        the same build through the public API with HOST (pinned) arrays: every step copies the
              point maps, confidences and embeddings host->device inside the timed region and reads the
-             finished map (centres + features) back device->host
+             finished map (centres + features + contributor tables) back device->host; `e2e.f32` is the same with
+             numpy float32 embeddings (the reference's contract, submap.py:41-65: twice the bytes)
   roofline   accumulate kernel: algorithmic bytes / CUDA-event time (events recorded inside libvsm on the
              launching stream) against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample, 1 core (the path is
-                single-threaded numpy); cpu_baseline.parallel: as many independent copies as the host has cores
-                (up to 16), each on its own submap, started together -- an extra figure, not the baseline
+                single-threaded numpy); `.parity`: the same sample fused by the GPU path and compared with the
+                oracle's output; `.parallel`: as many independent copies as the host has cores (an extra figure)
+  cuda_library_baseline  the reference's own torch-CUDA branch of the global voxelisation (map.py:322-348:
+                torch.unique + index_add_ over 1000-row host chunks) restated with torch, timed on this GPU
 
-`--impl reference` times that CPU port alone (the reference arm).  N>1 (torchrun): every rank fuses its own
-20 submaps (weak scaling), then voxels are exchanged by key-hash owner with an NCCL all-to-all and merged.
+`--impl reference` times the CPU port alone (the reference arm).  N>1 (torchrun): every rank fuses its own 20
+submaps (weak scaling) in rounds; each round's voxels are pushed to their owners (key hash) over NVLink peer memory and
+merged there on an exchange stream while the next round is fused; `dist_parity` is an in-process correctness check of
+that build (union of the shards == single-GPU map) run before the timing, and `secondary.long_trajectory` is BASELINE
+configs[2] (200 submaps of a corridor at 2 cm voxels, sharded over the ranks).
 """
 from __future__ import annotations
 
@@ -58,7 +64,11 @@ def parse_args():
     ap.add_argument("--voxel-size", type=float, default=0.05)
     ap.add_argument("--emb-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-submaps", type=int, default=-1, help="-1: all")
+    ap.add_argument("--e2e-submaps", type=int, default=6, help="submaps per GPU of the e2e arm (same at every N); -1: all")
+    ap.add_argument("--round-submaps", type=int, default=5, help="N>1: submaps per exchange round (0: one exchange at the end)")
+    ap.add_argument("--traj-submaps", type=int, default=200, help="submaps of the long-trajectory block (configs[2]); 0: skip")
+    ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per step (0: the largest of 4/8/16/32 that fits the time budget)")
+    ap.add_argument("--no-dist-parity", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one submap in the CPU sample")
     ap.add_argument("--cpu-procs", type=int, default=min(os.cpu_count() or 1, 16),
                     help="also run this many independent copies of the CPU port at once (cpu_baseline.parallel); 1: skip")
@@ -165,12 +175,12 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # CPU arm: the numpy oracle (port of vggt_slam/map.py:170-381, numpy branch) on a bounded sample
 # ---------------------------------------------------------------------------
-def cpu_sample_inputs(args, seed=1234):
-    """One submap's first `cpu_frames` frames, host numpy.  Generated on the GPU when there is one (identical
+def cpu_sample_inputs(args, seed=1234, frames=None):
+    """One submap's first `frames` frames, host numpy.  Generated on the GPU when there is one (identical
     generator to the GPU workload), else with the numpy generator."""
     import torch
 
-    S = args.cpu_frames
+    S = args.cpu_frames if frames is None else int(frames)
     if torch.cuda.is_available():
         from vsm import synth_device
 
@@ -192,7 +202,7 @@ def cpu_sample_inputs(args, seed=1234):
     return vo.OracleSubmap(0, pts, conf, vo.conf_threshold(conf, 25.0), emb, Hm, fids, names, S - 1)
 
 
-def cpu_run_once(sm, voxel_size):
+def cpu_run_once(sm, voxel_size, keep=False):
     from oracle import voxel_oracle as vo
 
     t0 = time.perf_counter()
@@ -200,7 +210,84 @@ def cpu_run_once(sm, voxel_size):
         out = vo.build_global([sm], voxel_size, exact_order=True, with_contributors=True)
     vo.coord_index(vo.coords_from_centers(out.centers_world, voxel_size))  # SemanticVoxelMap.__init__'s dict
     dt = time.perf_counter() - t0
-    return out.n_points, dt
+    return (out.n_points, dt, out) if keep else (out.n_points, dt)
+
+
+def gpu_parity_on_sample(sm, voxel_size, want):
+    """The CPU sample fused by the GPU path (same arrays, float32 embeddings from host numpy, public API) against the
+    oracle's output for it: centres and per-voxel counts bit-exact, features to 1e-3, contributors equal."""
+    import vsm
+
+    g = vsm.Submap(0)
+    g.add_all_points(sm.points, None, sm.conf, 25.0, None)
+    g.add_all_semantic_embeddings(np.ascontiguousarray(sm.emb, dtype=np.float32))
+    g.set_conf_masks(sm.conf)
+    g.set_reference_homography(sm.H_world_map)
+    g.frame_ids, g.frame_id_to_name = list(sm.frame_ids), dict(sm.frame_id_to_name)
+    g.frame_names = list(sm.frame_id_to_name.values())
+    g.set_last_non_loop_frame_index(sm.last_non_loop_frame_index)
+    gm = vsm.GraphMap()
+    gm.add_submap(g)
+    m = gm.build_semantic_voxel_map(voxel_size)
+    out = {"conf_threshold": bool(float(g.conf_threshold) == float(sm.conf_threshold)),
+           "voxels": int(len(want.centers_world)), "points": int(want.n_points)}
+    out["centers"] = bool(np.array_equal(m.get_centers_world(), want.centers_world))
+    counts = m._dm.export_geometry(coords=False, centers=False, counts=True, recon=False)[2].cpu().numpy()
+    out["counts"] = bool(out["centers"] and np.array_equal(counts, want.counts))
+    out["points_fused"] = bool(sum(st["n_fused"] for st in gm.last_build_stats) == want.n_points)
+    out["features_rtol"] = 1e-3
+    out["features"] = bool(out["centers"] and np.allclose(m.get_features(), want.features, rtol=1e-3, atol=1e-5))
+    contribs = m.get_contributors()
+    probe = range(0, len(want.contributors), max(1, len(want.contributors) // 2000))
+    out["contributors_sampled"] = bool(out["centers"] and all(contribs[i] == want.contributors[i] for i in probe))
+    out["ok"] = all(out[k] for k in ("conf_threshold", "centers", "counts", "points_fused", "features", "contributors_sampled"))
+    return out
+
+
+def cuda_library_baseline(sm, voxel_size, dev):
+    """The reference's torch-CUDA branch of the global voxelisation (vggt_slam/map.py:322-348) restated with the same
+    torch calls on the filtered observations of the CPU sample: floor(pts / vs) -> torch.unique(dim=0) -> index_add_
+    over 1000-row chunks that are copied host->device one by one -> bincount -> mean -> results back on the host.
+    (Everything before it -- masks, transform, the three filters -- stays numpy in the reference whichever branch runs.)
+    `features_resident`: the same with the features already on the device and ONE index_add_ (what the branch could
+    do at best)."""
+    import torch
+    from oracle import voxel_oracle as vo
+
+    with np.errstate(all="ignore"):
+        obs = vo.submap_observations(sm, voxel_size, 1, True)
+    pts_world_all, feats_all = np.ascontiguousarray(obs[0], dtype=np.float32), np.ascontiguousarray(obs[1], dtype=np.float32)
+    n = int(pts_world_all.shape[0])
+
+    def run(resident):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        pts_t = torch.from_numpy(pts_world_all).to(device=dev, dtype=torch.float32)
+        feats_t = torch.from_numpy(feats_all)
+        vc = torch.floor(pts_t / float(voxel_size)).to(torch.int64)
+        uniq, inv = torch.unique(vc, dim=0, return_inverse=True)
+        nv, d = int(uniq.shape[0]), int(feats_t.shape[1])
+        fsum = torch.zeros((nv, d), device=dev, dtype=torch.float32)
+        if resident:
+            fsum.index_add_(0, inv, feats_t.to(device=dev, dtype=torch.float32))
+        else:
+            for i in range(0, n, 1000):
+                fsum.index_add_(0, inv[i:i + 1000], feats_t[i:i + 1000].to(device=dev, dtype=torch.float32))
+        counts = torch.bincount(inv, minlength=nv).to(torch.float32)
+        avg = fsum / counts[:, None].clamp_min(1.0)
+        centers = (uniq.to(torch.float32) + 0.5) * float(voxel_size)
+        _ = uniq.cpu().numpy(), inv.cpu().numpy(), centers.cpu().numpy(), avg.cpu().numpy()
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t0, nv
+
+    run(False)
+    dt, nv = run(False)
+    run(True)
+    dt_res, _ = run(True)
+    return {"what": "reference torch-CUDA branch (map.py:322-348) restated: unique + chunked index_add_, global "
+                    "voxelisation only (per-submap filters excluded: numpy in the reference)",
+            "points": n, "voxels": nv, "value": n / dt, "unit": UNIT, "ms": 1e3 * dt,
+            "features_resident": {"value": n / dt_res, "unit": UNIT, "ms": 1e3 * dt_res}}
 
 
 _WORKER_SAMPLE = None
@@ -266,13 +353,23 @@ def cpu_parallel(args, procs):
     return {"procs": procs, "value": n / wall, "unit": UNIT, "wall_s": wall, "points": int(n)}
 
 
-def cpu_baseline(args):
+def cpu_baseline(args, dev=None):
     sm = cpu_sample_inputs(args)
-    n, dt = cpu_run_once(sm, args.voxel_size)
+    n, dt, want = cpu_run_once(sm, args.voxel_size, keep=True)
     out = {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
            "sample": f"1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32, "
                      f"{n} points fused in {dt:.1f} s by the numpy oracle (np.unique + np.add.at are single-threaded)",
            "host_cpus": os.cpu_count()}
+    if dev is not None:
+        try:
+            out["parity"] = gpu_parity_on_sample(sm, args.voxel_size, want)
+        except Exception as e:
+            out["parity"] = {"ok": False, "error": repr(e)}
+        try:
+            out["cuda_library_baseline"] = cuda_library_baseline(sm, args.voxel_size, dev)
+        except Exception as e:
+            out["cuda_library_baseline"] = {"error": repr(e)}
+    del want
     if args.cpu_procs > 1:
         try:
             del sm
@@ -284,10 +381,29 @@ def cpu_baseline(args):
 
 
 def run_reference_arm(args):
+    """The reference arm: the CPU port of GraphMap.build_semantic_voxel_map (the Python reference cannot travel to the
+    GPU box) on ONE submap of the benchmark's shape per step.  A full 32-frame submap takes ~1-2 minutes on one core
+    (BASELINE.md 3), so the step is a bounded sample: the largest of 4 / 8 / 16 / 32 frames for which warm-up + steps fit
+    ~7 minutes, measured from a 4-frame probe.  config.workload states exactly what ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sm = cpu_sample_inputs(args)
+    frames = args.ref_frames
+    probe_rate = None
+    if frames <= 0:
+        probe = max(1, min(4, args.frames))
+        sm = cpu_sample_inputs(args, frames=probe)
+        n, dt = cpu_run_once(sm, args.voxel_size)
+        probe_rate = n / dt
+        per_frame = dt / probe
+        budget = 420.0 / max(args.steps + min(args.warmup, 1), 1)
+        frames = probe
+        for f in (8, 16, 32):
+            if f <= args.frames and 1.15 * per_frame * f <= budget:
+                frames = f
+        del sm
+        release_host_memory()
+    sm = cpu_sample_inputs(args, frames=frames)
     for _ in range(min(args.warmup, 1)):
         cpu_run_once(sm, args.voxel_size)
     n_tot, t_tot = 0, 0.0
@@ -296,14 +412,21 @@ def run_reference_arm(args):
         n_tot += n
         t_tot += dt
     v = n_tot / t_tot
-    sample = (f"each step: 1 submap x {args.cpu_frames} frames of {args.width}x{args.height}, d={args.dim} f32 "
-              f"({n_tot // max(args.steps, 1)} points) through the numpy oracle port of GraphMap.build_semantic_voxel_map")
+    sample = (f"each step: 1 submap x {frames} frames of {args.width}x{args.height}, d={args.dim} f32 "
+              f"({n_tot // max(args.steps, 1)} points) through the numpy oracle port of GraphMap.build_semantic_voxel_map; "
+              f"1 untimed warm-up step")
+    cfg = {"workload": f"office_loop-shaped synthetic, bounded sample: 1 submap x {frames} frames, {args.width}x{args.height} "
+                       f"pointmaps, {args.dim}-d f32 embeddings, {args.voxel_size * 100:g} cm voxels, SL(4), outlier filters on "
+                       f"(the GPU arm runs {args.submaps} submaps x {args.frames} frames per step; rates are per point)",
+           "submaps_per_gpu": 1, "frames": frames, "height": args.height, "width": args.width, "dim": args.dim,
+           "voxel_size": args.voxel_size, "emb_dtype": "f32", "same_config_as_gpu_arm": False,
+           "parallelism": "one host core (numpy's unique / add.at are single-threaded)"}
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_tot / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": workload_config(args, 1),
+            "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                             "host_cpus": os.cpu_count()},
+                             "host_cpus": os.cpu_count(), "probe_points_per_s": probe_rate},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if args.cpu_procs > 1:
@@ -321,7 +444,11 @@ def workload_config(args, world):
                         f"{args.voxel_size * 100:g} cm voxels, SL(4), outlier filters on",
             "submaps_per_gpu": args.submaps, "frames": args.frames, "height": args.height, "width": args.width,
             "dim": args.dim, "voxel_size": args.voxel_size, "emb_dtype": args.emb_dtype,
-            "parallelism": f"submaps sharded over {world} GPU(s)" + (", voxels owned by key hash and pushed into the owners' inboxes over NVLink peer memory (one-sided, csrc/peer.cu), then merged" if world > 1 else ""),
+            "parallelism": f"submaps sharded over {world} GPU(s)" + (
+                f", fused in rounds of {args.round_submaps}; each round's voxels are pushed to their owners (key hash) over NVLink "
+                "peer memory (one-sided, csrc/peer.cu) and merged there on an exchange stream while the next round is fused"
+                if world > 1 and args.round_submaps > 0 else
+                (", voxels owned by key hash and pushed into the owners' inboxes over NVLink peer memory after the last submap" if world > 1 else "")),
             "l2_policy": "inputs larger than L2 (>= 4.9 GB of embeddings per submap, read once)"}
 
 
@@ -557,6 +684,144 @@ def indexed_embeddings(args, dev):
     return out
 
 
+def dist_parity(args, dev, rank, world):
+    """Collective, before the timing: vsm.dist.parity_check on 2*world+1 small submaps -- the union of the owner shards
+    must equal the map rank 0 builds alone (keys, counts, contributors bit-exact; features 1e-3; sharded query == single
+    query) -- for the one-shot exchange and for streaming rounds on a 2 cm corridor."""
+    import torch
+    from vsm import dist as vdist
+    from vsm import synth_device
+
+    def room(i):
+        return synth_device.to_submap(synth_device.make_submap_device(71, i, S=4, H=56, W=84, d=64, mode="sl4", room=(2.4, 1.8, 1.2),
+                                                                      emb_dtype=torch.float32, first_frame_number=4 * i))
+
+    def corridor(i):
+        return synth_device.to_submap(synth_device.make_trajectory_submap_device(72, i, S=4, H=56, W=84, d=64, room=(2.0, 1.5, 1.2),
+                                                                                 emb_dtype=torch.bfloat16))
+
+    n = 2 * world + 1
+    a = vdist.parity_check(room, n, 0.05, 64)
+    b = vdist.parity_check(corridor, n, 0.02, 64, round_submaps=1)
+    keys = ("keys", "counts", "features", "contributors", "query")
+    return {"ok": bool(a["ok"] and b["ok"]), "submaps": n,
+            "one_shot": {k: a.get(k) for k in keys + ("voxels", "features_rtol")}, "one_shot_invariants": a["invariants"]["ok"],
+            "streaming": {k: b.get(k) for k in keys + ("voxels", "features_rtol")}, "streaming_invariants": b["invariants"]["ok"]}
+
+
+def long_trajectory(args, dev, rank, world):
+    """BASELINE configs[2]: `traj_submaps` submaps x 32 frames of a corridor (one 8x6x3 m room per submap, vsm.synth_device.
+    make_trajectory_submap_device), 2 cm voxels, ~250 k new voxels per submap (~50 M at 200 submaps), the submaps sharded in
+    contiguous blocks over the ranks (strong scaling: the total is fixed), streaming exchange in rounds of 5.  Geometry is
+    generated per submap and stays resident (78 MB each); the 5 GB embedding arrays come from a pool of two (their values
+    do not decide which voxel a point falls into).  One warm-up build on a few submaps, then ONE timed build
+    (CUDA events on the main stream + wall clock, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    import vsm
+    from vsm import _native as N
+    from vsm import dist as vdist
+    from vsm import synth_device
+
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    vs, S, H, W, d = 0.02, args.frames, args.height, args.width, args.dim
+    emb_dtype = torch.bfloat16 if args.emb_dtype == "bf16" else torch.float32
+    total = args.traj_submaps
+    per_voxel_bytes = 4 * d + 64
+    free = torch.cuda.mem_get_info(dev)[0]
+    per_rank = (total + world - 1) // world
+    if world == 1:
+        # everything lands in one map: what fits beside the inputs (2 KB per voxel, ~0.27 M voxels per submap)
+        fit = int((0.80 * free - 2 * S * H * W * d * 2) / (0.27e6 * per_voxel_bytes + S * H * W * 16))
+        per_rank = max(4, min(per_rank, fit))
+    first = rank * per_rank
+    mine = list(range(first, min(first + per_rank, total if world > 1 else first + per_rank)))
+    pool = []
+    for k in range(2):
+        e = torch.empty((S, H, W, d), dtype=emb_dtype, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(9000 + 17 * rank + k)
+        for f in range(S):
+            e[f] = torch.randn((H, W, d), dtype=torch.float32, device=dev, generator=g).to(torch.bfloat16).to(emb_dtype)
+        pool.append(e)
+    gm = vsm.GraphMap()
+    for j, i in enumerate(mine):
+        dd = synth_device.make_trajectory_submap_device(4321, i, S=S, H=H, W=W, d=d, emb_dtype=emb_dtype, device=dev,
+                                                        with_emb=False, emb_from=pool[j % len(pool)])
+        gm.add_submap(synth_device.to_submap(dd))
+    torch.cuda.synchronize()
+    K = max(args.round_submaps, 1)
+
+    def build(sub_gm, cap_round=None, cap_owner=None, timings=None):
+        if world > 1:
+            return vdist.build_sharded_streaming(sub_gm, vs, K, round_capacity=cap_round, owner_capacity=cap_owner,
+                                                 timings=timings)
+        m = sub_gm.build_semantic_voxel_map(vs, capacity_hint=cap_owner)
+        return m, sub_gm.last_build_stats
+
+    # warm-up on the first 2 rounds' worth of submaps: warms the pools and measures voxels per submap
+    warm = vsm.GraphMap()
+    for sm in list(gm.ordered_submaps_by_key())[:min(2 * K, len(mine))]:
+        warm.add_submap(sm)
+    m0, st0 = build(warm)
+    vox_per_submap = max(s["n_submap_voxels"] for s in st0)
+    new_per_submap = m0._dm.num_voxels if world == 1 else None
+    n_warm = len(st0)
+    del m0
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    cap_round = int(1.15 * vox_per_submap * K) + (1 << 16)
+    if world == 1:
+        cap_owner = int(1.08 * new_per_submap / n_warm * len(mine)) + (1 << 18)
+    else:
+        cap_owner = int(1.25 * vox_per_submap * len(mine)) + (1 << 18)  # hash ownership spreads the voxels evenly
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    timings = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    m, st = build(gm, cap_round, cap_owner, timings)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    n_fused = float(sum(s["n_fused"] for s in st))
+    t = torch.tensor([ms, 1e3 * wall, n_fused, float(m._dm.num_voxels), float(len(mine))], dtype=torch.float64, device=dev)
+    out = {"workload": f"long-trajectory synthetic: {S} frames x {W}x{H} per submap, {d}-d {args.emb_dtype} embeddings, 2 cm voxels, "
+                       f"SL(4), outlier filters on; corridor of 8x6x3 m rooms, one per submap",
+           "scaling": "strong (the submaps are divided over the ranks)" if world > 1 else "single GPU",
+           "round_submaps": K if world > 1 else None}
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        shard_sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(shard_sizes, torch.tensor([m._dm.num_voxels], dtype=torch.int64, device=dev))
+        inv = vdist.shard_invariants(m, st)
+        row_bytes = timings.get("row_bytes", 16 + 4 * d)
+        sent = torch.tensor([float(timings.get("pushed_rows", 0)) * row_bytes + float(timings.get("pushed_contrib", 0)) * 32.0],
+                            dtype=torch.float64, device=dev)
+        dist.all_reduce(sent, op=dist.ReduceOp.SUM)
+        out.update({"submaps": int(tsum[4].item()), "submaps_per_gpu": len(mine), "ms": float(tmax[0].item()),
+                    "wall_ms": float(tmax[1].item()), "points_fused": int(tsum[2].item()),
+                    "points_per_s": float(tsum[2].item()) / (float(tmax[0].item()) * 1e-3),
+                    "voxels": int(m.n_global), "owner_shard_voxels": [int(x.item()) for x in shard_sizes],
+                    "exchange_bytes_total": int(sent.item()), "exchange_rounds": timings.get("rounds"),
+                    "exchange_GB_per_gpu": float(sent.item()) / world * 1e-9,
+                    "invariants": inv, "phases_ms_rank0": timings.get("phases_ms")})
+    else:
+        out.update({"submaps": len(mine), "submaps_per_gpu": len(mine), "ms": ms, "wall_ms": 1e3 * wall,
+                    "points_fused": int(n_fused), "points_per_s": n_fused / (ms * 1e-3), "voxels": int(m._dm.num_voxels),
+                    "note": None if len(mine) == total else f"{len(mine)} of {total} submaps: what one GPU's memory holds as ONE map"})
+    del m, gm, warm, pool
+    N.lib.vsm_map_cache_release()
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
@@ -604,15 +869,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- N > 1: the multi-GPU build is checked against a single-GPU build before anything is timed -----------------
+    parity = None
+    if world > 1 and not args.no_dist_parity:
+        parity = dist_parity(args, dev, rank, world)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "multi-GPU parity check failed", "dist_parity": parity}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(3)
+
     cap_hint = [1 << 18]
+    round_cap = [1 << 18]
 
     def step():
-        if world > 1:
+        if world > 1 and args.round_submaps > 0:
+            m, stats = vdist.build_sharded_streaming(gm, args.voxel_size, args.round_submaps, round_capacity=round_cap[0],
+                                                     owner_capacity=cap_hint[0], profile=True)
+            round_cap[0] = max(round_cap[0], int(1.3 * max(s["n_submap_voxels"] for s in stats) * args.round_submaps))
+        elif world > 1:
             m, stats = vdist.build_sharded(gm, args.voxel_size, capacity_hint=cap_hint[0], profile=True)
         else:
             m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], profile=True)
             stats = gm.last_build_stats
-        cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.05) + 1024)
+        cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.3) + 1024 if world > 1 else int(m._dm.num_voxels * 1.05) + 1024)
         return m, stats
 
     # the clock poller (a child process) starts before the warm-up, so that its NVML client set-up is long over
@@ -722,16 +1002,14 @@ def main():
     e2e = None
     if not args.no_e2e:
         n_e2e = args.submaps if args.e2e_submaps < 0 else min(args.e2e_submaps, args.submaps)
-        # the e2e arm pins its inputs in host memory (5 GB per submap): never more than 60 % of what the box has free,
-        # shared by the ranks of this node
+        # the e2e arm pins its inputs in host memory (5 GB per submap in bf16): never more than 60 % of what the box has
+        # free, shared by the ranks of this node; the default (6 submaps per GPU) is the same at every N
         try:
             import psutil
 
             per_submap = args.frames * args.height * args.width * (16 + args.dim * esize)
             local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
             budget = 0.6 * psutil.virtual_memory().available / max(local_world, 1)
-            if world > 1:
-                budget = min(budget, 32e9)  # N ranks pin in parallel: keep the multi-GPU runs short (6 submaps per rank)
             n_e2e = max(1, min(n_e2e, int(budget // per_submap)))
         except Exception:
             pass
@@ -739,58 +1017,78 @@ def main():
             t_n = torch.tensor([n_e2e], dtype=torch.int64, device=dev)
             dist.all_reduce(t_n, op=dist.ReduceOp.MIN)
             n_e2e = int(t_n.item())
-        gmh = vsm.GraphMap()
-        h2d = 0
-        for d in datas[:n_e2e]:
-            sm = synth_device.to_submap(d, host=True, pin=True)
-            sm.release_device_cache()
-            gmh.add_submap(sm)
-            h2d += d.points.numel() * 4 + d.conf.numel() * 4 + d.emb.numel() * esize
-        # free the device-resident copies: the e2e arm starts from host memory only
+
+        def e2e_arm(n_sub, as_f32, steps):
+            """Build from pinned host arrays; as_f32: numpy float32 embeddings (the reference's contract)."""
+            gmh = vsm.GraphMap()
+            h2d = 0
+            for d in datas[:n_sub]:
+                if as_f32:
+                    dd = synth_device.DeviceSubmapData(d.submap_id, d.points, d.conf, d.emb.float(), d.H_world_map,
+                                                       d.frame_paths, d.last_non_loop_frame_index, d.conf_percentile)
+                else:
+                    dd = d
+                sm = synth_device.to_submap(dd, host=True, pin=True)
+                sm.release_device_cache()
+                gmh.add_submap(sm)
+                h2d += d.points.numel() * 4 + d.conf.numel() * 4 + d.emb.numel() * (4 if as_f32 else esize)
+                del dd
+            torch.cuda.empty_cache()
+
+            def one():
+                for sm in gmh.get_submaps():
+                    sm.release_device_cache()
+                if world > 1:
+                    mm, st = vdist.build_sharded(gmh, args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
+                else:
+                    mm = gmh.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
+                    st = gmh.last_build_stats
+                loc = mm.local if hasattr(mm, "local") else mm
+                nbytes = 0
+                if loc is not None:
+                    nbytes += loc.get_features().nbytes + loc.get_centers_world().nbytes  # device -> host read of the map
+                    off, sub, mask = loc._dm.export_contributors()                        # ... and of its contributor tables
+                    nbytes += off.nbytes + sub.nbytes + mask.nbytes
+                return sum(s["n_fused"] for s in st), nbytes
+
+            one()  # warm-up (pinned staging, allocations)
+            barrier()
+            t0 = time.perf_counter()
+            pts, d2h = 0, 0
+            for _ in range(steps):
+                n, b = one()
+                pts += n
+                d2h = b
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt, float(pts)], dtype=torch.float64, device=dev)
+            if world > 1:
+                tmax, tsum = t.clone(), t.clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+                dt, pts = float(tmax[0]), float(tsum[1])
+            del gmh, one
+            release_host_memory()
+            return {"value": pts / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "submaps_per_gpu": n_sub, "steps": steps, "ms_per_step": 1e3 * dt / max(steps, 1)}
+
+        # free the device-resident copies of the Submaps: the e2e arm starts from host memory only
         for sm in gm.get_submaps():
             sm.release_device_cache()
         del gm
+        e2e = e2e_arm(n_e2e, False, args.e2e_steps)
+        e2e.update({"api": "GraphMap.build_semantic_voxel_map on pinned host arrays -> vsm_fuse_submap_host; get_features() / "
+                           "get_centers_world() / the contributor tables read the map back",
+                    "embeddings": args.emb_dtype,
+                    "cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU (NVML)" if numa_cpus else "unchanged")})
+        if args.emb_dtype != "f32":
+            try:
+                n32 = max(1, min(n_e2e, 3))
+                e2e["f32"] = dict(e2e_arm(n32, True, 1), embeddings="numpy float32 (the reference's contract, submap.py:41-65)")
+            except Exception as e:
+                e2e["f32"] = {"error": repr(e)}
         datas.clear()
         torch.cuda.empty_cache()
-
-        def e2e_step():
-            for sm in gmh.get_submaps():
-                sm.release_device_cache()
-            if world > 1:
-                mm, st = vdist.build_sharded(gmh, args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
-            else:
-                mm = gmh.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], host_streaming=True)
-                st = gmh.last_build_stats
-            loc = mm.local if hasattr(mm, "local") else mm
-            feats = loc.get_features()  # device -> host read of the finished map
-            cen = loc.get_centers_world()
-            return sum(s["n_fused"] for s in st), feats.nbytes + cen.nbytes
-
-        e2e_step()  # warm-up (pinned staging, allocations)
-        barrier()
-        t0 = time.perf_counter()
-        pts_e2e, d2h = 0, 0
-        for _ in range(args.e2e_steps):
-            n, b = e2e_step()
-            pts_e2e += n
-            d2h = b
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt, float(pts_e2e)], dtype=torch.float64, device=dev)
-        if world > 1:
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            tsum = t.clone()
-            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            dt, pts_e2e = float(tmax[0]), float(tsum[1])
-        e2e = {"value": pts_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "submaps_per_gpu": n_e2e, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / max(args.e2e_steps, 1),
-               "api": "GraphMap.build_semantic_voxel_map on pinned host arrays -> vsm_fuse_submap_host; "
-                      "get_features()/get_centers_world() read the map back",
-               "cpu_affinity": (f"{len(numa_cpus)} CPUs local to the GPU (NVML)" if numa_cpus else "unchanged")}
-        # the pinned inputs (5 GB per submap) go back to the OS before anything else needs host memory
-        del e2e_step, gmh
-        release_host_memory()
 
     # ---- secondary measurements (BASELINE configs[3] and configs[4]), rank 0's GPU only, outside the timed step ----
     secondary = None
@@ -802,6 +1100,17 @@ def main():
                          "indexed_embeddings": indexed_embeddings(args, dev)}
         except Exception as e:  # secondary numbers must never cost the headline line
             secondary = {"error": repr(e)}
+    # ---- BASELINE configs[2]: the long trajectory (collective at N > 1) ------------------------------------------------
+    if not args.no_extras and args.traj_submaps > 0:
+        try:
+            lt = long_trajectory(args, dev, rank, world)
+        except Exception as e:
+            lt = {"error": repr(e)}
+            if world > 1:
+                raise
+        if rank == 0:
+            secondary = secondary if secondary is not None else {}
+            secondary["long_trajectory"] = lt
     # ---- sharded text query (N > 1): every rank owns a shard of `query_voxels` voxels, prompts are scored per shard,
     # P x k candidates are all-gathered and merged (vsm.dist.ShardedVoxelMap); weak scaling of BASELINE configs[3]
     sharded_query = None
@@ -817,7 +1126,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(args)
+        cpu = cpu_baseline(args, dev)
 
     if rank == 0:
         cfg = workload_config(args, world)
@@ -829,6 +1138,10 @@ def main():
                 "data": "synthetic (device-generated box-room pointmaps, 1+Gamma(2,2) confidence, N(0,1) embeddings)",
                 "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "step_ms": [round(x, 3) for x in step_ms], "step_fuse_ms": step_fuse_ms, "retries_in_timed_region": counters, "secondary": secondary}
+        if parity is not None:
+            line["dist_parity"] = parity
+        if cpu is not None and "cuda_library_baseline" in cpu:
+            line["cuda_library_baseline"] = cpu.pop("cuda_library_baseline")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

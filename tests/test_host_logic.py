@@ -131,6 +131,9 @@ def test_bench_reference_arm_runs_on_cpu():
     par = j["cpu_baseline"]["parallel"]              # independent copies of the port, one per core (an extra figure)
     assert par["procs"] >= 1 and par["value"] > 0 and par["unit"] == "points/s"
     assert j["e2e"] == {"value": j["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the record says what actually ran: one submap of `frames` frames per step, not the GPU arm's workload
+    assert j["config"]["frames"] == 2 and j["config"]["submaps_per_gpu"] == 1 and j["config"]["same_config_as_gpu_arm"] is False
+    assert "1 submap x 2 frames" in j["config"]["workload"] and "1 submap x 2 frames" in j["cpu_baseline"]["sample"]
 
 
 def test_clock_sampler_without_nvml_reports_instead_of_failing():
