@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--e2e-submaps", type=int, default=6, help="submaps per GPU of the e2e arm (same at every N); -1: all")
     ap.add_argument("--round-submaps", type=int, default=5, help="N>1: submaps per exchange round (0: one exchange at the end)")
     ap.add_argument("--traj-submaps", type=int, default=200, help="submaps of the long-trajectory block (configs[2]); 0: skip")
+    ap.add_argument("--traj-room", default="8,6,3", help="room size (m) of the long-trajectory corridor, one room per submap")
     ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per step (0: the largest of 4/8/16/32 that fits the time budget)")
     ap.add_argument("--no-dist-parity", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of one submap in the CPU sample")
@@ -728,15 +729,11 @@ def long_trajectory(args, dev, rank, world):
     vs, S, H, W, d = 0.02, args.frames, args.height, args.width, args.dim
     emb_dtype = torch.bfloat16 if args.emb_dtype == "bf16" else torch.float32
     total = args.traj_submaps
-    per_voxel_bytes = 4 * d + 64
-    free = torch.cuda.mem_get_info(dev)[0]
+    room = tuple(float(x) for x in args.traj_room.split(","))
+    per_voxel_bytes = 4 * d + 96  # sums + key, count, hash slots at load 0.5, rank maps, norms
     per_rank = (total + world - 1) // world
-    if world == 1:
-        # everything lands in one map: what fits beside the inputs (2 KB per voxel, ~0.27 M voxels per submap)
-        fit = int((0.80 * free - 2 * S * H * W * d * 2) / (0.27e6 * per_voxel_bytes + S * H * W * 16))
-        per_rank = max(4, min(per_rank, fit))
     first = rank * per_rank
-    mine = list(range(first, min(first + per_rank, total if world > 1 else first + per_rank)))
+    K = max(args.round_submaps, 1)
     pool = []
     for k in range(2):
         e = torch.empty((S, H, W, d), dtype=emb_dtype, device=dev)
@@ -746,12 +743,12 @@ def long_trajectory(args, dev, rank, world):
             e[f] = torch.randn((H, W, d), dtype=torch.float32, device=dev, generator=g).to(torch.bfloat16).to(emb_dtype)
         pool.append(e)
     gm = vsm.GraphMap()
-    for j, i in enumerate(mine):
-        dd = synth_device.make_trajectory_submap_device(4321, i, S=S, H=H, W=W, d=d, emb_dtype=emb_dtype, device=dev,
-                                                        with_emb=False, emb_from=pool[j % len(pool)])
-        gm.add_submap(synth_device.to_submap(dd))
-    torch.cuda.synchronize()
-    K = max(args.round_submaps, 1)
+
+    def add(ids):
+        for i in ids:
+            dd = synth_device.make_trajectory_submap_device(4321, i, S=S, H=H, W=W, d=d, room=room, emb_dtype=emb_dtype, device=dev,
+                                                            with_emb=False, emb_from=pool[i % len(pool)])
+            gm.add_submap(synth_device.to_submap(dd))
 
     def build(sub_gm, cap_round=None, cap_owner=None, timings=None):
         if world > 1:
@@ -761,21 +758,28 @@ def long_trajectory(args, dev, rank, world):
         return m, sub_gm.last_build_stats
 
     # warm-up on the first 2 rounds' worth of submaps: warms the pools and measures voxels per submap
-    warm = vsm.GraphMap()
-    for sm in list(gm.ordered_submaps_by_key())[:min(2 * K, len(mine))]:
-        warm.add_submap(sm)
-    m0, st0 = build(warm)
+    n_warm = min(2 * K, per_rank, max(total - first, 0)) if world > 1 else min(2 * K, per_rank)
+    add(range(first, first + n_warm))
+    m0, st0 = build(gm)
     vox_per_submap = max(s["n_submap_voxels"] for s in st0)
-    new_per_submap = m0._dm.num_voxels if world == 1 else None
-    n_warm = len(st0)
+    new_per_submap = m0._dm.num_voxels / max(n_warm, 1)  # voxels the map gains per submap (neighbours share a wall)
     del m0
     N.lib.vsm_map_cache_release()
     torch.cuda.empty_cache()
+    if world == 1:
+        # everything lands in ONE map: as many submaps as fit beside their inputs
+        free = torch.cuda.mem_get_info(dev)[0]
+        fit = int(0.85 * free / (1.30 * new_per_submap * per_voxel_bytes + vox_per_submap * 32 + S * H * W * 20))
+        per_rank = max(n_warm, min(per_rank, fit))
+    mine = list(range(first, min(first + per_rank, total if world > 1 else first + per_rank)))
+    add(mine[n_warm:])
+    torch.cuda.synchronize()
     cap_round = int(1.15 * vox_per_submap * K) + (1 << 16)
     if world == 1:
-        cap_owner = int(1.08 * new_per_submap / n_warm * len(mine)) + (1 << 18)
+        cap_owner = int(1.30 * new_per_submap * len(mine)) + (1 << 18)
     else:
-        cap_owner = int(1.25 * vox_per_submap * len(mine)) + (1 << 18)  # hash ownership spreads the voxels evenly
+        # hash ownership spreads the voxels evenly: every owner ends with ~ the voxels its own submaps bring
+        cap_owner = int(1.20 * new_per_submap * len(mine)) + (1 << 18)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -783,7 +787,11 @@ def long_trajectory(args, dev, rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    m, st = build(gm, cap_round, cap_owner, timings)
+    try:
+        m, st = build(gm, cap_round, cap_owner, timings)
+    except Exception as e:
+        raise RuntimeError(f"{e!r}; submaps={len(mine)} new_voxels_per_submap={new_per_submap:.0f} "
+                           f"voxels_per_submap={vox_per_submap} owner_capacity={cap_owner} round_capacity={cap_round}") from e
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -791,7 +799,7 @@ def long_trajectory(args, dev, rank, world):
     n_fused = float(sum(s["n_fused"] for s in st))
     t = torch.tensor([ms, 1e3 * wall, n_fused, float(m._dm.num_voxels), float(len(mine))], dtype=torch.float64, device=dev)
     out = {"workload": f"long-trajectory synthetic: {S} frames x {W}x{H} per submap, {d}-d {args.emb_dtype} embeddings, 2 cm voxels, "
-                       f"SL(4), outlier filters on; corridor of 8x6x3 m rooms, one per submap",
+                       f"SL(4), outlier filters on; corridor of {args.traj_room} m rooms, one per submap",
            "scaling": "strong (the submaps are divided over the ranks)" if world > 1 else "single GPU",
            "round_submaps": K if world > 1 else None}
     if world > 1:
@@ -812,11 +820,12 @@ def long_trajectory(args, dev, rank, world):
                     "exchange_bytes_total": int(sent.item()), "exchange_rounds": timings.get("rounds"),
                     "exchange_GB_per_gpu": float(sent.item()) / world * 1e-9,
                     "invariants": inv, "phases_ms_rank0": timings.get("phases_ms")})
-    else:
+    out.update({"voxels_per_submap": int(vox_per_submap), "new_voxels_per_submap": int(new_per_submap), "owner_capacity": int(cap_owner)})
+    if world == 1:
         out.update({"submaps": len(mine), "submaps_per_gpu": len(mine), "ms": ms, "wall_ms": 1e3 * wall,
                     "points_fused": int(n_fused), "points_per_s": n_fused / (ms * 1e-3), "voxels": int(m._dm.num_voxels),
                     "note": None if len(mine) == total else f"{len(mine)} of {total} submaps: what one GPU's memory holds as ONE map"})
-    del m, gm, warm, pool
+    del m, gm, pool
     N.lib.vsm_map_cache_release()
     torch.cuda.empty_cache()
     return out

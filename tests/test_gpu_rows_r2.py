@@ -319,3 +319,87 @@ def test_frame_stream_equals_whole_submap():
         ua = np.bitwise_or.reduce(ma[oa[v]:oa[v + 1]], axis=0)
         ub = np.bitwise_or.reduce(mb[ob[v]:ob[v + 1]], axis=0)
         assert (ua == ub).all()
+
+
+# ---------------------------------------------------------------------------
+# f4: binary side-car persistence (semantic_voxel.py:128-165 at sizes the pickled lists cannot reach)
+# ---------------------------------------------------------------------------
+def _same_map(a, b, q):
+    np.testing.assert_array_equal(a.get_centers_world(), b.get_centers_world())
+    np.testing.assert_array_equal(a.get_features(), b.get_features())  # fp32 means written and read back: bit-equal
+    np.testing.assert_array_equal(a._voxel_coords, b._voxel_coords)
+    assert a.frame_name_maps == b.frame_name_maps
+    V = a.get_centers_world().shape[0]
+    for v in list(range(0, V, max(1, V // 97))) + [V - 1]:
+        # get_latest_frame_at_voxel sorts a voxel's list in place (reference quirk A-6): compare as sorted lists
+        assert sorted(map(tuple, a.voxels.contributors[v])) == sorted(map(tuple, b.voxels.contributors[v]))
+        assert a.get_latest_frame_at_voxel(v) == b.get_latest_frame_at_voxel(v)
+    assert a.query_with_embedding(q, top_k=7)[0] == b.query_with_embedding(q, top_k=7)[0]
+
+
+@pytest.mark.parametrize("chunk_rows", [1 << 18, 257])
+def test_sidecar_round_trip_device_built(tmp_path, chunk_rows):
+    """A device-built map (contributor CSR of frame masks) -> side-car -> load: same centres, features, reconstructed
+    coordinates, contributor lists, latest frames and query answers; the reference's npz next to it still loads."""
+    import vsm
+    from test_gpu_parity import graph_from
+
+    z = gio.load("case_c_global_sl4.npz")
+    m = graph_from(vsm, gio.inputs(z)).build_semantic_voxel_map(0.05)
+    out = tmp_path / "both"
+    m.save_to_directory(str(out), sidecar=True, npz=True, chunk_rows=chunk_rows)
+    side = out / "sidecar"
+    meta = json.loads((side / "meta.json").read_text())
+    V = m.get_centers_world().shape[0]
+    assert meta["contributors"] == "masks" and meta["num_voxels"] == V and meta["dim"] == m.get_features().shape[1]
+    assert np.load(side / "features.npy", mmap_mode="r").shape == (V, meta["dim"])
+    assert np.load(side / "contrib_offsets.npy").shape == (V + 1,)
+    q = z["q"][0]
+    a = vsm.SemanticVoxelMap.load_from_directory(str(out))  # prefers the side-car
+    assert getattr(a.voxels.contributors, "__class__").__name__ == "LazyContributors"
+    _same_map(a, m, q)
+    b = vsm.SemanticVoxelMap.load_from_directory(str(out), prefer_sidecar=False)  # the reference's file
+    np.testing.assert_array_equal(b.get_centers_world(), m.get_centers_world())
+    assert b.query_with_embedding(q, top_k=7)[0] == m.query_with_embedding(q, top_k=7)[0]
+    # side-car only (what a map beyond NPZ_MAX_VOXELS writes by default)
+    only = tmp_path / "only"
+    m.save_to_directory(str(only), sidecar=True, npz=False)
+    assert not (only / "semantic_voxels.npz").exists()
+    _same_map(vsm.SemanticVoxelMap.load_from_directory(str(only)), m, q)
+
+
+def test_sidecar_round_trip_of_a_loaded_map(tmp_path):
+    """A map loaded from the reference's own bytes (contributors are Python lists: the 'pairs' form) -> side-car -> load."""
+    import vsm
+
+    z = gio.load("case_c_global_sl4.npz")
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    (ref_dir / "semantic_voxels.npz").write_bytes(z["saved_npz_bytes"].tobytes())
+    (ref_dir / "frame_names.json").write_text(str(z["saved_json"]))
+    lm = vsm.SemanticVoxelMap.load_from_directory(str(ref_dir))
+    out = tmp_path / "side"
+    lm.save_to_directory(str(out), sidecar=True, npz=False)
+    assert json.loads((out / "sidecar" / "meta.json").read_text())["contributors"] == "pairs"
+    _same_map(vsm.SemanticVoxelMap.load_from_directory(str(out)), lm, z["q"][0])
+
+
+def test_sidecar_defaults_by_size(tmp_path):
+    import vsm
+
+    z = gio.load("case_c_global_sl4.npz")
+    from test_gpu_parity import graph_from
+
+    m = graph_from(vsm, gio.inputs(z)).build_semantic_voxel_map(0.05)
+    small = tmp_path / "small"
+    m.save_to_directory(str(small))  # a small map: the reference's files only
+    assert (small / "semantic_voxels.npz").exists() and not (small / "sidecar").exists()
+    old = vsm.SemanticVoxelMap.NPZ_MAX_VOXELS
+    vsm.SemanticVoxelMap.NPZ_MAX_VOXELS = 10
+    try:
+        big = tmp_path / "big"
+        m.save_to_directory(str(big))
+        assert (big / "sidecar" / "meta.json").exists() and not (big / "semantic_voxels.npz").exists()
+        assert (big / "frame_names.json").exists()
+    finally:
+        vsm.SemanticVoxelMap.NPZ_MAX_VOXELS = old

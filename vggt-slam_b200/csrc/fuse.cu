@@ -26,6 +26,8 @@
 #include <algorithm>
 #include <atomic>
 
+#include <cuda.h>
+
 #include "bracket.cuh"
 #include "hash.cuh"
 
@@ -40,6 +42,7 @@ std::atomic<int> g_range_policy{0};             // "coord_range_policy": 0 = fai
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
 std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
+std::atomic<int> g_acc_ctas_per_sm{2};          // resident CTAs per SM of the voxel-sorted accumulate kernel ("acc_ctas_per_sm")
 
 constexpr uint32_t PF_SEL = 1u;     // conf >= thr, on the stride grid, frame < end_idx
 constexpr uint32_t PF_FINITE = 2u;  // world point (and embedding row, if a mask was given) finite
@@ -987,11 +990,12 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
 }
 
 template <bool BF16, int VPL>
-static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s) {
+static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s, int n_sm) {
   const int block = 256;
   // The sorted list's length lives on the device: a fixed grid of resident CTAs strides over the chunks.  Two CTAs
   // per SM (16 warps x 4 rows of 1 KB in flight) already saturate HBM (measured: same time as 3 or 6 per SM).
-  int grid = sm_count() * 2;
+  // n_sm: the SMs the stream may use (an SM partition), 0 = all.
+  int grid = (n_sm > 0 ? n_sm : sm_count()) * std::max(1, std::min(8, g_acc_ctas_per_sm.load()));
   if (!sorted) {
     const int64_t n_chunks = (a.n + 31) >> 5;
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)sm_count() * 6);
@@ -1028,19 +1032,19 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
   return VSM_OK;
 }
 
-int launch_accumulate(const AccArgs& a, bool bf16, bool sorted, bool check, cudaStream_t s) {
+int launch_accumulate(const AccArgs& a, bool bf16, bool sorted, bool check, cudaStream_t s, int n_sm = 0) {
   if (!sorted && a.n <= 0) return VSM_OK;
   const int vpl = (a.nvec + 31) / 32;
   if (bf16) {
-    if (vpl <= 1) return launch_accumulate_t<true, 1>(a, sorted, check, s);
-    if (vpl <= 2) return launch_accumulate_t<true, 2>(a, sorted, check, s);
-    if (vpl <= 4) return launch_accumulate_t<true, 4>(a, sorted, check, s);
-    if (vpl <= 8) return launch_accumulate_t<true, 8>(a, sorted, check, s);
+    if (vpl <= 1) return launch_accumulate_t<true, 1>(a, sorted, check, s, n_sm);
+    if (vpl <= 2) return launch_accumulate_t<true, 2>(a, sorted, check, s, n_sm);
+    if (vpl <= 4) return launch_accumulate_t<true, 4>(a, sorted, check, s, n_sm);
+    if (vpl <= 8) return launch_accumulate_t<true, 8>(a, sorted, check, s, n_sm);
   } else {
-    if (vpl <= 1) return launch_accumulate_t<false, 1>(a, sorted, check, s);
-    if (vpl <= 2) return launch_accumulate_t<false, 2>(a, sorted, check, s);
-    if (vpl <= 4) return launch_accumulate_t<false, 4>(a, sorted, check, s);
-    if (vpl <= 8) return launch_accumulate_t<false, 8>(a, sorted, check, s);
+    if (vpl <= 1) return launch_accumulate_t<false, 1>(a, sorted, check, s, n_sm);
+    if (vpl <= 2) return launch_accumulate_t<false, 2>(a, sorted, check, s, n_sm);
+    if (vpl <= 4) return launch_accumulate_t<false, 4>(a, sorted, check, s, n_sm);
+    if (vpl <= 8) return launch_accumulate_t<false, 8>(a, sorted, check, s, n_sm);
   }
   set_error("embedding dimension %d too large (max %d)", a.d, bf16 ? 2048 : 1024);
   return VSM_E_INVALID;
@@ -1244,6 +1248,104 @@ static int ensure_acc_stream(Workspace* ws) {
   return VSM_OK;
 }
 
+// ---- SM partitions (CUDA green contexts; driver entry points looked up at run time: libvsm does not link libcuda) ----
+template <class F>
+static bool driver_fn(const char* name, F* out) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qr) != cudaSuccess || !p || qr != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    set_error("green contexts: %s is not available from this driver", name);
+    return false;
+  }
+  *out = reinterpret_cast<F>(p);
+  return true;
+}
+
+static void green_teardown(Workspace* ws) {
+  CUresult (*ctx_destroy)(CUgreenCtx) = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    if (ws->green_stream[i]) cudaStreamDestroy(ws->green_stream[i]);
+    ws->green_stream[i] = nullptr;
+  }
+  if ((ws->green_ctx[0] || ws->green_ctx[1]) && driver_fn("cuGreenCtxDestroy", &ctx_destroy))
+    for (int i = 0; i < 2; ++i)
+      if (ws->green_ctx[i]) ctx_destroy(reinterpret_cast<CUgreenCtx>(ws->green_ctx[i]));
+  ws->green_ctx[0] = ws->green_ctx[1] = nullptr;
+  ws->green_sms[0] = ws->green_sms[1] = 0;
+  ws->green_on = false;
+}
+
+// Splits the device's SMs into a preparation partition of >= prep_sms SMs (rounded up to the hardware's granularity,
+// 8 on sm_100) and an accumulate partition of the rest; one stream in each.  Needs the workspace lock and an idle device.
+static int green_setup(Workspace* ws, int dev, int prep_sms) {
+  green_teardown(ws);
+  if (prep_sms <= 0) return VSM_OK;
+  CUresult (*dev_get)(CUdevice*, int) = nullptr;
+  CUresult (*get_res)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*gen_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*ctx_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  if (!driver_fn("cuDeviceGet", &dev_get) || !driver_fn("cuDeviceGetDevResource", &get_res) ||
+      !driver_fn("cuDevSmResourceSplitByCount", &split) || !driver_fn("cuDevResourceGenerateDesc", &gen_desc) ||
+      !driver_fn("cuGreenCtxCreate", &ctx_create) || !driver_fn("cuGreenCtxStreamCreate", &stream_create))
+    return VSM_E_CUDA;
+  CUdevice cu_dev;
+  CUdevResource all, part[2];
+  unsigned int groups = 1;
+  CUresult r = dev_get(&cu_dev, dev);
+  if (r == CUDA_SUCCESS) r = get_res(cu_dev, &all, CU_DEV_RESOURCE_TYPE_SM);
+  if (r == CUDA_SUCCESS) r = split(&part[0], &groups, &all, &part[1], 0u, (unsigned int)prep_sms);
+  if (r != CUDA_SUCCESS || groups != 1 || part[1].sm.smCount == 0) {
+    set_error("green contexts: cannot split %d SMs off the device (CUresult %d)", prep_sms, (int)r);
+    return VSM_E_INVALID;
+  }
+  for (int i = 0; i < 2; ++i) {
+    CUdevResourceDesc desc;
+    CUgreenCtx ctx = nullptr;
+    CUstream st = nullptr;
+    r = gen_desc(&desc, &part[i], 1);
+    if (r == CUDA_SUCCESS) r = ctx_create(&ctx, desc, cu_dev, CU_GREEN_CTX_DEFAULT_STREAM);
+    if (r == CUDA_SUCCESS) {
+      ws->green_ctx[i] = ctx;
+      r = stream_create(&st, ctx, CU_STREAM_NON_BLOCKING, 0);
+    }
+    if (r != CUDA_SUCCESS) {
+      set_error("green contexts: cannot create partition %d (CUresult %d)", i, (int)r);
+      green_teardown(ws);
+      return VSM_E_CUDA;
+    }
+    ws->green_stream[i] = reinterpret_cast<cudaStream_t>(st);
+    ws->green_sms[i] = (int)part[i].sm.smCount;
+  }
+  if (!ws->ev_fork) VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+  if (!ws->ev_prep_join) VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_prep_join, cudaEventDisableTiming));
+  ws->green_on = true;
+  return VSM_OK;
+}
+
+// moves a fuse call's preparation kernels from the caller's stream to the preparation partition and back
+struct PrepFork {
+  Workspace* ws;
+  cudaStream_t user;
+  bool on = false;
+  PrepFork(Workspace* w, cudaStream_t u) : ws(w), user(u) {}
+  int fork(cudaStream_t* s) {
+    VSM_CUDA(cudaEventRecord(ws->ev_fork, user));
+    VSM_CUDA(cudaStreamWaitEvent(ws->green_stream[0], ws->ev_fork, 0));
+    *s = ws->green_stream[0];
+    on = true;
+    return VSM_OK;
+  }
+  ~PrepFork() {
+    // every return path: the caller's stream continues behind the preparation kernels queued so far
+    if (on && (cudaEventRecord(ws->ev_prep_join, ws->green_stream[0]) != cudaSuccess ||
+               cudaStreamWaitEvent(user, ws->ev_prep_join, 0) != cudaSuccess))
+      cudaGetLastError();
+  }
+};
+
 int join_accumulates(Workspace* ws, cudaStream_t s) {
   for (int b = 0; b < 2; ++b)
     if (ws->acc_used[b]) VSM_CUDA(cudaStreamWaitEvent(s, ws->ev_acc_done[b], 0));
@@ -1301,6 +1403,22 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_TRY(ws->sorted_pix[ab].ensure((size_t)n_sel_max * 8, s));  // packed entries
   }
 
+  // SM partitions: from here on the call's preparation kernels go to the preparation partition's stream (the plain
+  // device-resident, voxel-sorted call only: the optional paths allocate per-call buffers on the stream they run on)
+  const int sel_mode = g_select_mode.load();
+  PrepFork prep_fork(ws, s);
+  const bool green = ws->overlap && ws->green_on && !pixel_order && !keep_index && sel_mode != 2 &&
+                     !(filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr);
+  if (green) {
+    if (filters) {  // the select scratch is allocated on first use: do that on the caller's stream
+      SelectState* st0 = nullptr;
+      uint32_t* h0 = nullptr;
+      float* o0 = nullptr;
+      VSM_TRY(select_scratch(&st0, &h0, &o0));
+    }
+    VSM_TRY(prep_fork.fork(&s));
+  }
+
   LocalTable tb = table_view(ws->tb_slots, ws->tb_list, ws->tb_cap, &ctr->n_occ_b);
   LocalTable ta{};
   if (filters) ta = table_view(ws->ta_slots, ws->ta_list, ws->ta_cap, &ctr->n_occ_a);
@@ -1329,7 +1447,6 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   // collect inside the world-point kernel, exact resolve; repeated with the radix select when it cannot answer) gives
   // the same bounds and is kept as an option: on B200 it measured 6 % SLOWER per fuse call (its collect step more
   // than doubles the instruction-bound world-point kernel), see DESIGN.md 5.
-  const int sel_mode = g_select_mode.load();
   const bool bracket = filters && !(p->flags & kFuseForceRadix) && sel_mode == 2;
   SelectState* sst = nullptr;
   uint32_t* hist = nullptr;
@@ -1480,13 +1597,13 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     aa.pix_base = 0;
     aa.entries = ws->sorted_pix[ab].as<unsigned long long>();
     // the accumulate kernel goes to the side stream: the caller's stream is free for the next call's preparation
-    cudaStream_t sa = ws->overlap ? ws->acc_stream : s;
+    cudaStream_t sa = green ? ws->green_stream[1] : (ws->overlap ? ws->acc_stream : s);
     if (ws->overlap) {
       VSM_CUDA(cudaEventRecord(ws->ev_prep_done[ab], s));
       VSM_CUDA(cudaStreamWaitEvent(sa, ws->ev_prep_done[ab], 0));
     }
     if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], sa));
-    VSM_TRY(launch_accumulate(aa, bf16, true, check, sa));
+    VSM_TRY(launch_accumulate(aa, bf16, true, check, sa, green ? ws->green_sms[1] : 0));
     if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], sa));
     if (ws->overlap) {
       VSM_CUDA(cudaEventRecord(ws->ev_acc_done[ab], sa));
@@ -1910,6 +2027,27 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
     g_range_policy = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_ctas_per_sm") && value >= 1 && value <= 8) {
+    g_acc_ctas_per_sm = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "green_prep_sms") && value >= 0 && value <= 1024) {
+    // value > 0: partition the SMs (>= value for the preparation kernels, the rest for the accumulate kernel) and turn
+    // the overlap on; 0: back to one stream on the whole device
+    int dev = 0;
+    VSM_CUDA(cudaGetDevice(&dev));
+    Workspace* ws = workspace_for_device(dev);
+    if (!ws) {
+      set_error("vsm_set_option: no workspace for device %d", dev);
+      return VSM_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(ws->mu);
+    VSM_TRY(ensure_acc_stream(ws));
+    VSM_CUDA(cudaDeviceSynchronize());
+    VSM_TRY(green_setup(ws, dev, (int)value));
+    ws->overlap = value != 0;
     return VSM_OK;
   }
   if (!strcmp(key, "overlap") && (value == 0 || value == 1)) {

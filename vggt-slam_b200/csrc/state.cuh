@@ -133,6 +133,15 @@ struct Workspace {
   // Off by default: measured on B200, the HBM-saturating accumulate kernel and the latency-bound preparation
   // kernels slow each other down by as much as the overlap hides.  VSM_OVERLAP=1 / vsm_set_option.
   bool overlap = false;
+  // SM partitions (CUDA green contexts, "green_prep_sms" option): with the overlap on, the preparation kernels of a call
+  // run on a stream confined to `green_sms[0]` SMs and the accumulate kernel on a stream confined to the other
+  // `green_sms[1]`, so that the HBM-bound accumulate of call i and the latency / issue-bound preparation of call
+  // i+1 run side by side without competing for registers and warp slots on the same SM.
+  bool green_on = false;
+  void* green_ctx[2] = {nullptr, nullptr};  // CUgreenCtx
+  cudaStream_t green_stream[2] = {nullptr, nullptr};  // [0] preparation, [1] accumulate
+  int green_sms[2] = {0, 0};
+  cudaEvent_t ev_fork = nullptr, ev_prep_join = nullptr;
 };
 Workspace* workspace_for_device(int device);
 

@@ -327,7 +327,11 @@ def wrap_device_map(dm, fused, frame_name_maps, voxel_size, deduplicate_contribu
     else:
         contributors = _per_point_contributors_global(dm, fused, V)
     vox = SemanticVoxel.lazy(float(voxel_size), centers, dm.features_to_host, contributors)
-    return SemanticVoxelMap(vox, frame_name_maps=frame_name_maps, _device_map=dm, exact_coords=exact_coords)
+    m = SemanticVoxelMap(vox, frame_name_maps=frame_name_maps, _device_map=dm, exact_coords=exact_coords)
+    if deduplicate_contributors:
+        # the device's contributor CSR + the frame ids of every submap: what the binary side-car stores instead of V lists
+        m._contrib_csr = {"dm": dm, "frame_ids": {int(f["submap"].get_id()): list(f["submap"].frame_ids) for f in fused}}
+    return m
 
 
 def _empty_voxels(voxel_size) -> SemanticVoxel:

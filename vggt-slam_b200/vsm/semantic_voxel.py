@@ -11,6 +11,7 @@ Behaviour kept from the reference, on purpose:
 """
 from __future__ import annotations
 
+import ctypes as C
 import json
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -249,29 +250,169 @@ class SemanticVoxelMap:
         submap_id, frame_id = voxel_contributors[0]
         return self.resolve_contributor(submap_id, frame_id), submap_id, frame_id
 
-    # -- persistence (semantic_voxel.py:128-165): same files, loadable by the reference ----------
-    def save_to_directory(self, directory_path: str) -> None:
+    # -- persistence (semantic_voxel.py:128-165) ---------------------------------------------------
+    # Two layouts in one directory:
+    #   semantic_voxels.npz + frame_names.json   the reference's files, byte-compatible (its loader reads ours, ours reads
+    #                                            its): a pickled object array of V Python lists -- fine for small maps
+    #   sidecar/                                 plain .npy arrays, memory-mappable, written and read in row blocks
+    #                                            straight from / to the device: meta.json, centers_world.npy (V,3) f32,
+    #                                            features.npy (V,d) f32, contributors as a CSR -- contrib_offsets.npy
+    #                                            (V+1) i64 + either contrib_submap.npy (M) i32 / contrib_mask.npy (M,2)
+    #                                            u64 / frame_ids.json (device-built maps: one entry per submap and voxel,
+    #                                            bit f = frame f) or contrib_pair.npy (M) i32 / pairs.json (any list)
+    NPZ_MAX_VOXELS = 2_000_000
+    SIDECAR = "sidecar"
+
+    def save_to_directory(self, directory_path: str, sidecar: Optional[bool] = None, npz: Optional[bool] = None,
+                          chunk_rows: int = 1 << 18) -> None:
+        """``npz``: write the reference's file (default: when the map has at most NPZ_MAX_VOXELS voxels -- the pickled
+        contributor lists do not scale); ``sidecar``: write the binary side-car (default: when the npz is skipped, or
+        the map has more than 100 k voxels)."""
         os.makedirs(directory_path, exist_ok=True)
-        contribs = self.voxels.contributors
-        contribs = contribs.tolist() if isinstance(contribs, LazyContributors) else contribs
-        np.savez_compressed(
-            os.path.join(directory_path, "semantic_voxels.npz"),
-            voxel_size=np.float32(self.voxel_size),
-            centers_world=np.asarray(self.voxels.centers_world).astype(np.float32),
-            features=np.asarray(self.voxels.features).astype(np.float32),
-            contributors=np.array(contribs, dtype=object),
-        )
+        V = len(self.voxels.contributors) if self.voxels.contributors is not None else 0
+        npz = (V <= self.NPZ_MAX_VOXELS) if npz is None else bool(npz)
+        sidecar = ((not npz) or V > 100_000) if sidecar is None else bool(sidecar)
+        if npz:
+            contribs = self.voxels.contributors
+            contribs = contribs.tolist() if isinstance(contribs, LazyContributors) else contribs
+            np.savez_compressed(
+                os.path.join(directory_path, "semantic_voxels.npz"),
+                voxel_size=np.float32(self.voxel_size),
+                centers_world=np.asarray(self.voxels.centers_world).astype(np.float32),
+                features=np.asarray(self.voxels.features).astype(np.float32),
+                contributors=np.array(contribs, dtype=object),
+            )
         with open(os.path.join(directory_path, "frame_names.json"), "w") as f:
             json.dump(self.frame_name_maps, f, indent=2)
+        if sidecar:
+            self._save_sidecar(os.path.join(directory_path, self.SIDECAR), chunk_rows)
+
+    def _save_sidecar(self, path: str, chunk_rows: int) -> None:
+        import torch
+        from numpy.lib.format import write_array_header_1_0
+
+        os.makedirs(path, exist_ok=True)
+        dm = self._dm
+        V = 0 if dm is None else dm.num_voxels
+        d = 0 if dm is None else dm.dim
+        np.save(os.path.join(path, "centers_world.npy"), np.asarray(self.voxels.centers_world, dtype=np.float32).reshape(V, 3))
+        # features.npy: header, then the rows block by block through two pinned buffers (the device->host copy of
+        # block i+1 runs while block i is written): the (V,d) matrix is never resident twice, on the device or on the host
+        with open(os.path.join(path, "features.npy"), "wb") as fp:
+            write_array_header_1_0(fp, {"descr": "<f4", "fortran_order": False, "shape": (int(V), int(d))})
+            if V:
+                n_blk = min(chunk_rows, V)
+                stage = [torch.empty((n_blk, d), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+                buf = [torch.empty((n_blk, d), dtype=torch.float32, device=dm.device) for _ in range(2)]
+                done = [torch.cuda.Event(), torch.cuda.Event()]
+                stream = torch.cuda.current_stream(dm.device)
+                blocks = [(r0, min(V, r0 + chunk_rows)) for r0 in range(0, V, chunk_rows)]
+
+                def issue(i):
+                    r0, r1 = blocks[i]
+                    dm.export_features(r0, r1, buf[i & 1][: r1 - r0])
+                    stage[i & 1][: r1 - r0].copy_(buf[i & 1][: r1 - r0], non_blocking=True)
+                    done[i & 1].record(stream)
+
+                issue(0)
+                for i, (r0, r1) in enumerate(blocks):
+                    if i + 1 < len(blocks):
+                        issue(i + 1)
+                    done[i & 1].synchronize()
+                    fp.write(memoryview(stage[i & 1][: r1 - r0].numpy()).cast("B"))
+        meta = {"version": 1, "voxel_size": float(self.voxel_size), "dim": int(d), "num_voxels": int(V)}
+        src = getattr(self, "_contrib_csr", None)
+        if src is not None:
+            off, sub, mask = src["dm"].export_contributors()
+            np.save(os.path.join(path, "contrib_offsets.npy"), off.astype(np.int64))
+            np.save(os.path.join(path, "contrib_submap.npy"), sub.astype(np.int32))
+            np.save(os.path.join(path, "contrib_mask.npy"), mask.astype(np.uint64))
+            with open(os.path.join(path, "frame_ids.json"), "w") as f:
+                json.dump({str(k): [str(x) for x in v] for k, v in src["frame_ids"].items()}, f)
+            meta["contributors"] = "masks"
+        else:
+            contribs = self.voxels.contributors
+            pairs, index, off, flat = [], {}, np.zeros(V + 1, dtype=np.int64), []
+            for i in range(V):
+                for sid, fid in contribs[i]:
+                    key = (int(sid), str(fid))
+                    j = index.get(key)
+                    if j is None:
+                        j = index[key] = len(pairs)
+                        pairs.append([key[0], key[1]])
+                    flat.append(j)
+                off[i + 1] = len(flat)
+            np.save(os.path.join(path, "contrib_offsets.npy"), off)
+            np.save(os.path.join(path, "contrib_pair.npy"), np.asarray(flat, dtype=np.int32))
+            with open(os.path.join(path, "pairs.json"), "w") as f:
+                json.dump(pairs, f)
+            meta["contributors"] = "pairs"
+        with open(os.path.join(path, "meta.json"), "w") as f:  # written last: its presence marks a complete side-car
+            json.dump(meta, f)
+
+    @classmethod
+    def _load_sidecar(cls, path: str, frame_name_maps, chunk_rows: int = 1 << 18) -> "SemanticVoxelMap":
+        import torch
+
+        with open(os.path.join(path, "meta.json")) as f:
+            meta = json.load(f)
+        V, d, vs = int(meta["num_voxels"]), int(meta["dim"]), float(meta["voxel_size"])
+        centers = np.load(os.path.join(path, "centers_world.npy"), mmap_mode="r")
+        feats = np.load(os.path.join(path, "features.npy"), mmap_mode="r")
+        off = np.load(os.path.join(path, "contrib_offsets.npy"), mmap_mode="r")
+        if meta.get("contributors") == "masks":
+            sub = np.load(os.path.join(path, "contrib_submap.npy"), mmap_mode="r")
+            mask = np.load(os.path.join(path, "contrib_mask.npy"), mmap_mode="r")
+            with open(os.path.join(path, "frame_ids.json")) as f:
+                frame_ids = {int(k): v for k, v in json.load(f).items()}
+
+            def maker(i):
+                out = set()
+                for e in range(int(off[i]), int(off[i + 1])):
+                    sid = int(sub[e])
+                    ids = frame_ids[sid]
+                    for w in range(2):
+                        bits = int(mask[e, w])
+                        while bits:
+                            b = (bits & -bits).bit_length() - 1
+                            out.add((sid, str(ids[64 * w + b])))
+                            bits &= bits - 1
+                return sorted(out)
+        else:
+            pair = np.load(os.path.join(path, "contrib_pair.npy"), mmap_mode="r")
+            with open(os.path.join(path, "pairs.json")) as f:
+                pairs = [(int(a), str(b)) for a, b in json.load(f)]
+
+            def maker(i):
+                return [pairs[int(j)] for j in pair[int(off[i]):int(off[i + 1])]]
+
+        dm = None
+        if V:
+            require_cuda()
+            dm = DeviceVoxelMap(vs, d, N.F32, capacity=max(V, 1024))
+            N.check(N.lib.vsm_map_load_begin(dm._h, V, C.c_void_p(torch.cuda.current_stream(dm.device).cuda_stream)))
+            for r0 in range(0, V, chunk_rows):
+                r1 = min(V, r0 + chunk_rows)
+                c = torch.from_numpy(np.ascontiguousarray(centers[r0:r1], dtype=np.float32)).to(dm.device)
+                f = torch.from_numpy(np.ascontiguousarray(feats[r0:r1], dtype=np.float32)).to(dm.device)
+                N.check(N.lib.vsm_map_load_rows(dm._h, r0, r1 - r0, C.c_void_p(c.data_ptr()), C.c_void_p(f.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(dm.device).cuda_stream)))
+                torch.cuda.current_stream(dm.device).synchronize()
+            dm.finalize()
+        vox = SemanticVoxel.lazy(vs, lambda: np.asarray(centers), lambda: np.asarray(feats), LazyContributors(V, maker))
+        return cls(vox, frame_name_maps=frame_name_maps, _device_map=dm)
 
     @staticmethod
-    def load_from_directory(directory_path: str) -> "SemanticVoxelMap":
-        data = np.load(os.path.join(directory_path, "semantic_voxels.npz"), allow_pickle=True)
+    def load_from_directory(directory_path: str, prefer_sidecar: bool = True) -> "SemanticVoxelMap":
         json_path = os.path.join(directory_path, "frame_names.json")
         frame_name_maps: Dict[str, Dict[str, str]] = {}
         if os.path.exists(json_path):
             with open(json_path, "r") as f:
                 frame_name_maps = json.load(f)
+        side = os.path.join(directory_path, SemanticVoxelMap.SIDECAR)
+        if prefer_sidecar and os.path.exists(os.path.join(side, "meta.json")):
+            return SemanticVoxelMap._load_sidecar(side, frame_name_maps)
+        data = np.load(os.path.join(directory_path, "semantic_voxels.npz"), allow_pickle=True)
         vox = SemanticVoxel(
             voxel_size=float(data["voxel_size"]),
             centers_world=data["centers_world"],

@@ -104,13 +104,15 @@ def make_trajectory_submap_device(seed: int, submap_id: int, S: int = 32, H: int
                                    room=(8.0, 6.0, 3.0), step: float = 0.2, noise: float = 0.005,
                                    emb_dtype: torch.dtype = torch.bfloat16,
                                    device: Optional[torch.device] = None, with_emb: bool = True,
-                                   emb_from: Optional[torch.Tensor] = None) -> DeviceSubmapData:
+                                   emb_from: Optional[torch.Tensor] = None, projective: float = 1e-5) -> DeviceSubmapData:
     """Submap `submap_id` of the LONG-TRAJECTORY workload (BASELINE configs[2]): a corridor of rooms chained
     along x, one room per submap (room i spans x in [i*Lx, (i+1)*Lx]); neighbouring rooms share a wall plane, so
     consecutive submaps overlap there and the voxel count of the map grows linearly with the number of submaps.
     Everything is a function of (seed, submap_id) only: any rank can regenerate any submap, nothing depends on how the
     submaps are sharded.  ``emb_from``: reuse an existing embedding tensor (the benchmark keeps a small pool of 5 GB
-    embedding arrays instead of one per submap: the values do not influence which voxels a point falls into)."""
+    embedding arrays instead of one per submap: the values do not influence which voxels a point falls into).
+    ``projective``: scale of the common SL(4) frame's last row -- small, so that w stays within a few percent of 1 along a
+    corridor of 200 rooms (1.6 km); the box-room default 2e-3 would put w = 0 inside the corridor."""
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     gen = torch.Generator(device=device)
     gen.manual_seed(seed * 1000003 + 7919 * submap_id + 17)
@@ -126,7 +128,7 @@ def make_trajectory_submap_device(seed: int, submap_id: int, S: int = 32, H: int
     T = np.eye(4)
     T[0, 3] = float(room[0]) * submap_id  # the room's place in the corridor
     rng = np.random.default_rng([seed, submap_id, 3])
-    G = synth.random_sl4(np.random.default_rng([seed, 987654321]))
+    G = synth.random_sl4(np.random.default_rng([seed, 987654321]), projective=projective)
     Hm = G @ T @ M_room_local
     Hm = Hm @ (np.eye(4) + 1e-4 * rng.normal(size=(4, 4)))
     Hm = Hm / abs(np.linalg.det(Hm)) ** 0.25
