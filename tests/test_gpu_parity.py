@@ -336,11 +336,21 @@ def test_build_orders_agree(vsm_mod):
     thr = vm.conf_threshold(s.conf, 25.0)
     pts, conf, emb = (torch.from_numpy(x).cuda() for x in (s.points, s.conf, s.emb))
     outs = []
-    for mode in ("sorted", "pixel", "host"):
+    # "host": pageable numpy arrays, staged frame by frame; "host_pinned": pinned memory, which the accumulate kernel
+    # reads in place over PCIe (only the rows of selected pixels); "host_pinned_staged": the same with the option off
+    pinned = torch.from_numpy(s.emb).pin_memory()
+    for mode in ("sorted", "pixel", "host", "host_pinned", "host_pinned_staged"):
         dm = vm.DeviceVoxelMap(0.05, 128, N.F32)
         flags = N.FUSE_FILTERS | (N.FUSE_PIXEL_ORDER if mode == "pixel" else 0)
         p = dm.make_params(4, 56, 84, 4, 1, thr, s.H_world_map, 0, flags)
-        st = dm.fuse_host(s.points, s.conf, s.emb, p) if mode == "host" else dm.fuse(pts, conf, emb, p)
+        if mode.startswith("host"):
+            N.set_option("host_zero_copy", 0 if mode.endswith("staged") else 1)
+            try:
+                st = dm.fuse_host(s.points, s.conf, s.emb if mode == "host" else pinned.numpy(), p)
+            finally:
+                N.set_option("host_zero_copy", 1)
+        else:
+            st = dm.fuse(pts, conf, emb, p)
         dm.finalize()
         coords, _, counts, _ = dm.export_geometry()
         outs.append((coords.cpu().numpy(), counts.cpu().numpy(), dm.features_to_host(), st["n_fused"]))

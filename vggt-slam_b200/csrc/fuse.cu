@@ -42,6 +42,7 @@ std::atomic<int> g_range_policy{0};             // "coord_range_policy": 0 = fai
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
 std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
+std::atomic<int> g_host_zero_copy{1};            // "host_zero_copy": pinned host embeddings are read in place by the accumulate kernel
 std::atomic<int> g_acc_ctas_per_sm{2};          // resident CTAs per SM of the voxel-sorted accumulate kernel ("acc_ctas_per_sm")
 
 constexpr uint32_t PF_SEL = 1u;     // conf >= thr, on the stride grid, frame < end_idx
@@ -1213,6 +1214,9 @@ static int validate_params(const vsm_map* m, const vsm_fuse_params* p) {
 // two halves so that a whole build runs without the host ever waiting on the device between submaps.
 struct HostEmb {
   const uint8_t* emb_host = nullptr;  // (S,H,W,d) rows on the host, map dtype
+  // device-side address of the same rows when they live in pinned (mapped) host memory: the accumulate kernel then
+  // reads the rows it needs straight over PCIe -- rows of pixels that were not selected never cross the bus
+  const uint8_t* emb_mapped = nullptr;
 };
 
 static int ensure_stream_objects(vsm_map* m, size_t chunk_bytes) {
@@ -1624,6 +1628,12 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
       if (call.profiled) VSM_CUDA(cudaEventRecord(ev[1], s));
       VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
       if (call.profiled) VSM_CUDA(cudaEventRecord(ev[2], s));
+    } else if (host->emb_mapped != nullptr) {
+      // zero-copy: one accumulate over all pixels, rows fetched from mapped host memory by the kernel itself
+      aa.emb = host->emb_mapped;
+      aa.pix_base = 0;
+      aa.n = n_px;
+      VSM_TRY(launch_accumulate(aa, bf16, false, check, s));
     } else {
       // stream the embeddings frame by frame through two device buffers
       const size_t chunk_bytes = (size_t)px_per_frame * row_bytes;
@@ -1919,6 +1929,13 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
   }
   HostEmb he;
   he.emb_host = (const uint8_t*)emb_host;
+  if (g_host_zero_copy.load()) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, emb_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+      he.emb_mapped = (const uint8_t*)at.devicePointer;
+    else
+      cudaGetLastError();  // pageable memory: staged copies
+  }
   vsm_fuse_params q = *p;
   q.flags &= ~VSM_FUSE_EMB_PRECHECK;  // not available when streaming from the host
   // a call the device aborts for lack of room is repeated by the collect with device-resident inputs only, which
@@ -2027,6 +2044,10 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
     g_range_policy = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "host_zero_copy") && (value == 0 || value == 1)) {
+    g_host_zero_copy = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "acc_ctas_per_sm") && value >= 1 && value <= 8) {

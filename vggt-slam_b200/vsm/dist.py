@@ -382,6 +382,7 @@ def build_sharded_streaming(graph_map, voxel_size: float, round_submaps: int, st
     stats_all, fused_all, names = [], [], {}
     prof = None
     pushed_rows = pushed_contrib = 0
+    round_ev = [] if (timings is not None and timings.get("per_round")) else None  # exchange-stream events per round
     for r in range(n_rounds):
         chunk = todo[r * round_submaps:(r + 1) * round_submaps]
         b = r & 1
@@ -417,11 +418,21 @@ def build_sharded_streaming(graph_map, voxel_size: float, round_submaps: int, st
             torch.cuda.synchronize(dev)  # the owner's allocation (zeroed rows) is complete before any stream uses it
         with torch.cuda.stream(xs):
             xs.wait_event(ev)
+            if round_ev is not None:
+                marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                round_ev.append(marks)
+                marks[0].record(xs)
             ex.push(L)
+            if round_ev is not None:
+                marks[1].record(xs)
             L.clear_async()
             free_ev[b] = torch.cuda.Event()
             free_ev[b].record(xs)
+            if round_ev is not None:
+                marks[2].record(xs)
             ex.drain_async(owner, slot=0)
+            if round_ev is not None:
+                marks[3].record(xs)
     ph.mark("rounds")
     with torch.cuda.stream(xs):
         got_rows, got_contrib = peer.drain_collect(owner, slot=0)  # synchronises the exchange stream; errors surface here
@@ -433,6 +444,11 @@ def build_sharded_streaming(graph_map, voxel_size: float, round_submaps: int, st
     graph_map.last_build_stats = stats_all
     graph_map.last_profile = prof
     shard = _finish_shard(owner, fused_all, voxel_size, group, dev, ph)
+    if round_ev:
+        torch.cuda.synchronize(dev)
+        timings["per_round_ms"] = {"push": [m[0].elapsed_time(m[1]) for m in round_ev],
+                                   "clear": [m[1].elapsed_time(m[2]) for m in round_ev],
+                                   "wait_and_drain": [m[2].elapsed_time(m[3]) for m in round_ev]}
     if timings is not None:
         timings.update({"rounds": n_rounds, "pushed_rows": int(pushed_rows), "pushed_contrib": int(pushed_contrib),
                         "received_rows": int(got_rows), "received_contrib": int(got_contrib),
