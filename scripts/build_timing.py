@@ -6,6 +6,9 @@ import torch
 import vsm
 from vsm import synth_device, _native as N
 
+N.set_option("prep_variant", int(os.environ.get("PREP_VARIANT", "5")))
+N.set_option("select_mode", int(os.environ.get("SELECT_MODE", "0")))
+VS = float(os.environ.get("VOXEL", "0.05"))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 gm = vsm.GraphMap()
@@ -16,7 +19,7 @@ hint = 1 << 18
 keep = None
 for rep in range(reps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    m = gm.build_semantic_voxel_map(0.05, capacity_hint=hint, profile=(rep % 2 == 0))
+    m = gm.build_semantic_voxel_map(VS, capacity_hint=hint, profile=(rep % 2 == 0))
     torch.cuda.synchronize(); t1 = time.perf_counter()
     per = [round(s.get("n_map_voxels", 0) / 1000) for s in gm.last_build_stats]
     print(f"rep {rep}: build {1e3*(t1-t0):.1f} ms  hint {hint} voxels {m._dm.num_voxels} launches {N.launch_count()} prof {gm.last_profile}")

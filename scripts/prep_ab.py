@@ -21,8 +21,9 @@ for i in range(n_sub):
 torch.cuda.synchronize()
 print(f"{'voxel':>6} {'prep':>5} {'acc':>4} {'fuse ms/submap':>15} {'accumulate ms':>14} {'prep ms':>8} {'voxels':>9}")
 for vs in (0.05, 0.02):
-    for prep, acc in ((0, 0), (1, 0), (4, 0), (5, 0)):
+    for prep, acc in ((5, 0), (13, 0), (13, 2), (13, 3)):
         N.set_option("prep_variant", prep)
+        N.set_option("select_mode", acc)  # (the 'acc' column: select mode)
         hint = 1 << 18
         for _ in range(3):
             m = gm.build_semantic_voxel_map(vs, capacity_hint=hint, profile=True)
@@ -36,4 +37,5 @@ for vs in (0.05, 0.02):
         f, a = tot["fuse_ms"] / reps / n_sub, tot["accumulate_ms"] / reps / n_sub
         print(f"{vs:6.2f} {prep:5d} {acc:4d} {f:15.4f} {a:14.4f} {f - a:8.4f} {m._dm.num_voxels:9d}", flush=True)
         del m
-N.set_option("prep_variant", 5)
+N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
+N.set_option("select_mode", 0)

@@ -167,3 +167,40 @@ def test_two_maps_on_two_streams_share_the_workspace_safely():
             np.testing.assert_array_equal(k0, k1)
             np.testing.assert_array_equal(c0, c1)
             np.testing.assert_allclose(f0, f1, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("filters", [False, True])
+@pytest.mark.parametrize("variant", [5, 13])
+def test_table_prefix_too_small_is_repeated_with_the_whole_table(filters, variant):
+    """The submap-local tables use a prefix sized from earlier calls (here: forced to its minimum of 16 K slots).  A call
+    with more voxels than 3/4 of the prefix is stopped on the device before it touches the map and repeated with the
+    whole table: same map as with the prefix sizing off, and the retry is counted."""
+    from vsm import _native as N
+    from vsm import voxel_map as vm
+
+    s = synth.make_submap(17, 0, S=5, H=56, W=84, d=16, mode="sl4", room=(2.4, 1.8, 1.2))
+    thr = vm.conf_threshold(s.conf, 25.0)
+    flags = N.FUSE_FILTERS if filters else 0
+    outs = []
+    N.set_option("prep_variant", variant)
+    try:
+        for small in (0, 1):
+            N.set_option("small_tables", small)
+            N.set_option("table_hint", 1)  # prefix = the minimum: 16 384 slots (4 096 for the coarse cells)
+            r0 = N.get_counter("table_retries")
+            dm = vm.DeviceVoxelMap(0.004, 16, N.F32, capacity=1 << 16)  # 4 mm voxels: nearly one voxel per point
+            st = dm.fuse(*_dev(s), dm.make_params(5, 56, 84, 5, 1, thr, s.H_world_map, 0, flags))
+            dm.finalize()
+            if not filters:  # (with filters on it is the coarse table's prefix that overflows: 12 mm cells of ~1 point)
+                assert st["n_submap_voxels"] > 12288
+            if not (filters and variant == 5):  # (two tables + filters: 12 mm cells of ~1 point, neither prefix fills up)
+                assert (N.get_counter("table_retries") > r0) == bool(small)
+            outs.append((st, [t.cpu().numpy() for t in dm.export_geometry()], dm.features_to_host()))
+    finally:
+        N.set_option("small_tables", 1)
+        N.set_option("table_hint", 0)
+        N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
+    assert repr(outs[0][0]) == repr(outs[1][0])  # (the percentile box is NaN without filters: compare the text)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6)

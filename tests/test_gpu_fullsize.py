@@ -67,8 +67,9 @@ def test_config_shapes_against_torch(mode, S, H, W):
     torch.testing.assert_close(dm2.export_features(), feats, rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", [1, 2], ids=["radix_select", "bracket_select"])
-def test_filter_bounds_at_config_size(mode):
+@pytest.mark.parametrize("mode,variant", [(1, 5), (2, 5), (1, 13), (3, 13)],
+                         ids=["radix_select", "bracket_select", "one_table_radix", "one_table_deferred_box"])
+def test_filter_bounds_at_config_size(mode, variant):
     """The bbox filter's 0.5 / 99.5 percentiles (map.py:257-258) at config-1 size against np.percentile on the same
     world points, bit-exact, for both select implementations; the one-pass bracket select must answer without
     falling back; both give the same map."""
@@ -86,6 +87,7 @@ def test_filter_bounds_at_config_size(mode):
     want_hi = np.percentile(pw[keep], 99.5, axis=0)
     assert want_lo.dtype == np.float32
     N.set_option("select_mode", mode)
+    N.set_option("prep_variant", variant)
     try:
         misses0 = N.get_counter("select_misses")
         dm = vm.DeviceVoxelMap(0.05, 64, N.BF16, capacity=1 << 17)
@@ -93,13 +95,24 @@ def test_filter_bounds_at_config_size(mode):
         assert N.get_counter("select_misses") == misses0
     finally:
         N.set_option("select_mode", 0)
+        N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
     np.testing.assert_array_equal(np.asarray(st["bbox_lo"], np.float32), want_lo)
     np.testing.assert_array_equal(np.asarray(st["bbox_hi"], np.float32), want_hi)
     inside = keep & (pw >= want_lo).all(axis=1) & (pw <= want_hi).all(axis=1)
     assert st["n_finite"] == int(keep.sum()) and st["n_bbox"] == int(inside.sum())
     dm.finalize()
-    _, _, cnt, _ = dm.export_geometry()
+    coords, _, cnt, _ = dm.export_geometry()
     assert int(cnt.sum()) == st["n_fused"] <= st["n_bbox"]
+    # filter 3 and the voxel keys restated independently (map.py:271-280, 351): cells of float32(3 vs) with >= 10 points
+    pin = pw[inside]
+    ck = np.floor(pin / np.float32(0.05 * 3.0)).astype(np.int64)
+    _, inv, n_cell = np.unique(ck, axis=0, return_inverse=True, return_counts=True)
+    ok = n_cell[inv.reshape(-1)] >= 10
+    assert st["n_fused"] == int(ok.sum())
+    vk, vn = np.unique(np.floor(pin[ok] / np.float32(0.05)).astype(np.int64), axis=0, return_counts=True)
+    np.testing.assert_array_equal(coords.cpu().numpy(), vk)
+    np.testing.assert_array_equal(cnt.cpu().numpy(), vn)
+    assert st["n_submap_voxels"] == vk.shape[0]
     dm.close()
 
 

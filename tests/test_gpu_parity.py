@@ -192,7 +192,7 @@ def test_fuse_submap_oracle(vsm_mod, seed, S, H, W, d, mode, kind, kernel_varian
 # ---------------------------------------------------------------------------
 # a7: global build with the three filters
 # ---------------------------------------------------------------------------
-@pytest.fixture(params=[1, 2], ids=["radix_select", "bracket_select"])
+@pytest.fixture(params=[1, 2, 3], ids=["radix_select", "bracket_select", "deferred_box"])
 def select_mode(request):
     """Both implementations of the bbox percentiles (three-pass radix select / one-pass bracket select with its
     retry path) must give the reference's bounds."""
@@ -214,7 +214,7 @@ def fuse_overlap(request):
     N.set_option("overlap", 0)
 
 
-@pytest.fixture(params=[0, 5, 7], ids=["row_kernels", "default_kernels", "mask_probe"])
+@pytest.fixture(params=[0, 5, 7, 13, 8], ids=["row_kernels", "two_table_kernels", "mask_probe", "one_table_kernels", "one_table_rows"])
 def kernel_variant(request):
     """The preparation kernels with a warp per 32-pixel row run / per 4x8 patch (+ merged select steps, + frame-mask
     probe): every combination must give the reference's map."""
@@ -222,7 +222,7 @@ def kernel_variant(request):
 
     N.set_option("prep_variant", request.param)
     yield request.param
-    N.set_option("prep_variant", 5)
+    N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
 
 
 def graph_from(vsm, subs, **kw):
@@ -267,6 +267,66 @@ def test_build_global_filter_stages(vsm_mod, select_mode):
         assert st["n_fused"] == stages["n_coarse"]
         np.testing.assert_array_equal(np.asarray(st["bbox_lo"], np.float32), stages["lo"])
         np.testing.assert_array_equal(np.asarray(st["bbox_hi"], np.float32), stages["hi"])
+
+
+@pytest.mark.parametrize("voxel_size", [0.05, 0.02, 0.1, 0.3])
+@pytest.mark.parametrize("variant", [13, 5])
+def test_points_on_coarse_cell_boundaries(vsm_mod, voxel_size, variant, select_mode):
+    """The coarse-cell filter (map.py:271-280) on points placed within a few float32 steps of the cell boundaries
+    k * float32(3 * vs): float32(vs * 3) is not 3 * float32(vs), so floor(p / cell) and floor(floor(p / vs) / 3)
+    disagree for some of them -- the one-table preparation derives a voxel's cell from its coordinates and must find
+    exactly those points.  A dense cloud keeps most cells above the 10-point limit, a thin shell leaves sparse cells
+    next to them, so both outcomes of the filter meet boundary points.  Keys, counts and filter stages: bit-exact."""
+    from vsm import _native as N
+
+    rng = np.random.default_rng(int(voxel_size * 1000) + 7)
+    cell = np.float32(voxel_size * 3.0)
+    S, H, W, d = 2, 96, 128, 8
+    n = S * H * W
+    pts = np.empty((n, 3), dtype=np.float32)
+    half = n // 2
+    # boundary points: coordinates k * cell moved by -3 .. +3 float32 steps, on every axis independently
+    k = rng.integers(-60, 60, size=(half, 3)).astype(np.float64)
+    b = (k * np.float64(cell)).astype(np.float32)
+    steps = rng.integers(-3, 4, size=(half, 3))
+    for _ in range(3):
+        up = np.nextafter(b, np.float32(np.inf))
+        dn = np.nextafter(b, np.float32(-np.inf))
+        b = np.where(steps > 0, up, np.where(steps < 0, dn, b))
+        steps = steps - np.sign(steps)
+    on_boundary = rng.random(size=(half, 3)) < 0.5  # the other coordinates anywhere in the box
+    box = 60.0 * float(cell)
+    pts[:half] = np.where(on_boundary, b, rng.uniform(-box, box, size=(half, 3)).astype(np.float32))
+    # dense cloud in a small box around the origin (cells well above 10 points) + nothing else: the boundary points
+    # far from it sit in sparse cells
+    pts[half:] = rng.uniform(-4.0 * float(cell), 4.0 * float(cell), size=(n - half, 3)).astype(np.float32)
+    pts[:half // 2] = np.clip(pts[:half // 2], -4.0 * float(cell), 4.0 * float(cell))  # half of the boundary points inside it
+    rng.shuffle(pts, axis=0)
+    s = synth.SynthSubmap(0, pts.reshape(S, H, W, 3), (1.0 + rng.gamma(2.0, 2.0, size=(S, H, W))).astype(np.float32),
+                          np.zeros((S, H, W, 3), np.uint8), synth.round_to_bf16(rng.normal(size=(S, H, W, d)).astype(np.float32)),
+                          np.eye(4), [f"f_{i:03d}.png" for i in range(S)], S - 1)
+    stages = {}
+    with np.errstate(all="ignore"):
+        want = vo.build_global([gio.to_oracle_submap(s)], voxel_size, exact_order=False)
+        vo.submap_observations(gio.to_oracle_submap(s), voxel_size, 1, True, stages)
+    # the case is adversarial: for some points the reference's cell is not the cell of the point's voxel
+    fine = vo.voxel_keys(pts, float(voxel_size))
+    assert int((vo.voxel_keys(pts, float(voxel_size) * 3.0) != np.floor_divide(fine, 3)).any(axis=1).sum()) > 20
+    N.set_option("prep_variant", variant)
+    try:
+        gm = graph_from(vsm_mod, [s], device_inputs=True)
+        m = gm.build_semantic_voxel_map(voxel_size)
+    finally:
+        N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
+    st = gm.last_build_stats[0]
+    assert st["n_bbox"] == stages["n_bbox"] and st["n_fused"] == stages["n_coarse"]
+    assert 0 < stages["n_coarse"] < stages["n_bbox"]
+    coords, _, counts, _ = m._dm.export_geometry()
+    np.testing.assert_array_equal(coords.cpu().numpy(), want.coords)
+    np.testing.assert_array_equal(counts.cpu().numpy(), want.counts)
+    assert st["n_submap_voxels"] == want.coords.shape[0]
+    np.testing.assert_allclose(m.get_features(), want.features, rtol=RTOL, atol=ATOL)
+    assert m.get_contributors() == want.contributors
 
 
 def test_build_global_errors_and_empty(vsm_mod):

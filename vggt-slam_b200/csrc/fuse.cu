@@ -34,13 +34,17 @@
 namespace vsm {
 
 constexpr uint32_t kFuseForceRadix = 1u << 30;  // internal flag: this call must use the three-pass radix select
-std::atomic<int> g_select_mode{0};              // 0 default (= 1), 1 radix, 2 bracket (vsm_set_option "select_mode")
+constexpr uint32_t kFuseForceBigTables = 1u << 28;  // internal flag: this call must use the full-size submap-local tables
+std::atomic<int> g_small_tables{1};             // "small_tables": size the submap-local tables from earlier calls
+std::atomic<int> g_select_mode{0};              // 0 default (= 3), 1 radix, 2 bracket in the world kernel, 3 deferred box ("select_mode")
 // preparation kernels (vsm_set_option "prep_variant"): bit 0 = a warp takes a 4x8 pixel patch instead of 32 pixels of a
-// row; bit 1 = read the frame-mask word before the atomic OR; bit 2 = select with merged one-block steps
-std::atomic<int> g_prep_variant{5};
+// row; bit 1 = read the frame-mask word before the atomic OR; bit 2 = select with merged one-block steps; bit 3 = one-table
+// preparation (coarse cells counted per distinct voxel, ordinals instead of a second round of atomics)
+std::atomic<int> g_prep_variant{13};
 std::atomic<int> g_range_policy{0};             // "coord_range_policy": 0 = fail the call (VSM_E_COORD_RANGE), 1 = drop + count
 std::atomic<long long> g_select_misses{0};      // calls repeated because the bracket select could not answer
 std::atomic<long long> g_capacity_retries{0};   // calls repeated after the map / contributor log had to grow
+std::atomic<long long> g_table_retries{0};      // calls repeated because the table prefix sized from earlier calls was too small
 std::atomic<long long> g_early_collects{0};     // queued calls collected by a later submit (full ring, log growth)
 std::atomic<int> g_host_zero_copy{1};            // "host_zero_copy": pinned host embeddings are read in place by the accumulate kernel
 std::atomic<int> g_acc_ctas_per_sm{2};          // resident CTAs per SM of the voxel-sorted accumulate kernel ("acc_ctas_per_sm")
@@ -91,56 +95,45 @@ __device__ __forceinline__ void hist0_add(uint32_t* sh, const float4& p, bool va
   }
 }
 
-// One CTA per axis: transform a hashed sample of the RAW points, sort the valid ones, publish the brackets that the
-// world-point kernel collects into (bracket.cuh).
+// One CTA per bracket (axis x {low, high} percentile): transform a hashed sample of the RAW points, keep the valid
+// ones' coordinate on this axis as ordered keys in shared memory, and read off the bracket [lo, hi] -- the sample order
+// statistics 5 sigma either side of the wanted sample rank -- with a two-target radix select (bracket.cuh).
 __global__ void __launch_bounds__(1024) bracket_sample_kernel(WorldArgs a, HMat Hm, BracketState* bs, float q0, float q1) {
-  __shared__ float sv[kBrSample];
+  __shared__ uint32_t sv[kBrSample];
+  __shared__ uint32_t hist[2 * 2048];
+  __shared__ uint32_t sm[8];
   __shared__ uint32_t s_n;
-  const int c = blockIdx.x;
+  const int t = blockIdx.x, c = t >> 1;
   if (threadIdx.x == 0) s_n = 0u;
   __syncthreads();
   const uint32_t m = a.n_px < (uint32_t)kBrSample ? a.n_px : (uint32_t)kBrSample;
   const uint32_t step = m > 0 ? a.n_px / m : 1u;
+#pragma unroll 4
   for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) {
     const uint32_t pix = j * step + hash32(j * 3u + 0x9E3779B9u) % step;
     uint32_t f;
     const float4 w = world_one(a, Hm, pix, a.pts[3 * (size_t)pix], a.pts[3 * (size_t)pix + 1], a.pts[3 * (size_t)pix + 2],
                                a.conf[pix], f);
-    if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) sv[atomicAdd(&s_n, 1u)] = c == 0 ? w.x : (c == 1 ? w.y : w.z);
+    if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE))
+      sv[atomicAdd(&s_n, 1u)] = float_to_ordered(c == 0 ? w.x : (c == 1 ? w.y : w.z));
   }
   __syncthreads();
   const uint32_t mv = s_n;
-  for (uint32_t j = mv + threadIdx.x; j < (uint32_t)kBrSample; j += blockDim.x) sv[j] = __int_as_float(0x7F800000);  // +inf pads
-  __syncthreads();
-  // bitonic sort, one compare-exchange per thread and step
-  for (uint32_t k = 2; k <= (uint32_t)kBrSample; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-      for (uint32_t t = threadIdx.x; t < (uint32_t)kBrSample / 2; t += blockDim.x) {
-        const uint32_t i = 2 * t - (t & (j - 1));  // index with bit j clear
-        const uint32_t l = i + j;
-        const bool up = (i & k) == 0;
-        const float x = sv[i], y = sv[l];
-        if ((x > y) == up) {
-          sv[i] = y;
-          sv[l] = x;
-        }
-      }
-      __syncthreads();
-    }
+  float lo = -__int_as_float(0x7F800000), hi = __int_as_float(0x7F800000);
+  if (mv < 64u) {
+    if (threadIdx.x == 0) atomicOr(&bs->miss, 1u);  // too few valid samples to bracket anything
+  } else {
+    const float q = (t & 1) ? q1 : q0;
+    const float r = q * (float)(mv - 1);
+    const float w = 5.0f * sqrtf(fmaxf((float)mv * q * (1.0f - q), 1.0f)) + 2.0f;
+    const float ra = floorf(r - w), rb = ceilf(r + w);
+    const bool has_lo = ra >= 1.0f, has_hi = rb <= (float)(mv - 2);
+    uint32_t k0, k1;
+    cta_select2(sv, mv, has_lo ? (uint32_t)ra : 0u, has_hi ? (uint32_t)rb : mv - 1u, hist, sm, k0, k1);
+    if (has_lo) lo = ordered_to_float(k0);
+    if (has_hi) hi = ordered_to_float(k1);
   }
-  if (threadIdx.x < 2) {
-    const int t = c * 2 + threadIdx.x;
-    const float q = threadIdx.x == 0 ? q0 : q1;
-    float lo = -__int_as_float(0x7F800000), hi = __int_as_float(0x7F800000);
-    if (mv < 64u) {
-      atomicOr(&bs->miss, 1u);  // too few valid samples to bracket anything
-    } else {
-      const float r = q * (float)(mv - 1);
-      const float w = 6.0f * sqrtf(fmaxf((float)mv * q * (1.0f - q), 1.0f)) + 2.0f;
-      const float ra = floorf(r - w), rb = ceilf(r + w);
-      if (ra >= 1.0f) lo = sv[(uint32_t)ra];
-      if (rb <= (float)(mv - 2)) hi = sv[(uint32_t)rb];
-    }
+  if (threadIdx.x == 0) {
     bs->lo[t] = lo;
     bs->hi[t] = hi;
   }
@@ -152,8 +145,16 @@ template <bool VEC4, int MODE>
 __global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm, FuseCounters* ctr, BracketArgs br) {
   constexpr bool HIST = MODE == 1;
   __shared__ uint32_t sh[HIST ? 3 * 2048 : 1];
+  __shared__ float s_stage[MODE == 2 ? kBrWarps * kBrLists * kBrStage : 1];
+  __shared__ uint32_t s_stage_n[MODE == 2 ? kBrWarps * kBrLists : 1];
+  float* const my_stage = s_stage + (MODE == 2 ? (threadIdx.x >> 5) * kBrLists * kBrStage : 0);
+  uint32_t* const my_stage_n = s_stage_n + (MODE == 2 ? (threadIdx.x >> 5) * kBrLists : 0);
   BracketLocal bl;
-  if (MODE == 2) bracket_load(bl, br.bs);
+  if (MODE == 2) {
+    bracket_load(bl, br.bs);
+    if (lane_id() < kBrLists) my_stage_n[lane_id()] = 0u;
+    __syncwarp();
+  }
   if (HIST) {
     for (int i = threadIdx.x; i < 3 * 2048; i += blockDim.x) sh[i] = 0u;
     __syncthreads();
@@ -203,10 +204,15 @@ __global__ void __launch_bounds__(256) world_points_kernel(WorldArgs a, HMat Hm,
       n_sel += (f[j] & PF_SEL) ? 1u : 0u;
       n_fin += (f[j] & PF_FINITE) ? 1u : 0u;
       if (HIST) hist0_add(sh, o[j], (f[j] & PF_FINITE) != 0u);
-      if (MODE == 2) bracket_collect(bl, br, o[j].x, o[j].y, o[j].z, (f[j] & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE));
+    }
+    if (MODE == 2) {
+      bool valid[PPT];
+#pragma unroll
+      for (uint32_t j = 0; j < PPT; ++j) valid[j] = (f[j] & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
+      bracket_collect<(int)PPT>(bl, br, o, valid, my_stage, my_stage_n);
     }
   }
-  if (MODE == 2) bracket_flush(bl, br);
+  if (MODE == 2) bracket_flush(bl, br, my_stage, my_stage_n);
   for (int o = 16; o > 0; o >>= 1) {
     n_sel += __shfl_xor_sync(0xffffffffu, n_sel, o);
     n_fin += __shfl_xor_sync(0xffffffffu, n_fin, o);
@@ -288,6 +294,7 @@ __device__ __forceinline__ bool map_pixel(const PixMap& pm, uint32_t item, int l
   return pix < pm.n_px;
 }
 
+constexpr uint32_t kMaxLocalProbes = 4096u;
 constexpr int kOptMaskProbe = 1;  // read the frame-mask word before the atomic OR (most ORs would set a bit that is set)
 constexpr int kOptDropRange = 2;  // drop points whose finite voxel coordinate cannot be packed instead of failing the call
 
@@ -296,7 +303,8 @@ constexpr int kOptDropRange = 2;  // drop points whose finite voxel coordinate c
 __device__ __forceinline__ int table_claim(const LocalTable& t, unsigned long long key, uint32_t add, bool& is_new,
                                            FuseCounters* ctr) {
   uint32_t h = (uint32_t)mix64(key) & t.cap_mask;
-  for (uint32_t probes = 0; probes <= t.cap_mask; ++probes) {
+  const uint32_t max_probes = min(t.cap_mask, kMaxLocalProbes);  // a table that fills up is reported, not searched end to end
+  for (uint32_t probes = 0; probes <= max_probes; ++probes) {
     Slot* sl = t.slots + h;
     unsigned long long cur = sl->key;
     if (cur == kEmptyKey) {
@@ -332,7 +340,10 @@ __device__ __forceinline__ int warp_insert(const LocalTable& t, bool active, uns
   if (newm) {
     const int nl = __ffs(newm) - 1;
     uint32_t base = 0;
-    if (lane == nl) base = atomicAdd(t.n_occ, (uint32_t)__popc(newm));
+    if (lane == nl) {
+      base = atomicAdd(t.n_occ, (uint32_t)__popc(newm));
+      if (base + (uint32_t)__popc(newm) > t.limit) atomicExch(t.overflow, 1u);
+    }
     base = __shfl_sync(0xffffffffu, base, nl);
     if (is_new) t.slot_list[base + (uint32_t)__popc(newm & ((1u << lane) - 1u))] = (uint32_t)slot;
   }
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(256) count_new_decide_kernel(LocalTable tb, Gl
     const bool fits = ((unsigned long long)map_state[0] + total_new <= vcap) &&
                       ((unsigned long long)log_n + n_occ <= log_cap) &&
                       (ctr->n_finite <= (unsigned long long)entry_cap || ctr->n_fused <= (unsigned long long)entry_cap);
-    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss || ctr->bad_index) {
+    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss || ctr->bad_index || ctr->tbl_overflow) {
       ctr->abort = 1u;
     } else {
       ctr->log_base = log_n;  // calls on one stream run one after the other: plain read-modify-write
@@ -688,6 +699,673 @@ __global__ void __launch_bounds__(256) point_gid_kernel(const int32_t* __restric
       if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) g = -2;
     }
     point_gid[pix] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one-table preparation (vsm_set_option("prep_variant") bit 3)
+// ---------------------------------------------------------------------------
+// The two-table preparation above visits every point twice: bbox_coarse_kernel counts the points per coarse cell
+// (map.py:271-275), fine_insert_kernel looks the count up and inserts the survivors into the voxel table.  Here every
+// bbox survivor is inserted into the voxel table at once and the coarse cells are counted per DISTINCT VOXEL
+// afterwards (~10^5 voxels instead of ~5 x 10^6 points): a coarse cell is F x F x F voxels, so the cell of a voxel
+// follows from its integer coordinates, floor(i / F).  The reference computes the cell of a POINT in float32,
+// floor(p / float32(vs * F)), which differs from floor(floor(p / float32(vs)) / F) for the few points within ~1e-6
+// cells of a cell boundary (float32(vs * F) != F * float32(vs), and the two quotients round differently).  Those
+// IRREGULAR points (tens per submap) are found exactly -- a cheap conservative band test, then the reference's own
+// arithmetic -- and take a side path: they are counted in their float32 cell, and the accepted ones enter the voxel
+// table under a PSEUDO key (voxel key | bit 63) which the global merge maps back to the voxel itself.  Every regular
+// point of a voxel lies in the voxel's derived cell, so the coarse-cell filter keeps or drops a table entry as a whole.
+// The insert also hands every point its ordinal inside its voxel (the old value of the count it adds to), so the
+// counting sort needs no second round of atomics: position = segment start + ordinal.
+//   insert7        px: bbox test, voxel key, irregularity test, claim + count + frame mask -> (slot, ordinal)
+//   coarse7        distinct voxel: derived cell -> coarse table (weighted by the voxel's count); irregular points:
+//                  +1 in their float32 cell; last block: accepted irregular points claim their pseudo voxels
+//   keep7          distinct voxel: cell count >= min_pts -> kept list, n_fused, exact capacity check; last block decides
+//   compact_merge7 kept voxel: segment of the sorted list, global insert, counts, contributor log
+//   scatter7       px: entries[segment start + ordinal] = (voxel id, pixel)
+constexpr uint32_t kLidReject = 0xFFFFFFFFu;
+constexpr unsigned long long kPseudoBit = 1ull << 63;
+constexpr uint32_t kIrrCap = 1u << 16;
+constexpr uint32_t kFuseForceTwoTables = 1u << 29;  // internal flag: this call must use the two-table preparation
+
+struct alignas(32) IrrEntry {
+  unsigned long long fine_key, coarse_key;
+  uint32_t pix, frame, cslot, pad;
+};
+
+struct CoarseMap {  // coarse axis code from a fine axis code: floor((c + (F-1) 2^20) / F), c >= 1
+  FastDiv div;
+  uint32_t add;
+};
+__device__ __forceinline__ unsigned long long coarse_from_fine(unsigned long long key, const CoarseMap& cm) {
+  unsigned long long out = 0ull;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const uint32_t c = (uint32_t)(key >> (21 * ax)) & 0x1FFFFFu;
+    const uint32_t cc = c == 0u ? 0u : fdiv_u32(c + cm.add, cm.div);
+    out |= (unsigned long long)cc << (21 * ax);
+  }
+  return out;
+}
+
+// table_claim that also returns the count before the add (the group's first ordinal inside its voxel)
+__device__ __forceinline__ int table_claim_ord(const LocalTable& t, unsigned long long key, uint32_t add, bool& is_new,
+                                               uint32_t& old, FuseCounters* ctr) {
+  uint32_t h = (uint32_t)mix64(key) & t.cap_mask;
+  const uint32_t max_probes = min(t.cap_mask, kMaxLocalProbes);  // a table that fills up is reported, not searched end to end
+  for (uint32_t probes = 0; probes <= max_probes; ++probes) {
+    Slot* sl = t.slots + h;
+    unsigned long long cur = sl->key;
+    if (cur == kEmptyKey) {
+      cur = atomicCAS(&sl->key, kEmptyKey, key);
+      if (cur == kEmptyKey) {
+        is_new = true;
+        cur = key;
+      }
+    }
+    if (cur == key) {
+      old = atomicAdd(&sl->count, add);
+      return (int)h;
+    }
+    h = (h + 1u) & t.cap_mask;
+  }
+  atomicAdd(&ctr->internal_err, 1u);
+  return -1;
+}
+
+__device__ __forceinline__ void claim_list_append(const LocalTable& t, bool is_new, int slot) {
+  const int lane = lane_id();
+  const unsigned newm = __ballot_sync(0xffffffffu, is_new);
+  if (newm) {
+    const int nl = __ffs(newm) - 1;
+    uint32_t base = 0;
+    if (lane == nl) {
+      base = atomicAdd(t.n_occ, (uint32_t)__popc(newm));
+      if (base + (uint32_t)__popc(newm) > t.limit) atomicExch(t.overflow, 1u);
+    }
+    base = __shfl_sync(0xffffffffu, base, nl);
+    if (is_new) t.slot_list[base + (uint32_t)__popc(newm & ((1u << lane) - 1u))] = (uint32_t)slot;
+  }
+}
+
+// warp_insert + ordinals.  All 32 lanes must call.
+__device__ __forceinline__ int warp_insert_ord(const LocalTable& t, bool active, unsigned long long key, int frame, int opts,
+                                               FuseCounters* ctr, uint32_t& ord) {
+  const int lane = lane_id();
+  const unsigned long long k = active ? key : kEmptyKey;
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(grp) - 1;
+  int slot = -1;
+  uint32_t old = 0;
+  bool is_new = false;
+  if (active && lane == leader) slot = table_claim_ord(t, key, (uint32_t)__popc(grp), is_new, old, ctr);
+  claim_list_append(t, is_new, slot);
+  slot = __shfl_sync(0xffffffffu, slot, leader);
+  old = __shfl_sync(0xffffffffu, old, leader);
+  ord = old + (uint32_t)__popc(grp & ((1u << lane) - 1u));
+  const int lf = __shfl_sync(0xffffffffu, frame, leader);
+  if (active && slot >= 0 && (lane == leader || frame != lf)) {
+    unsigned long long* mp = &t.slots[slot].mask[frame >> 6];
+    const unsigned long long bit = 1ull << (frame & 63);
+    if (!(opts & kOptMaskProbe) || (__ldcg(mp) & bit) == 0ull) atomicOr(mp, bit);
+  }
+  return active ? slot : -1;
+}
+
+// insert with a weight per lane (the points of a voxel): lanes with equal keys add their weights with one atomic
+__device__ __forceinline__ int warp_insert_weighted(const LocalTable& t, bool active, unsigned long long key, uint32_t w,
+                                                    FuseCounters* ctr) {
+  const int lane = lane_id();
+  const unsigned long long k = active ? key : kEmptyKey;
+  const unsigned grp = __match_any_sync(0xffffffffu, k);
+  const int leader = __ffs(grp) - 1;
+  const uint32_t sum = __reduce_add_sync(grp, active ? w : 0u);
+  int slot = -1;
+  bool is_new = false;
+  if (active && lane == leader) slot = table_claim(t, key, sum, is_new, ctr);
+  claim_list_append(t, is_new, slot);
+  slot = __shfl_sync(0xffffffffu, slot, leader);
+  return active ? slot : -1;
+}
+
+struct Prep7Args {
+  const float4* pw;
+  uint2* pt2;
+  IrrEntry* irr;
+  uint32_t frame_base;
+  float cell;         // float32(voxel size)
+  float cell_coarse;  // float32(voxel size * F), the reference's coarse cell
+  float inv_coarse;   // 1 / cell_coarse (band test only)
+  CoarseMap cm;
+  uint32_t min_pts;
+  int opts;
+};
+
+// Warp-collective (all 32 lanes call): lanes with cand = true hold a point that has passed the confidence, finite and
+// percentile-box tests.  Voxel key, irregularity test, claim + count + frame mask; (slot, ordinal) of every lane with
+// inside = true is written to pt2 (slot -1: not fused, or irregular -- coarse7 decides).
+__device__ __forceinline__ void insert7_lanes(const Prep7Args& a, const LocalTable& tb, FuseCounters* ctr, bool inside,
+                                              bool cand, const float4& p, uint32_t pix, int frame, unsigned& n_in) {
+  const int lane = lane_id();
+  bool act = false, irr = false, never = false;
+  unsigned long long key = kEmptyKey, ckey = 0ull;
+  if (cand) {
+    bool rerr = false;
+    key = pack_key(p.x, p.y, p.z, a.cell, rerr);
+    if (rerr) {
+      // a voxel coordinate that cannot be packed: the call fails, or (drop policy) the point is dropped -- but it
+      // still counts in its coarse cell, as in the two-table preparation, through the irregular list
+      if (range_problem(true, a.opts, ctr)) {
+        bool r2 = false;
+        ckey = pack_key(p.x, p.y, p.z, a.cell_coarse, r2);
+        if (!r2) {
+          n_in += 1u;
+          irr = true;
+          never = true;
+        }
+      }
+    } else {
+      n_in += 1u;  // passes the percentile box (map.py:259-263)
+      act = true;
+      // Irregular only if p / cell_coarse is within ~3e-7 (relative) of an integer: the three quotients involved
+      // (this estimate, the reference's float32 quotient, the voxel coordinate / F) all lie that close to the real
+      // p / cell_coarse.  The band is 1e-6: everything outside it is regular without looking further.
+      const float tx = __fmul_rn(p.x, a.inv_coarse), ty = __fmul_rn(p.y, a.inv_coarse), tz = __fmul_rn(p.z, a.inv_coarse);
+      const bool near_x = fabsf(tx - rintf(tx)) <= fmaf(fabsf(tx), 1e-6f, 1e-6f);
+      const bool near_y = fabsf(ty - rintf(ty)) <= fmaf(fabsf(ty), 1e-6f, 1e-6f);
+      const bool near_z = fabsf(tz - rintf(tz)) <= fmaf(fabsf(tz), 1e-6f, 1e-6f);
+      if (near_x || near_y || near_z) {
+        bool r2 = false;
+        ckey = pack_key(p.x, p.y, p.z, a.cell_coarse, r2);  // the reference's arithmetic (map.py:271-274)
+        irr = ckey != coarse_from_fine(key, a.cm);
+        act = !irr;
+      }
+    }
+  }
+  uint32_t ord = 0;
+  const int slot = warp_insert_ord(tb, act, key, frame, a.opts, ctr, ord);
+  const unsigned im = __ballot_sync(0xffffffffu, irr);
+  if (im) {
+    const int il = __ffs(im) - 1;
+    uint32_t base = 0;
+    if (lane == il) base = atomicAdd(&ctr->n_irr, (uint32_t)__popc(im));
+    base = __shfl_sync(0xffffffffu, base, il);
+    if (irr) {
+      const uint32_t idx = base + (uint32_t)__popc(im & ((1u << lane) - 1u));
+      if (idx < kIrrCap) {
+        IrrEntry e;
+        e.fine_key = key;
+        e.coarse_key = ckey;
+        e.pix = pix;
+        e.frame = never ? 0xFFFFFFFFu : (uint32_t)frame;  // 0xFFFFFFFF: counted in its cell, never fused
+        e.cslot = 0u;
+        e.pad = 0u;
+        a.irr[idx] = e;
+      } else {
+        atomicExch(&ctr->irr_overflow, 1u);
+      }
+    }
+  }
+  if (inside) a.pt2[pix] = make_uint2((uint32_t)slot, ord);  // irregular points: -1 for now (coarse7 decides)
+}
+
+template <bool PATCH>
+__global__ void __launch_bounds__(256) insert7_kernel(Prep7Args a, PixMap pm, LocalTable tb, FuseCounters* ctr) {
+  const float lx = ctr->bounds[0], hx = ctr->bounds[1], ly = ctr->bounds[2], hy = ctr->bounds[3], lz = ctr->bounds[4],
+              hz = ctr->bounds[5];
+  unsigned n_in = 0;
+  const int lane = lane_id();
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
+    uint32_t pix, fidx;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix, fidx);
+    bool cand = false;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) {
+      p = a.pw[pix];
+      const uint32_t f = __float_as_uint(p.w);
+      cand = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE) && (p.x >= lx) && (p.x <= hx) && (p.y >= ly) &&
+             (p.y <= hy) && (p.z >= lz) && (p.z <= hz);
+    }
+    insert7_lanes(a, tb, ctr, inside, cand, p, pix, (int)(a.frame_base + fidx), n_in);
+  }
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  if (lane == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
+}
+
+// ---- deferred percentile box ("select_mode" 3) ------------------------------------------------------------------
+// The percentile box needs the 0.5 % / 99.5 % order statistics of all points of the submap -- two more passes over
+// the points with the radix select.  Here a sorted sample (bracket_sample_kernel) gives, per axis, a bracket around
+// each of the two percentiles, and the brackets alone already classify ~95 % of the points: below the low bracket or
+// above the high one -> outside the box; between the two brackets on every axis -> inside, inserted right away.  The
+// rest (inside some bracket, outside nowhere) is listed.  The same pass counts the points below / above the brackets
+// and collects the coordinates inside them, so bracket_resolve_kernel can pick the exact order statistics (ranks
+// relative to the counts) without reading the points again; insert7u_kernel then applies the exact box to the listed
+// pixels.  A percentile that falls outside its bracket (probability ~1e-6) or a list that overflows sets sel_miss: the
+// call stops before it touches the map and is repeated with the radix select.  Never an approximation.
+constexpr int kStageLists = kBrLists + 1;  // + the undecided pixels
+
+__device__ __forceinline__ void stage7_flush(const BracketArgs& br, uint32_t* buf, uint32_t* cnt, int t) {
+  const int lane = lane_id();
+  const uint32_t n = min(cnt[t], (uint32_t)kBrStage);
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(t < kBrLists ? &br.bs->cursor[t] : &br.bs->und_cursor, n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (uint32_t i = lane; i < n; i += 32u) {
+    const uint32_t v = buf[t * kBrStage + i];
+    if (t < kBrLists) {
+      if (base + i < br.cap) br.lists[(size_t)t * br.cap + base + i] = __uint_as_float(v);
+    } else if (base + i < br.und_cap) {
+      br.und[base + i] = v;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) cnt[t] = 0u;
+  __syncwarp();
+}
+
+template <bool PATCH>
+__global__ void __launch_bounds__(256) insert7d_kernel(Prep7Args a, PixMap pm, LocalTable tb, FuseCounters* ctr, BracketArgs br) {
+  __shared__ uint32_t s_buf[kBrWarps * kStageLists * kBrStage];
+  __shared__ uint32_t s_cnt[kBrWarps * kStageLists];
+  uint32_t* const buf = s_buf + (threadIdx.x >> 5) * kStageLists * kBrStage;
+  uint32_t* const cnt = s_cnt + (threadIdx.x >> 5) * kStageLists;
+  const int lane = lane_id();
+  if (lane < kStageLists) cnt[lane] = 0u;
+  __syncwarp();
+  float lo_l[3], hi_l[3], lo_h[3], hi_h[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    lo_l[ax] = br.bs->lo[2 * ax];
+    hi_l[ax] = br.bs->hi[2 * ax];
+    lo_h[ax] = br.bs->lo[2 * ax + 1];
+    hi_h[ax] = br.bs->hi[2 * ax + 1];
+  }
+  uint32_t below[3] = {0u, 0u, 0u}, above[3] = {0u, 0u, 0u};
+  unsigned n_in = 0;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t item = warp; item < pm.n_items; item += n_warps) {
+    uint32_t pix, fidx;
+    const bool inside = map_pixel<PATCH>(pm, item, lane, pix, fidx);
+    bool cand = false;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) {
+      p = a.pw[pix];
+      const uint32_t f = __float_as_uint(p.w);
+      if ((f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE)) {
+        const float c3[3] = {p.x, p.y, p.z};
+        bool out = false, und = false;
+#pragma unroll
+        for (int ax = 0; ax < 3; ++ax) {
+          const float c = c3[ax];
+          if (c <= hi_l[ax]) {  // at or below the low bracket's upper end: ~1 % of the points
+            if (c < lo_l[ax]) {
+              ++below[ax];
+              out = true;
+            } else {
+              und = true;
+              buf[(2 * ax) * kBrStage + atomicAdd(&cnt[2 * ax], 1u)] = __float_as_uint(c);
+            }
+          }
+          if (c >= lo_h[ax]) {
+            if (c > hi_h[ax]) {
+              ++above[ax];
+              out = true;
+            } else {
+              und = true;
+              buf[(2 * ax + 1) * kBrStage + atomicAdd(&cnt[2 * ax + 1], 1u)] = __float_as_uint(c);
+            }
+          }
+        }
+        cand = !out && !und;
+        if (und && !out) buf[kBrLists * kBrStage + atomicAdd(&cnt[kBrLists], 1u)] = pix;  // box test waits for the percentiles
+      }
+    }
+    // a list is flushed once it is half full: an iteration adds at most 32 values (one per lane) to each
+    __syncwarp();
+    unsigned full = __ballot_sync(0xffffffffu, lane < kStageLists && cnt[lane < kStageLists ? lane : 0] >= (uint32_t)kBrStage / 2);
+    while (full) {
+      const int t = __ffs(full) - 1;
+      full &= full - 1;
+      stage7_flush(br, buf, cnt, t);
+    }
+    insert7_lanes(a, tb, ctr, inside, cand, p, pix, (int)(a.frame_base + fidx), n_in);
+  }
+  __syncwarp();
+  for (int t = 0; t < kStageLists; ++t)
+    if (cnt[t]) stage7_flush(br, buf, cnt, t);
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    uint32_t b = below[ax], ab = above[ax];
+    for (int o = 16; o > 0; o >>= 1) {
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    if (lane == 0) {
+      if (b) atomicAdd(&br.bs->below[2 * ax], b);
+      if (ab) atomicAdd(&br.bs->above[2 * ax + 1], ab);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  if (lane == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
+}
+
+// the listed pixels against the exact box (ctr->bounds, written by bracket_resolve_kernel; NaN after a miss: nothing passes)
+__global__ void __launch_bounds__(256) insert7u_kernel(Prep7Args a, PixMap pm, LocalTable tb, FuseCounters* ctr, BracketArgs br) {
+  const float lx = ctr->bounds[0], hx = ctr->bounds[1], ly = ctr->bounds[2], hy = ctr->bounds[3], lz = ctr->bounds[4],
+              hz = ctr->bounds[5];
+  const uint32_t n = min(br.bs->und_cursor, br.und_cap);
+  const uint32_t n_round = (n + 31u) & ~31u;
+  unsigned n_in = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool inside = i < n;
+    uint32_t pix = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool cand = false;
+    if (inside) {
+      pix = br.und[i];
+      p = a.pw[pix];
+      cand = (p.x >= lx) && (p.x <= hx) && (p.y >= ly) && (p.y <= hy) && (p.z >= lz) && (p.z <= hz);
+    }
+    insert7_lanes(a, tb, ctr, inside, cand, p, pix, (int)(a.frame_base + fdiv_u32(pix, pm.div_ppf)), n_in);
+  }
+  for (int o = 16; o > 0; o >>= 1) n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
+  if (lane_id() == 0 && n_in) atomicAdd(&ctr->n_bbox, (unsigned long long)n_in);
+}
+
+__global__ void __launch_bounds__(256) coarse7_kernel(Prep7Args a, LocalTable tb, LocalTable ta, FuseCounters* ctr) {
+  const uint32_t n_occ = ctr->n_occ_b;
+  const uint32_t n_round = (n_occ + 31u) & ~31u;
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
+    const bool on = lid < n_occ;
+    uint32_t slot = 0, cnt = 0;
+    unsigned long long ckey = kEmptyKey;
+    if (on) {
+      slot = tb.slot_list[lid];
+      const Slot* sl = tb.slots + slot;
+      ckey = coarse_from_fine(sl->key, a.cm);
+      cnt = sl->count;
+    }
+    const int cs = warp_insert_weighted(ta, on, ckey, cnt, ctr);
+    if (on) tb.slots[slot].lid = (uint32_t)cs;  // the voxel's coarse cell, until keep7 decides
+  }
+  const uint32_t n_irr = min(ctr->n_irr, kIrrCap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_irr; i += gridDim.x * blockDim.x) {
+    bool nw = false;
+    const int cs = table_claim(ta, a.irr[i].coarse_key, 1u, nw, ctr);
+    if (nw) {
+      const uint32_t at = atomicAdd(ta.n_occ, 1u);
+      if (at + 1u > ta.limit) atomicExch(ta.overflow, 1u);
+      ta.slot_list[at] = (uint32_t)cs;
+    }
+    a.irr[i].cslot = (uint32_t)cs;
+  }
+  if (n_irr == 0u) return;
+  // the last block to finish sees every cell's final count: accepted irregular points enter the voxel table
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ctr->ticket2, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (uint32_t i = threadIdx.x; i < n_irr; i += blockDim.x) {
+    const IrrEntry* e = a.irr + i;
+    const uint32_t cs = __ldcg(&e->cslot);
+    const uint32_t fr = __ldcg(&e->frame);
+    if (fr == 0xFFFFFFFFu || (int)cs < 0 || __ldcg(&ta.slots[cs].count) < a.min_pts) continue;
+    const unsigned long long pkey = __ldcg(&e->fine_key) | kPseudoBit;
+    if (pkey == kEmptyKey) {
+      atomicAdd(&ctr->internal_err, 1u);
+      continue;
+    }
+    bool nw = false;
+    uint32_t old = 0;
+    const int s = table_claim_ord(tb, pkey, 1u, nw, old, ctr);
+    if (s < 0) continue;
+    if (nw) {
+      const uint32_t at = atomicAdd(tb.n_occ, 1u);
+      if (at + 1u > tb.limit) atomicExch(tb.overflow, 1u);
+      tb.slot_list[at] = (uint32_t)s;
+    }
+    atomicOr(&tb.slots[s].mask[fr >> 6], 1ull << (fr & 63u));
+    a.pt2[__ldcg(&e->pix)] = make_uint2((uint32_t)s, old);
+  }
+}
+
+__global__ void __launch_bounds__(256) keep7_kernel(LocalTable tb, LocalTable ta, GlobalStore g, FuseCounters* ctr,
+                                                    uint32_t* __restrict__ kept, uint32_t min_pts,
+                                                    uint32_t* __restrict__ map_state, uint32_t vcap, uint32_t log_cap,
+                                                    uint32_t entry_cap) {
+  const uint32_t n_occ = ctr->n_occ_b;
+  const uint32_t n_round = (n_occ + 31u) & ~31u;
+  const int lane = lane_id();
+  unsigned n_new = 0, n_dist = 0;
+  unsigned long long n_fused = 0;
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
+    const bool on = lid < n_occ;
+    uint32_t slot = 0, cnt = 0;
+    unsigned long long key = 0ull;
+    bool keep = false;
+    if (on) {
+      slot = tb.slot_list[lid];
+      const Slot* sl = tb.slots + slot;
+      key = sl->key;
+      cnt = sl->count;
+      keep = (key & kPseudoBit) != 0ull || ta.slots[sl->lid].count >= min_pts;
+    }
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    if (km) {
+      const int kl = __ffs(km) - 1;
+      uint32_t base = 0;
+      if (lane == kl) base = atomicAdd(&ctr->n_kept, (uint32_t)__popc(km));
+      base = __shfl_sync(0xffffffffu, base, kl);
+      if (keep) kept[base + (uint32_t)__popc(km & ((1u << lane) - 1u))] = slot;
+    }
+    if (keep) {
+      n_fused += cnt;
+      const unsigned long long real = key & ~kPseudoBit;
+      bool found = false;
+      uint64_t h = mix64(real) & g.gmask;
+      for (uint64_t probes = 0; probes <= g.gmask; ++probes) {
+        const unsigned long long cur = g.gkeys[h];
+        if (cur == real) {
+          found = true;
+          break;
+        }
+        if (cur == kEmptyKey) break;
+        h = (h + 1) & g.gmask;
+      }
+      n_new += found ? 0u : 1u;  // a pseudo voxel and its voxel both count: an upper bound, which is all the check needs
+      bool distinct = true;
+      if (key & kPseudoBit) {
+        // n_submap_voxels counts voxels: not distinct if the voxel itself is in the table and kept
+        uint32_t h2 = (uint32_t)mix64(real) & tb.cap_mask;
+        for (uint32_t probes = 0; probes <= tb.cap_mask; ++probes) {
+          const unsigned long long cur = tb.slots[h2].key;
+          if (cur == kEmptyKey) break;
+          if (cur == real) {
+            const uint32_t l2 = __ldcg(&tb.slots[h2].lid);  // its cell, or kLidReject if this kernel has dropped it already
+            distinct = l2 == kLidReject || ta.slots[l2].count < min_pts;
+            break;
+          }
+          h2 = (h2 + 1u) & tb.cap_mask;
+        }
+      }
+      n_dist += distinct ? 1u : 0u;
+    } else if (on) {
+      tb.slots[slot].lid = kLidReject;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_new += __shfl_xor_sync(0xffffffffu, n_new, o);
+    n_dist += __shfl_xor_sync(0xffffffffu, n_dist, o);
+    n_fused += __shfl_xor_sync(0xffffffffu, n_fused, o);
+  }
+  if (lane == 0) {
+    if (n_new) atomicAdd(&ctr->n_new, n_new);
+    if (n_dist) atomicAdd(&ctr->n_distinct, n_dist);
+    if (n_fused) atomicAdd(&ctr->n_fused, n_fused);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&ctr->ticket, 1u) == gridDim.x - 1) {
+    __threadfence();
+    const uint32_t total_new = atomicAdd(&ctr->n_new, 0u);
+    const uint32_t n_kept = atomicAdd(&ctr->n_kept, 0u);
+    const unsigned long long fused = atomicAdd(&ctr->n_fused, 0ull);
+    const uint32_t log_n = map_state[1];
+    const bool fits = ((unsigned long long)map_state[0] + total_new <= vcap) &&
+                      ((unsigned long long)log_n + n_kept <= log_cap) &&
+                      (ctr->n_finite <= (unsigned long long)entry_cap || fused <= (unsigned long long)entry_cap);
+    if (!fits || ctr->range_err || ctr->internal_err || ctr->sel_miss || ctr->bad_index || ctr->irr_overflow ||
+        ctr->tbl_overflow) {
+      ctr->abort = 1u;
+    } else {
+      ctr->log_base = log_n;
+      ctr->vox_base = map_state[0];
+      map_state[1] = log_n + n_kept;
+    }
+  }
+}
+
+// compact_merge_kernel over the kept list.  Pseudo voxels merge into their voxel (two local entries, one global id:
+// the waits for a published id therefore come AFTER the warp's own publications).  Leaves (segment start, voxel id) in
+// the slot's first mask word -- the frame masks have gone to the contributor log -- for scatter7.
+__global__ void __launch_bounds__(256) compact_merge7_kernel(LocalTable tb, const uint32_t* __restrict__ kept, GlobalStore g,
+                                                             FuseCounters* ctr, int32_t* __restrict__ log_gid,
+                                                             int32_t* __restrict__ log_sub,
+                                                             unsigned long long* __restrict__ log_mask, int32_t submap_id) {
+  if (ctr->abort) return;
+  const uint32_t n_kept = ctr->n_kept;
+  const uint32_t n_round = (n_kept + 31u) & ~31u;
+  const size_t log_base = ctr->log_base;
+  const int lane = lane_id();
+  for (uint32_t lid = blockIdx.x * blockDim.x + threadIdx.x; lid < n_round; lid += gridDim.x * blockDim.x) {
+    const bool on = lid < n_kept;
+    uint32_t cnt = 0, slot = 0;
+    unsigned long long key = kEmptyKey, m0 = 0ull, m1 = 0ull;
+    if (on) {
+      slot = kept[lid];
+      const Slot* sl = tb.slots + slot;
+      key = sl->key & ~kPseudoBit;
+      cnt = sl->count;
+      m0 = sl->mask[0];
+      m1 = sl->mask[1];
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(&ctr->seg_total, incl);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int gid = -1;
+    uint64_t hslot = 0;
+    bool claimed = false, found = false;
+    if (on) {
+      uint64_t h = mix64(key) & g.gmask;
+      for (uint64_t probes = 0; probes <= g.gmask; ++probes) {
+        unsigned long long cur = g.gkeys[h];
+        if (cur == kEmptyKey) {
+          cur = atomicCAS(&g.gkeys[h], kEmptyKey, key);
+          if (cur == kEmptyKey) {
+            claimed = true;
+            hslot = h;
+            break;
+          }
+        }
+        if (cur == key) {
+          found = true;
+          hslot = h;
+          break;
+        }
+        h = (h + 1) & g.gmask;
+      }
+      if (!claimed && !found) atomicAdd(&ctr->internal_err, 1u);
+    }
+    const unsigned newm = __ballot_sync(0xffffffffu, claimed);
+    if (newm) {
+      const int nl = __ffs(newm) - 1;
+      uint32_t id0 = 0;
+      if (lane == nl) id0 = atomicAdd(g.n_vox, (uint32_t)__popc(newm));
+      id0 = __shfl_sync(0xffffffffu, id0, nl);
+      if (claimed) {
+        const uint32_t id = id0 + (uint32_t)__popc(newm & ((1u << lane) - 1u));
+        if (id >= g.vcap) {
+          atomicAdd(&ctr->internal_err, 1u);
+          reinterpret_cast<volatile int32_t*>(g.gids)[hslot] = -2;
+        } else {
+          g.vkey[id] = key;
+          __threadfence();
+          reinterpret_cast<volatile int32_t*>(g.gids)[hslot] = (int32_t)id;
+          gid = (int)id;
+        }
+      }
+    }
+    if (found) {
+      while ((gid = reinterpret_cast<volatile int32_t*>(g.gids)[hslot]) == -1) {
+      }
+    }
+    if (on) {
+      Slot* sl = tb.slots + slot;
+      sl->lid = lid;
+      sl->mask[0] = (unsigned long long)(base + incl - cnt) | ((unsigned long long)(uint32_t)gid << 32);
+      if (gid >= 0) atomicAdd(&g.vcount[gid], cnt);
+      log_gid[log_base + lid] = gid;
+      log_sub[log_base + lid] = submap_id;
+      log_mask[2 * (log_base + lid)] = m0;
+      log_mask[2 * (log_base + lid) + 1] = m1;
+    }
+  }
+}
+
+// counting sort without a second round of atomics: entries[segment start + ordinal] = (voxel id, pixel); check-only
+// pixels behind.  entries == nullptr (pixel-order / host paths): only the per-pixel voxel ids (-2 = check-only).
+__global__ void __launch_bounds__(256) scatter7_kernel(const uint2* __restrict__ pt2, const float4* __restrict__ pw,
+                                                       uint32_t n_px, LocalTable tb, int mark_checks,
+                                                       unsigned long long* __restrict__ entries,
+                                                       int32_t* __restrict__ point_gid, FuseCounters* ctr) {
+  if (ctr->abort) return;
+  const uint32_t n_fused = (uint32_t)ctr->n_fused;
+  const int lane = lane_id();
+  const uint32_t n_round = (n_px + 31u) & ~31u;
+  for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_round; pix += gridDim.x * blockDim.x) {
+    const bool inside = pix < n_px;
+    int gid = -1;
+    if (inside) {
+      const uint2 ps = pt2[pix];
+      if ((int)ps.x >= 0) {
+        const Slot* sl = tb.slots + ps.x;
+        if (sl->lid != kLidReject) {
+          const unsigned long long m0 = sl->mask[0];
+          gid = (int)(uint32_t)(m0 >> 32);
+          if (entries != nullptr && gid >= 0) entries[(uint32_t)m0 + ps.y] = make_entry(gid, pix);
+        }
+      }
+    }
+    if (mark_checks) {
+      bool chk = false;
+      if (inside && gid < 0) {
+        const uint32_t f = __float_as_uint(pw[pix].w);
+        chk = (f & (PF_SEL | PF_FINITE)) == (PF_SEL | PF_FINITE);
+      }
+      if (entries != nullptr) {
+        const unsigned cm = __ballot_sync(0xffffffffu, chk);
+        if (cm) {
+          uint32_t cbase = 0;
+          if (lane == __ffs(cm) - 1) cbase = atomicAdd(&ctr->n_check, (uint32_t)__popc(cm));
+          cbase = __shfl_sync(0xffffffffu, cbase, __ffs(cm) - 1);
+          if (chk) entries[n_fused + cbase + (uint32_t)__popc(cm & ((1u << lane) - 1u))] = make_entry(-2, pix);
+        }
+      } else if (chk) {
+        gid = -2;
+      }
+    }
+    if (point_gid != nullptr && inside) point_gid[pix] = gid;
   }
 }
 
@@ -1229,12 +1907,14 @@ static int ensure_stream_objects(vsm_map* m, size_t chunk_bytes) {
   return VSM_OK;
 }
 
-static LocalTable table_view(DevBuf& slots, DevBuf& list, uint64_t cap, uint32_t* n_occ) {
+static LocalTable table_view(DevBuf& slots, DevBuf& list, uint64_t cap, uint32_t* n_occ, uint32_t* overflow) {
   LocalTable t{};
   t.slots = slots.as<Slot>();
   t.slot_list = list.as<uint32_t>();
   t.n_occ = n_occ;
   t.cap_mask = (uint32_t)(cap - 1);
+  t.limit = (uint32_t)(cap - cap / 4);
+  t.overflow = overflow;
   return t;
 }
 
@@ -1399,6 +2079,12 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   VSM_TRY(ws->lv_off.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_cursor.ensure((size_t)n_sel_max * 4, s));
   VSM_TRY(ws->lv_gid.ensure((size_t)n_sel_max * 4, s));
+  if (filters && (g_prep_variant.load() & 8)) {  // one-table preparation: (slot, ordinal) per pixel, kept list, irregular points
+    VSM_TRY(ws->pt2.ensure((size_t)n_px * 8, s));
+    VSM_TRY(ws->kept.ensure((size_t)n_sel_max * 4, s));
+    VSM_TRY(ws->irr.ensure((size_t)(1u << 16) * 32, s));
+  }
+  if (filters && g_select_mode.load() != 1) VSM_TRY(ws->sel_bracket.ensure(bracket_scratch_bytes(n_px), s));
   VSM_TRY(ensure_acc_stream(ws));
   const int ab = ws->acc_parity;  // which sorted list this call fills
   if (!pixel_order) {
@@ -1409,9 +2095,9 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
 
   // SM partitions: from here on the call's preparation kernels go to the preparation partition's stream (the plain
   // device-resident, voxel-sorted call only: the optional paths allocate per-call buffers on the stream they run on)
-  const int sel_mode = g_select_mode.load();
+  const int sel_mode = g_select_mode.load() == 0 ? 3 : g_select_mode.load();  // (3 needs the one-table preparation: else radix)
   PrepFork prep_fork(ws, s);
-  const bool green = ws->overlap && ws->green_on && !pixel_order && !keep_index && sel_mode != 2 &&
+  const bool green = ws->overlap && ws->green_on && !pixel_order && !keep_index &&
                      !(filters && (p->flags & VSM_FUSE_EMB_PRECHECK) && emb_ok == nullptr);
   if (green) {
     if (filters) {  // the select scratch is allocated on first use: do that on the caller's stream
@@ -1423,9 +2109,23 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_TRY(prep_fork.fork(&s));
   }
 
-  LocalTable tb = table_view(ws->tb_slots, ws->tb_list, ws->tb_cap, &ctr->n_occ_b);
+  // The tables are allocated for the worst case (every selected pixel a voxel of its own: 2^24 slots, 0.5 GB, at the
+  // benchmark's shape) but a call only uses a prefix sized from the most voxels any call on this device has had: 4x
+  // that, a power of two -- 16 MB at 5 cm, resident in L2 instead of probed at random in HBM.  A call that outgrows
+  // the prefix is stopped by the device before it touches the map and repeated with the whole table.
+  uint64_t cap_b = lcap, cap_a = lcap;  // (the allocation can be larger than this call's worst case: probe no more than that)
+  if (g_small_tables.load() && ws->hint_n_occ > 0 && !(p->flags & kFuseForceBigTables)) {
+    // the hint was taken at voxel size hint_vs: surfaces fill (hint_vs / vs)^2 as many voxels of size vs
+    double scale = ws->hint_vs > 0.0 ? (ws->hint_vs / m->cfg.voxel_size) * (ws->hint_vs / m->cfg.voxel_size) : 1.0;
+    scale = std::min(64.0, std::max(1.0 / 64.0, scale));
+    const int64_t hint = std::max<int64_t>(m->last_n_occ, (int64_t)((double)ws->hint_n_occ * scale));
+    const uint64_t want = next_pow2(4 * (uint64_t)std::max<int64_t>(hint, 4096));
+    cap_b = std::min<uint64_t>(lcap, want);
+    cap_a = std::min<uint64_t>(lcap, std::max<uint64_t>(want / 4, 1u << 14));
+  }
+  LocalTable tb = table_view(ws->tb_slots, ws->tb_list, cap_b, &ctr->n_occ_b, &ctr->tbl_overflow);
   LocalTable ta{};
-  if (filters) ta = table_view(ws->ta_slots, ws->ta_list, ws->ta_cap, &ctr->n_occ_a);
+  if (filters) ta = table_view(ws->ta_slots, ws->ta_list, cap_a, &ctr->n_occ_a, &ctr->tbl_overflow);
 
   if (emb_index != nullptr) {
     index_check_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(conf, emb_index, (uint32_t)n_px, p->conf_threshold, p->emb_rows, ctr);
@@ -1451,7 +2151,16 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   // collect inside the world-point kernel, exact resolve; repeated with the radix select when it cannot answer) gives
   // the same bounds and is kept as an option: on B200 it measured 6 % SLOWER per fuse call (its collect step more
   // than doubles the instruction-bound world-point kernel), see DESIGN.md 5.
-  const bool bracket = filters && !(p->flags & kFuseForceRadix) && sel_mode == 2;
+  const int variant = g_prep_variant.load();
+  // one-table preparation: an integer number of voxels per coarse cell (the reference's 3) is what lets the cell of
+  // a voxel follow from its coordinates
+  const double cf = p->coarse_factor;
+  const bool v7 = filters && (variant & 8) != 0 && !(p->flags & kFuseForceTwoTables) && cf >= 1.0 && cf <= 1024.0 &&
+                  cf == (double)(int64_t)cf;
+  // select_mode 2: brackets collected by the world-point kernel; 3 (one-table preparation only): brackets applied and
+  // collected by the insert kernel, no percentile pass at all
+  const bool deferred = v7 && !(p->flags & kFuseForceRadix) && sel_mode == 3 && ws->sel_bracket.p != nullptr;
+  const bool bracket = filters && !(p->flags & kFuseForceRadix) && (sel_mode == 2 || deferred) && ws->sel_bracket.p != nullptr;
   SelectState* sst = nullptr;
   uint32_t* hist = nullptr;
   float* sel_out = nullptr;
@@ -1459,7 +2168,6 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_TRY(select_scratch(&sst, &hist, &sel_out));
     VSM_TRY(select_reset(sst, hist, s));
   }
-  if (bracket) VSM_TRY(ws->sel_bracket.ensure(bracket_scratch_bytes(n_px), s));
   HMat Hm;
   for (int i = 0; i < 16; ++i) Hm.m[i] = p->H_world_map[i];
   WorldArgs wa;
@@ -1479,14 +2187,20 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   const float q1 = (float)p->bbox_hi_pct / 100.0f;
   BracketArgs br{};
   if (bracket) {
+    static const cudaError_t smem_opt_in = cudaFuncSetAttribute(bracket_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                (int)(kResolveStage * sizeof(uint32_t)));
+    VSM_CUDA(smem_opt_in);
     br.bs = reinterpret_cast<BracketState*>(ws->sel_bracket.p);
     br.lists = reinterpret_cast<float*>(reinterpret_cast<char*>(ws->sel_bracket.p) + 256);
     br.cap = bracket_list_cap(n_px);
+    br.und = reinterpret_cast<uint32_t*>(br.lists + (size_t)kBrLists * br.cap);
+    br.und_cap = bracket_und_cap(n_px);
     VSM_CUDA(cudaMemsetAsync(br.bs, 0, sizeof(BracketState), s));
-    bracket_sample_kernel<<<3, 1024, 0, s>>>(wa, Hm, br.bs, q0, q1);
+    if (deferred) VSM_CUDA(cudaMemsetAsync(&br.bs->deferred, 1, 1, s));  // (little-endian: the word becomes 1)
+    bracket_sample_kernel<<<kBrLists, 1024, 0, s>>>(wa, Hm, br.bs, q0, q1);
     VSM_LAUNCHED();
   }
-  const int wmode = !filters ? 0 : (bracket ? 2 : 1);
+  const int wmode = (!filters || deferred) ? 0 : (bracket ? 2 : 1);
 #define VSM_WORLD(VEC4_)                                                            \
   do {                                                                              \
     if (wmode == 0)                                                                 \
@@ -1504,8 +2218,8 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   VSM_LAUNCHED();
 
   // ---- filters and the two submap-local tables -----------------------------------------------------------
-  const int variant = g_prep_variant.load();
   const bool patch = (variant & 1) != 0;
+  static_assert(kIrrCap == (1u << 16) && sizeof(IrrEntry) == 32, "irregular list: 64 K entries of 32 bytes");
   FilterArgs fa;
   fa.pw = ws->pw.as<float4>();
   fa.pt_slot = ws->pt_slot.as<int32_t>();
@@ -1514,10 +2228,27 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   fa.opts = ((variant & 2) ? kOptMaskProbe : 0) | (g_range_policy.load() == 1 ? kOptDropRange : 0);
   const PixMap pm = make_pixmap(n_px, p->end_idx, p->H, p->W, patch);
   const int grid = grid_for((int64_t)pm.n_items * 32, 256);
+  call.v7 = v7;
+  Prep7Args a7{};
+  if (v7) {
+    a7.pw = ws->pw.as<float4>();
+    a7.pt2 = ws->pt2.as<uint2>();
+    a7.irr = ws->irr.as<IrrEntry>();
+    a7.frame_base = (uint32_t)p->frame_base;
+    a7.cell = m->vs_f;
+    a7.cell_coarse = (float)(m->cfg.voxel_size * cf);
+    a7.inv_coarse = 1.0f / a7.cell_coarse;
+    a7.cm.div = make_fastdiv((uint32_t)cf);
+    a7.cm.add = ((uint32_t)cf - 1u) << 20;
+    a7.min_pts = fa.min_pts;
+    a7.opts = fa.opts;
+  }
   if (filters) {
-    if (bracket) {
-      bracket_resolve_kernel<<<kBrLists, 1024, 0, s>>>(br.bs, br.lists, br.cap, &ctr->n_finite, q0, q1, ctr->bounds,
-                                                       &ctr->sel_miss);
+    if (deferred) {
+      // nothing here: the insert kernel applies and fills the brackets, the exact percentiles follow it
+    } else if (bracket) {
+      bracket_resolve_kernel<<<kBrLists, 1024, kResolveStage * sizeof(uint32_t), s>>>(br.bs, br.lists, br.cap, &ctr->n_finite, q0, q1, ctr->bounds,
+                                                       &ctr->sel_miss, br.und_cap);
       VSM_LAUNCHED();
     } else if (variant & 4) {
       VSM_TRY(run_percentiles_world_fast(sst, hist, ws->pw.as<float4>(), n_px, PF_SEL | PF_FINITE, q0, q1, ctr->bounds,
@@ -1532,18 +2263,37 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
       src.n_items = n_px;
       VSM_TRY(run_percentiles_after_hist0(sst, hist, src, 2, q0, q1, ctr->bounds, &ctr->n_finite, s));
     }
-    fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
-    if (patch)
-      bbox_coarse_kernel<true><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
-    else
-      bbox_coarse_kernel<false><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
-    VSM_LAUNCHED();
-    fa.cell = m->vs_f;
-    if (patch)
-      fine_insert_kernel<true, true><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
-    else
-      fine_insert_kernel<true, false><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
-    VSM_LAUNCHED();
+    if (deferred) {
+      if (patch)
+        insert7d_kernel<true><<<grid, 256, 0, s>>>(a7, pm, tb, ctr, br);
+      else
+        insert7d_kernel<false><<<grid, 256, 0, s>>>(a7, pm, tb, ctr, br);
+      VSM_LAUNCHED();
+      bracket_resolve_kernel<<<kBrLists, 1024, kResolveStage * sizeof(uint32_t), s>>>(br.bs, br.lists, br.cap, &ctr->n_finite, q0, q1, ctr->bounds,
+                                                       &ctr->sel_miss, br.und_cap);
+      VSM_LAUNCHED();
+      insert7u_kernel<<<grid_for((int64_t)br.und_cap, 256, sm_count() * 8), 256, 0, s>>>(a7, pm, tb, ctr, br);
+      VSM_LAUNCHED();
+    } else if (v7) {
+      if (patch)
+        insert7_kernel<true><<<grid, 256, 0, s>>>(a7, pm, tb, ctr);
+      else
+        insert7_kernel<false><<<grid, 256, 0, s>>>(a7, pm, tb, ctr);
+      VSM_LAUNCHED();
+    } else {
+      fa.cell = (float)(m->cfg.voxel_size * p->coarse_factor);  // float(voxel_size) * 3.0, weak scalar -> float32
+      if (patch)
+        bbox_coarse_kernel<true><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
+      else
+        bbox_coarse_kernel<false><<<grid, 256, 0, s>>>(fa, pm, ta, ctr);
+      VSM_LAUNCHED();
+      fa.cell = m->vs_f;
+      if (patch)
+        fine_insert_kernel<true, true><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
+      else
+        fine_insert_kernel<true, false><<<grid, 256, 0, s>>>(fa, pm, ta, tb, ctr);
+      VSM_LAUNCHED();
+    }
   } else {
     fa.cell = m->vs_f;
     if (patch)
@@ -1553,17 +2303,31 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
     VSM_LAUNCHED();
   }
   const int vgrid = grid_for((int64_t)std::min<uint64_t>(n_sel_max, (uint64_t)sm_count() * 8 * 256), 256, sm_count() * 8);
-  count_new_decide_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
-                                                (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
-                                                (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
-  VSM_LAUNCHED();
+  if (v7) {
+    coarse7_kernel<<<vgrid, 256, 0, s>>>(a7, tb, ta, ctr);
+    VSM_LAUNCHED();
+    keep7_kernel<<<vgrid, 256, 0, s>>>(tb, ta, global_store(m), ctr, ws->kept.as<uint32_t>(), a7.min_pts,
+                                       m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
+                                       (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
+                                       (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
+    VSM_LAUNCHED();
+    compact_merge7_kernel<<<vgrid, 256, 0, s>>>(tb, ws->kept.as<uint32_t>(), global_store(m), ctr, m->log_gid.as<int32_t>(),
+                                                m->log_fuse.as<int32_t>(), m->log_mask.as<unsigned long long>(),
+                                                p->submap_id);
+    VSM_LAUNCHED();
+  } else {
+    count_new_decide_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, m->d_n_vox.as<uint32_t>(), (uint32_t)m->vcap,
+                                                  (uint32_t)std::min<int64_t>(m->log_cap, 0xFFFFFFFFll),
+                                                  (uint32_t)std::min<uint64_t>(n_sel_max, 0xFFFFFFFFull));
+    VSM_LAUNCHED();
 
-  // ---- distinct voxels -> global map; points -> sorted entries ---------------------------------------------
-  compact_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, ws->lv_off.as<uint32_t>(),
-                                             ws->lv_cursor.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
-                                             m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
-                                             m->log_mask.as<unsigned long long>(), p->submap_id);
-  VSM_LAUNCHED();
+    // ---- distinct voxels -> global map; points -> sorted entries ---------------------------------------------
+    compact_merge_kernel<<<vgrid, 256, 0, s>>>(tb, global_store(m), ctr, ws->lv_off.as<uint32_t>(),
+                                               ws->lv_cursor.as<uint32_t>(), ws->lv_gid.as<int32_t>(),
+                                               m->log_gid.as<int32_t>(), m->log_fuse.as<int32_t>(),
+                                               m->log_mask.as<unsigned long long>(), p->submap_id);
+    VSM_LAUNCHED();
+  }
 
   FuseRecord& rec = m->fuses[call.fuse_index];
   int32_t* point_gid = nullptr;
@@ -1583,8 +2347,12 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
   aa.d = m->d;
   aa.nvec = (int)(row_bytes / 16);
   aa.ctr = ctr;
+  const int grid7 = grid_for(n_px, 256);
   if (!pixel_order) {
-    if (patch)
+    if (v7)
+      scatter7_kernel<<<grid7, 256, 0, s>>>(ws->pt2.as<uint2>(), ws->pw.as<float4>(), (uint32_t)n_px, tb, check ? 1 : 0,
+                                            ws->sorted_pix[ab].as<unsigned long long>(), point_gid, ctr);
+    else if (patch)
       scatter_kernel<true><<<grid, 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), pm, tb,
                                                 ws->lv_off.as<uint32_t>(), ws->lv_cursor.as<uint32_t>(),
                                                 ws->lv_gid.as<int32_t>(), check ? 1 : 0,
@@ -1615,8 +2383,12 @@ static int fuse_enqueue(vsm_map* m, PendingCall& call, const HostEmb* host, cuda
       ws->acc_parity ^= 1;
     }
   } else {
-    point_gid_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
-                                                         ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
+    if (v7)
+      scatter7_kernel<<<grid7, 256, 0, s>>>(ws->pt2.as<uint2>(), ws->pw.as<float4>(), (uint32_t)n_px, tb, check ? 1 : 0,
+                                            nullptr, point_gid, ctr);
+    else
+      point_gid_kernel<<<grid_for(n_px, 256), 256, 0, s>>>(ws->pt_slot.as<int32_t>(), ws->pw.as<float4>(), (uint32_t)n_px, tb,
+                                                           ws->lv_gid.as<int32_t>(), check ? 1 : 0, point_gid, ctr);
     VSM_LAUNCHED();
     tables_cleanup_kernel<<<vgrid, 256, 0, s>>>(ta, filters ? 1 : 0, tb);
     VSM_LAUNCHED();
@@ -1733,7 +2505,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     FuseCounters c = hc[k];
     const bool filters = (call.p.flags & VSM_FUSE_FILTERS) != 0;
     int status = VSM_OK;
-    for (int attempt = 0; c.abort && !c.internal_err && !c.range_err && !c.bad_index; ++attempt) {
+    for (int attempt = 0; c.abort && (!c.internal_err || c.tbl_overflow) && !c.range_err && !c.bad_index; ++attempt) {
       // nothing was modified: grow and run the call again, alone
       if (attempt >= 3) {
         set_error("internal: fuse call kept aborting after the map was grown");
@@ -1748,10 +2520,15 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
         // the one-pass percentile select could not answer (its counts are meaningless): radix select this time
         call.p.flags |= kFuseForceRadix;
         ++g_select_misses;
+      } else if (c.tbl_overflow) {
+        call.p.flags |= kFuseForceBigTables;  // more voxels than the table prefix sized from earlier calls holds
+        ++g_table_retries;
+      } else if (c.irr_overflow) {
+        call.p.flags |= kFuseForceTwoTables;  // more irregular points than the side list holds: two-table preparation
       } else {
         ++g_capacity_retries;
         VSM_TRY(map_grow(m, m->n_vox + (int64_t)c.n_new, s));
-        VSM_TRY(log_grow(m, m->log_n + (int64_t)c.n_occ_b, s));
+        VSM_TRY(log_grow(m, m->log_n + (int64_t)(call.v7 ? c.n_kept : c.n_occ_b), s));
       }
       call.slot = 0;
       m->fuses[call.fuse_index].point_gid.release();
@@ -1765,7 +2542,8 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
     st.n_finite = (int64_t)c.n_finite;
     st.n_bbox = filters ? (int64_t)c.n_bbox : (int64_t)c.n_conf;
     st.n_fused = (int64_t)c.n_fused;
-    st.n_submap_voxels = c.n_occ_b;
+    const uint32_t n_local = call.v7 ? c.n_kept : c.n_occ_b;  // local table entries merged into the map (log entries)
+    st.n_submap_voxels = call.v7 ? c.n_distinct : c.n_occ_b;
     st.n_bad_emb_rows = (int64_t)c.n_bad_emb;
     st.n_range_dropped = (int64_t)c.range_dropped;
     for (int i = 0; i < 3; ++i) {
@@ -1790,8 +2568,12 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
       }
     }
     if (status == VSM_OK || status == VSM_E_NONFINITE_EMB) {
-      m->last_n_occ = c.n_occ_b;
-      m->ws->hint_n_occ = std::max<int64_t>(m->ws->hint_n_occ, c.n_occ_b);  // largest call seen on this device
+      m->last_n_occ = n_local;
+      if (m->ws->hint_vs != m->cfg.voxel_size) {  // the hint follows the voxel size of the calls
+        m->ws->hint_n_occ = 0;
+        m->ws->hint_vs = m->cfg.voxel_size;
+      }
+      m->ws->hint_n_occ = std::max<int64_t>(m->ws->hint_n_occ, n_local);  // largest call seen on this device
       m->fuses[call.fuse_index].n_fused = (int64_t)c.n_fused;
       if (call.profiled && c.n_fused > 0 && !hc[k].abort) {
         float t_acc = 0.f;
@@ -1810,7 +2592,7 @@ static int fuse_collect_locked(vsm_map* m, cudaStream_t s, std::vector<vsm_fuse_
         m->prof.accumulate_ms += t_acc;
         m->prof.fuse_calls += 1;
         m->prof.accumulate_launches += 1;
-        m->prof.accumulate_bytes += (int64_t)c.n_fused * m->d * m->esize + (int64_t)c.n_occ_b * m->d * 4;
+        m->prof.accumulate_bytes += (int64_t)c.n_fused * m->d * m->esize + (int64_t)n_local * m->d * 4;
         m->prof.points_fused += (int64_t)c.n_fused;
       }
     }
@@ -1960,7 +2742,7 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
     VSM_TRY(fuse_enqueue(m, call, &he, s));
     FuseCounters c{};
     VSM_TRY(read_back(m, &c, m->ctr_ring.p, sizeof(FuseCounters), s));
-    if (c.abort && !c.internal_err && !c.range_err) {
+    if (c.abort && (!c.internal_err || c.tbl_overflow) && !c.range_err) {
       m->fuses.back().point_gid.release();
       m->fuses.pop_back();
       if (c.sel_miss) {
@@ -1969,11 +2751,22 @@ extern "C" int vsm_fuse_submap_host(vsm_map* m, const float* pts_host, const flo
         --attempt;  // not a capacity retry
         continue;
       }
+      if (c.tbl_overflow) {
+        q.flags |= kFuseForceBigTables;
+        ++g_table_retries;
+        --attempt;
+        continue;
+      }
+      if (c.irr_overflow) {
+        q.flags |= kFuseForceTwoTables;
+        --attempt;
+        continue;
+      }
       uint32_t state[2] = {0, 0};
       VSM_TRY(read_back(m, state, m->d_n_vox.p, sizeof(state), s));
       VSM_TRY(map_grow(m, (int64_t)state[0] + (int64_t)c.n_new, s));
-      VSM_TRY(log_grow(m, (int64_t)state[1] + (int64_t)c.n_occ_b, s));
-      m->last_n_occ = c.n_occ_b;
+      VSM_TRY(log_grow(m, (int64_t)state[1] + (int64_t)(call.v7 ? c.n_kept : c.n_occ_b), s));
+      m->last_n_occ = call.v7 ? c.n_kept : c.n_occ_b;
       continue;
     }
     // account for it through the common path
@@ -2034,16 +2827,33 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
     set_error("vsm_set_option: null key");
     return VSM_E_INVALID;
   }
-  if (!strcmp(key, "select_mode") && value >= 0 && value <= 2) {
+  if (!strcmp(key, "select_mode") && value >= 0 && value <= 3) {
     g_select_mode = (int)value;
     return VSM_OK;
   }
-  if (!strcmp(key, "prep_variant") && value >= 0 && value <= 7) {
+  if (!strcmp(key, "prep_variant") && value >= 0 && value <= 15) {
     g_prep_variant = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
     g_range_policy = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "small_tables") && (value == 0 || value == 1)) {
+    g_small_tables = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "table_hint")) {  // forget (0) or set the voxel count the table prefix is sized from (tests)
+    int dev = 0;
+    VSM_CUDA(cudaGetDevice(&dev));
+    Workspace* ws = workspace_for_device(dev);
+    if (!ws || value < 0) {
+      set_error("vsm_set_option: table_hint needs a device workspace and a value >= 0");
+      return VSM_E_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(ws->mu);
+    ws->hint_n_occ = value;
+    ws->hint_vs = 0.0;
     return VSM_OK;
   }
   if (!strcmp(key, "host_zero_copy") && (value == 0 || value == 1)) {
@@ -2096,6 +2906,10 @@ extern "C" int vsm_get_counter(const char* key, int64_t* out_host) {
   }
   if (!strcmp(key, "select_misses")) {
     *out_host = g_select_misses.load();
+    return VSM_OK;
+  }
+  if (!strcmp(key, "table_retries")) {
+    *out_host = g_table_retries.load();
     return VSM_OK;
   }
   if (!strcmp(key, "capacity_retries")) {

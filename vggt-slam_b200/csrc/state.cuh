@@ -42,6 +42,8 @@ struct LocalTable {
   uint32_t* slot_list;  // occupied slots in claim order
   uint32_t* n_occ;      // number of occupied slots (device counter)
   uint32_t cap_mask;    // capacity - 1
+  uint32_t limit;       // claims beyond this many flag an overflow (3/4 of the capacity)
+  uint32_t* overflow;   // the call's tbl_overflow flag
 };
 
 // device-resident counters of one fuse call (zeroed at the start of every call)
@@ -60,6 +62,14 @@ struct FuseCounters {
   float bounds[6];     // bbox filter bounds laid out [axis][lo,hi]
   uint32_t vox_base;   // voxels in the map before this call: ids >= vox_base are new, their sum rows are still zero
   uint32_t range_dropped;  // points dropped because a finite voxel coordinate cannot be packed ("coord_range_policy" 1)
+  // one-table preparation (fuse.cu, "prep v7"): every bbox survivor is inserted into the fine table; coarse cells are
+  // counted per distinct voxel afterwards
+  uint32_t n_kept;        // local voxels that survive the coarse-cell filter (+ pseudo voxels of irregular points)
+  uint32_t n_distinct;    // distinct fine voxels among them (n_submap_voxels)
+  uint32_t n_irr;         // irregular points: float32 coarse cell != the cell derived from the voxel's integer coordinates
+  uint32_t irr_overflow;  // the irregular-point list overflowed: repeat the call with the two-table preparation
+  uint32_t ticket2;       // last-block ticket of the coarse-count kernel
+  uint32_t tbl_overflow;  // a submap-local table sized from earlier calls filled up: repeat the call with full-size tables
 };
 
 // radix-select state (device)
@@ -87,6 +97,7 @@ struct PendingCall {
   int slot;             // index into the counter / event rings
   int fuse_index;       // index into vsm_map::fuses
   bool profiled;
+  bool v7;              // queued with the one-table preparation (which counters hold the call's voxel count)
   DevBuf precheck_mask; // row mask computed for VSM_FUSE_EMB_PRECHECK, alive until the call is collected
 };
 
@@ -110,6 +121,9 @@ struct Workspace {
   std::mutex mu;
   DevBuf pw;        // float4[N_px]
   DevBuf pt_slot;   // int32[N_px]
+  DevBuf pt2;       // uint2[N_px]: (fine-table slot | -1, ordinal of the point inside its voxel) -- one-table preparation
+  DevBuf kept;      // uint32[N_sel]: slots of the local voxels that survive the coarse-cell filter
+  DevBuf irr;       // irregular-point list (IrrEntry)
   DevBuf ta_slots, ta_list;  // coarse table
   DevBuf tb_slots, tb_list;  // fine table
   uint64_t ta_cap = 0, tb_cap = 0;
@@ -121,7 +135,8 @@ struct Workspace {
   DevBuf lv_cnt, lv_off, lv_cursor, lv_gid;  // per local voxel
   DevBuf sorted_pix[2], sorted_gid;
   DevBuf sel_bracket;  // scratch of the one-pass percentile select
-  int64_t hint_n_occ = 0;  // most distinct voxels any collected fuse call on this device had (growth heuristic)
+  int64_t hint_n_occ = 0;  // most distinct voxels any collected fuse call on this device had (growth heuristic, table prefix)
+  double hint_vs = 0.0;    // voxel size of the calls the hint comes from (0: unknown)
   // The accumulate kernel of a (voxel-sorted, device-resident) fuse call runs on this side stream, so that the
   // preparation kernels of the NEXT call -- queued on the caller's stream -- overlap it.  The sorted entry lists
   // are double-buffered; ev_acc_done[b] marks the end of the last accumulate that read sorted_pix[b].

@@ -145,6 +145,10 @@ def check(status: int) -> None:
         raise _EXC.get(status, RuntimeError)(f"libvsm[{status}]: {last_error()}")
 
 
+DEFAULT_PREP_VARIANT = 13  # csrc/fuse.cu g_prep_variant
+DEFAULT_SELECT_MODE = 0    # 0 = the library's default (deferred percentile box)
+
+
 def set_option(key: str, value: int) -> None:
     check(lib.vsm_set_option(key.encode(), int(value)))
 
