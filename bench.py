@@ -69,6 +69,9 @@ def parse_args():
                     help="N>1, main workload: submaps per exchange round (0: one exchange at the end -- every submap of config 2 sees "
                          "the same room, so rounds would push the same voxels again and again; measured 29.4 ms per step in rounds of "
                          "5 against 23.9 ms with one exchange at N=2)")
+    ap.add_argument("--sm-partition", default="auto",
+                    help="SM partition (CUDA green contexts): 'off', a number of SMs for the preparation kernels, or 'auto' "
+                         "(default): a few splits are timed before the warm-up and the fastest is kept")
     ap.add_argument("--traj-round-submaps", type=int, default=5, help="N>1, long trajectory: submaps per exchange round")
     ap.add_argument("--traj-submaps", type=int, default=200, help="submaps of the long-trajectory block (configs[2]); 0: skip")
     ap.add_argument("--traj-room", default="8,6,3", help="room size (m) of the long-trajectory corridor, one room per submap")
@@ -82,6 +85,7 @@ def parse_args():
     ap.add_argument("--query", action="store_true", help="also report query latency on the built map")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the two secondary measurements (text-query latency at 10 M voxels, per-frame streaming latency)")
+    ap.add_argument("--only-traj", action="store_true", help="of the secondary measurements, run the long trajectory only")
     ap.add_argument("--query-voxels", type=float, default=10e6)
     return ap.parse_args()
 
@@ -758,7 +762,27 @@ def long_trajectory(args, dev, rank, world):
         if world > 1:
             return vdist.build_sharded_streaming(sub_gm, vs, K, round_capacity=cap_round, owner_capacity=cap_owner,
                                                  timings=timings, profile=True)
-        m = sub_gm.build_semantic_voxel_map(vs, capacity_hint=cap_owner, profile=True)
+        # build_semantic_voxel_map, taken apart to time its phases (host clock, device synchronised at each mark)
+        from vsm import voxel_map as vm
+        from vsm.map import wrap_device_map
+        marks = [time.perf_counter()]
+
+        def mark():
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
+
+        code = N.BF16 if args.emb_dtype == "bf16" else N.F32
+        dm = vm.DeviceVoxelMap(vs, d, code, capacity=int(cap_owner or (1 << 18)), device=dev)
+        mark()
+        dm, fused, names = sub_gm.fuse_into_device_map(vs, 1, True, True, None, None, True, dm=dm)
+        mark()
+        dm.finalize()
+        mark()
+        m = wrap_device_map(dm, fused, names, vs, True, False)
+        mark()
+        if timings is not None:
+            timings["phases_ms"] = {k: round(1e3 * (marks[i + 1] - marks[i]), 2)
+                                    for i, k in enumerate(("create_map", "fuse_calls", "finalize", "wrap"))}
         return m, sub_gm.last_build_stats
 
     # warm-up on the first 2 rounds' worth of submaps: warms the pools and measures voxels per submap
@@ -800,6 +824,7 @@ def long_trajectory(args, dev, rank, world):
         dist.barrier()
     torch.cuda.synchronize()
     timings = {}
+    ctr0 = {k: N.get_counter(k) for k in ("select_misses", "capacity_retries", "early_collects", "table_retries")}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
@@ -837,10 +862,11 @@ def long_trajectory(args, dev, rank, world):
                     "exchange_GB_per_gpu": float(sent.item()) / world * 1e-9,
                     "invariants": inv, "phases_ms_rank0": timings.get("phases_ms")})
     prof = gm.last_profile or {}
-    out.update({"fuse_calls_ms": prof.get("fuse_ms"), "accumulate_ms": prof.get("accumulate_ms")})
+    out.update({"fuse_calls_ms": prof.get("fuse_ms"), "accumulate_ms": prof.get("accumulate_ms"),
+                "retries": {k: N.get_counter(k) - v for k, v in ctr0.items()}})
     out.update({"voxels_per_submap": int(vox_per_submap), "new_voxels_per_submap": int(new_per_submap), "owner_capacity": int(cap_owner)})
     if world == 1:
-        out.update({"submaps": len(mine), "submaps_per_gpu": len(mine), "ms": ms, "wall_ms": 1e3 * wall,
+        out.update({"phases_ms": timings.get("phases_ms"), "submaps": len(mine), "submaps_per_gpu": len(mine), "ms": ms, "wall_ms": 1e3 * wall,
                     "points_fused": int(n_fused), "points_per_s": n_fused / (ms * 1e-3), "voxels": int(m._dm.num_voxels),
                     "note": None if len(mine) == total else f"{len(mine)} of {total} submaps: what one GPU's memory holds as ONE map"})
     del m, gm, pool
@@ -932,6 +958,54 @@ def main():
     # maps alternate (libvsm parks a destroyed map and hands it to the next vsm_map_create).  A warm-up that dropped
     # its map at once would leave the second of the two to be created -- allocated, grown -- inside the timed region.
     m = None
+    for _ in range(2):
+        m, stats = step()
+    # ---- SM partition: preparation kernels of call i+1 beside the accumulate kernel of call i ------------------------
+    def set_partition(prep_sms):
+        N.set_option("green_prep_sms", int(prep_sms))
+        N.set_option("acc_ctas_per_sm", 3 if prep_sms else 2)
+
+    def timed_builds(n):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        acc = 0.0
+        for _ in range(n):
+            step()
+            acc += gm.last_profile["accumulate_ms"] / max(gm.last_profile["accumulate_launches"], 1)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n, acc / n
+
+    # One split is tried against none: 64 of the 148 SMs for the preparation kernels measured fastest (56: 17.9, 64: 17.0,
+    # 72: 17.4 ms per step; none: 20.1).  Trying several splits in one process is avoided on purpose: every partition
+    # brings two more streams, and past the device's hardware connections (CUDA_DEVICE_MAX_CONNECTIONS) streams share
+    # queues -- with three partitions created, later host-driven phases (finalisation of a 17 M-voxel map) ran 10-20x
+    # slower even after the partitions were gone.
+    CANDS = (0, 64)
+    partition = {"prep_sms": 0, "mode": args.sm_partition}
+    if args.sm_partition == "auto":
+        tuned = {}
+        for cand in CANDS:
+            try:
+                set_partition(cand)
+                timed_builds(1)
+                tuned[cand] = timed_builds(2)
+            except Exception as e:  # noqa: BLE001 -- e.g. a driver without green contexts: stay unpartitioned
+                tuned[cand] = (float("inf"), float("inf"))
+                partition["error"] = repr(e)
+        t_choice = torch.tensor([tuned[c][0] for c in CANDS], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_choice, op=dist.ReduceOp.MAX)  # every rank takes the same split
+        best = CANDS[int(torch.argmin(t_choice).item())]
+        if t_choice.min().item() > 0.97 * t_choice[0].item():
+            best = 0  # within noise of the plain launch order: keep it
+        partition.update({"prep_sms": best, "tuned_ms_per_step": {str(c): round(float(t_choice[i]), 3) for i, c in enumerate(CANDS)},
+                          "accumulate_ms_alone": round(tuned[0][1], 4)})
+        set_partition(best)
+    elif args.sm_partition != "off":
+        partition["prep_sms"] = int(args.sm_partition)
+        set_partition(partition["prep_sms"])
     for _ in range(n_warm):
         m, stats = step()
     n_fused_step = sum(s["n_fused"] for s in stats)
@@ -968,6 +1042,7 @@ def main():
     step_ms = [step_events[i].elapsed_time(step_events[i + 1]) for i in range(len(step_events) - 1)]
     launches = N.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    set_partition(0)  # the other measurements below (end-to-end arm, long trajectory, queries) run unpartitioned
 
     t = torch.tensor([elapsed_ms, float(points)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -1001,9 +1076,14 @@ def main():
                 "peak_source": peak_src,
                 "accumulate_ms_per_launch": prof["accumulate_ms"] / max(prof["accumulate_launches"], 1),
                 "accumulate_share_of_step": prof["accumulate_ms"] * (1.0 if world == 1 else 1.0) / max(elapsed_ms, 1e-9),
+                "sm_partition": partition,
                 "fuse_calls_GBps": fuse_bytes_step * args.steps / max(prof["fuse_ms"], 1e-9) * 1e-6,
                 "fuse_calls_frac": fuse_bytes_step * args.steps / max(prof["fuse_ms"], 1e-9) * 1e-6 / peak}
 
+    if partition.get("accumulate_ms_alone"):
+        # the kernel on the whole device (timed while the partition was being chosen, same builds): what the kernel
+        # itself reaches; `frac` above is what it reaches inside the timed region, next to the preparation kernels
+        roofline["frac_alone"] = roofline["algorithmic_bytes_per_launch"] / (partition["accumulate_ms_alone"] * 1e-3) * 1e-9 / peak
     # ---- query latency (optional, reported inside config) ---------------------------
     extra = {}
     if args.query:
@@ -1119,7 +1199,7 @@ def main():
 
     # ---- secondary measurements (BASELINE configs[3] and configs[4]), rank 0's GPU only, outside the timed step ----
     secondary = None
-    if rank == 0 and not args.no_extras:
+    if rank == 0 and not args.no_extras and not args.only_traj:
         try:
             N.lib.vsm_map_cache_release()
             torch.cuda.empty_cache()
@@ -1141,7 +1221,7 @@ def main():
     # ---- sharded text query (N > 1): every rank owns a shard of `query_voxels` voxels, prompts are scored per shard,
     # P x k candidates are all-gathered and merged (vsm.dist.ShardedVoxelMap); weak scaling of BASELINE configs[3]
     sharded_query = None
-    if world > 1 and not args.no_extras:
+    if world > 1 and not args.no_extras and not args.only_traj:
         try:
             sharded_query = sharded_query_latency(args, dev, rank, world)
         except Exception as e:

@@ -19,7 +19,9 @@ variant = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 sel = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 N.set_option("prep_variant", variant)
 N.set_option("select_mode", sel)
-print("prep_variant", variant, "select_mode", sel)
+ring = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+N.set_option("acc_ring", ring)
+print("prep_variant", variant, "select_mode", sel, "acc_ring", ring)
 gm = vsm.GraphMap()
 for i in range(n_sub):
     d = synth_device.make_submap_device(1234, i, first_frame_number=32 * i)
@@ -49,7 +51,7 @@ def run(vs, reps=4):
 print(f"{'voxel':>6} {'prep SMs':>9} {'acc CTAs/SM':>12} {'ms/submap':>10}  signature (voxels, points, sum|f|)")
 for vs in sizes:
     ref = None
-    for prep_sms, ctas in ((0, 2), (48, 3), (56, 3), (64, 3), (72, 3), (80, 3), (88, 3), (64, 2), (72, 2), (72, 4), (-1, 2)):
+    for prep_sms, ctas in ((0, 2), (48, 3), (56, 3), (64, 3), (72, 3), (80, 3), (88, 3), (96, 3), (-1, 2)):
         if prep_sms < 0:  # overlap on two plain streams, no partition (round-1 experiment)
             N.set_option("green_prep_sms", 0)
             N.set_option("overlap", 1)
@@ -70,3 +72,4 @@ N.set_option("overlap", 0)
 N.set_option("acc_ctas_per_sm", 2)
 N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
 N.set_option("select_mode", 0)
+N.set_option("acc_ring", 1)

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <vector>
 
@@ -43,8 +44,25 @@ static cudaStream_t alloc_stream_for(int dev) {
   return streams[dev];
 }
 
+static double host_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool host_trace() {
+  static const bool on = getenv("VSM_TRACE") && getenv("VSM_TRACE")[0] == '1';
+  return on;
+}
+
 int DevBuf::ensure(size_t need, cudaStream_t s, size_t keep_bytes, double slack) {
   if (need <= bytes && p != nullptr) return VSM_OK;
+  const double t_begin = host_trace() ? host_ms() : 0.0;
+  struct Report {
+    double t0;
+    size_t need, keep;
+    ~Report() {
+      if (t0 > 0.0 && host_ms() - t0 > 1.0)
+        fprintf(stderr, "[vsm trace] allocation of %.1f MB (keeping %.1f MB) took %.2f ms\n", need * 1e-6, keep * 1e-6, host_ms() - t0);
+    }
+  } report{t_begin, need, keep_bytes};
   if (need == 0) need = 16;
   size_t want = (size_t)((double)need * slack);
   want = (want + 255) & ~(size_t)255;

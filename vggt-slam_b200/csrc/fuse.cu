@@ -1668,6 +1668,181 @@ __global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_kernel(Acc
   if (CHECK && n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
 }
 
+// ---- the same accumulate with the rows staged through shared memory (cp.async) --------------------------------
+// accumulate_kernel keeps U = 4 rows of a warp in REGISTERS while they are on their way from HBM: 96 KB in flight per
+// SM at three CTAs, which needs every SM of the device to cover HBM's latency x bandwidth.  Here every lane copies its
+// 16-byte pieces of the next DEPTH rows straight into a ring in shared memory (cp.async.cg, no register in between) and
+// adds row r while rows r+1 .. r+DEPTH are in flight; a lane only ever reads the bytes it copied itself, so the ring
+// needs no barrier, only cp.async.wait_group.  With ~190 KB in flight per SM the kernel saturates HBM on a PART of the
+// SMs -- which is what lets the next call's preparation kernels run beside it on the rest (SM partitions, above).
+// Voxel-sorted lists with full rows only (d a multiple of 32 vectors); check-only entries as in accumulate_kernel.
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t smem_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_addr));
+  return v;
+}
+
+template <bool BF16, int VPL, bool CHECK, int DEPTH>
+__global__ void __launch_bounds__(256, 2) accumulate_ring_kernel(AccArgs a) {
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr uint32_t ROW = (uint32_t)VPL * 512u;  // bytes per row
+  extern __shared__ __align__(16) uint8_t ring_smem[];
+  if (a.ctr->abort) return;
+  const int lane = lane_id();
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_entries = (int64_t)a.ctr->n_fused;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const uint8_t* emb0 = a.emb - a.pix_base * a.row_bytes + (size_t)lane * 16;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  // this lane's 16-byte column of the warp's ring
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring_smem) + (threadIdx.x >> 5) * (uint32_t)DEPTH * ROW + (uint32_t)lane * 16u;
+  unsigned n_bad = 0;
+
+  float acc[VPL * EPV];
+#pragma unroll
+  for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      bool ok = true;
+      if (CHECK) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);  // NaN iff some accumulator is Inf/NaN
+        ok = !__any_sync(0xffffffffu, t != t);
+        if (!ok && lane == 0) ++n_bad;
+      }
+      if (ok) {
+        float* dst = vsum0 + (size_t)cur * d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int q = 0; q < EPV / 4; ++q)
+            red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1], acc[v * EPV + 4 * q + 2],
+                       acc[v * EPV + 4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  };
+
+  // entries of the chunk being added (C) and of the next one (N): the copies run up to DEPTH <= 32 rows ahead
+  auto load_entries = [&](int64_t chunk, uint32_t& pix, int& gid) {
+    pix = 0u;
+    gid = -1;
+    if (chunk < n_chunks) {
+      const int64_t i = (chunk << 5) + lane;
+      if (i < n_entries) {
+        const unsigned long long e = a.entries[i];
+        pix = (uint32_t)e;
+        gid = (int)(uint32_t)(e >> 32);
+        if (a.emb_index != nullptr) pix = (uint32_t)a.emb_index[pix];
+      }
+    }
+  };
+  uint32_t pixC, pixN;
+  int gidC, gidN;
+  load_entries(warp, pixC, gidC);
+  load_entries(warp + n_warps, pixN, gidN);
+  auto issue = [&](uint32_t pix, int gid, int src_lane, uint32_t slot) {
+    const uint32_t pj = __shfl_sync(0xffffffffu, pix, src_lane);
+    const int gj = __shfl_sync(0xffffffffu, gid, src_lane);
+    if (gj >= 0) {
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) cp_async_16(ring0 + slot * ROW + (uint32_t)v * 512u, row + v * 512);
+    }
+    cp_async_commit();  // one group per row, empty or not: wait_group counts rows
+  };
+  // prologue: the first DEPTH rows of the first chunk
+#pragma unroll
+  for (int r = 0; r < DEPTH; ++r) issue(pixC, gidC, r, (uint32_t)r);
+  uint32_t slot = 0;
+  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      cp_async_wait<DEPTH - 1>();  // row (chunk, j) has landed
+      const int gj = __shfl_sync(0xffffffffu, gidC, j);
+      uint4 rows[VPL];
+      if (gj >= 0) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) rows[v] = lds_v4(ring0 + slot * ROW + (uint32_t)v * 512u);
+      }
+      // the slot is free again: row j + DEPTH goes into it
+      const int jj = j + DEPTH;
+      if (jj < 32)
+        issue(pixC, gidC, jj, slot);
+      else
+        issue(pixN, gidN, jj - 32, slot);
+      slot = slot + 1u == (uint32_t)DEPTH ? 0u : slot + 1u;
+      if (gj >= 0) {
+        if (gj != cur) {
+          flush();
+          cur = gj;
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[v]);
+      }
+    }
+    pixC = pixN;
+    gidC = gidN;
+    load_entries(chunk + 2 * n_warps, pixN, gidN);
+  }
+  cp_async_wait<0>();
+  flush();
+
+  if (CHECK) {
+    // check-only entries sit behind the fused ones: one warp per row, test the raw values
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      if (a.emb_index != nullptr) pj = (uint32_t)a.emb_index[pj];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+    if (n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+  }
+}
+
+// Measured on B200 (config 2, 8 submaps): 1.08 ms per submap against 1.01 ms with accumulate_kernel on the whole device,
+// 0.95 against 0.90 with 64 SMs set aside for the preparation kernels, and no better on 60 SMs -- twice the bytes in
+// flight per SM do not buy bandwidth on fewer SMs here.  Kept as an option ("acc_ring"), off by default.
+std::atomic<int> g_acc_ring{0};
+
+template <bool BF16, int VPL>
+static int launch_accumulate_ring(const AccArgs& a, bool check, cudaStream_t s, int n_sm) {
+  // ring depth: ~96 KB of rows per CTA of 8 warps, two CTAs per SM
+  constexpr int DEPTH = VPL == 1 ? 24 : (VPL == 2 ? 12 : (VPL == 4 ? 6 : 3));
+  constexpr size_t smem = (size_t)8 * DEPTH * VPL * 512;
+  static const cudaError_t opt0 = cudaFuncSetAttribute(accumulate_ring_kernel<BF16, VPL, false, DEPTH>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const cudaError_t opt1 = cudaFuncSetAttribute(accumulate_ring_kernel<BF16, VPL, true, DEPTH>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  VSM_CUDA(opt0);
+  VSM_CUDA(opt1);
+  const int grid = (n_sm > 0 ? n_sm : sm_count()) * 2;
+  if (check)
+    accumulate_ring_kernel<BF16, VPL, true, DEPTH><<<grid, 256, smem, s>>>(a);
+  else
+    accumulate_ring_kernel<BF16, VPL, false, DEPTH><<<grid, 256, smem, s>>>(a);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
 template <bool BF16, int VPL>
 static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaStream_t s, int n_sm) {
   const int block = 256;
@@ -1680,6 +1855,7 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)sm_count() * 6);
   }
   const bool full = a.nvec == 32 * VPL;
+  if (sorted && full && a.emb_index == nullptr && g_acc_ring.load()) return launch_accumulate_ring<BF16, VPL>(a, check, s, n_sm);
   if (sorted && full && a.emb_index != nullptr) {
     if (check)
       accumulate_kernel<BF16, VPL, true, true, true, true><<<grid, block, 0, s>>>(a);
@@ -1946,25 +2122,31 @@ static bool driver_fn(const char* name, F* out) {
   return true;
 }
 
-static void green_teardown(Workspace* ws) {
-  CUresult (*ctx_destroy)(CUgreenCtx) = nullptr;
+static void green_deactivate(Workspace* ws) {
   for (int i = 0; i < 2; ++i) {
-    if (ws->green_stream[i]) cudaStreamDestroy(ws->green_stream[i]);
+    ws->green_ctx[i] = nullptr;
     ws->green_stream[i] = nullptr;
+    ws->green_sms[i] = 0;
   }
-  if ((ws->green_ctx[0] || ws->green_ctx[1]) && driver_fn("cuGreenCtxDestroy", &ctx_destroy))
-    for (int i = 0; i < 2; ++i)
-      if (ws->green_ctx[i]) ctx_destroy(reinterpret_cast<CUgreenCtx>(ws->green_ctx[i]));
-  ws->green_ctx[0] = ws->green_ctx[1] = nullptr;
-  ws->green_sms[0] = ws->green_sms[1] = 0;
   ws->green_on = false;
 }
 
 // Splits the device's SMs into a preparation partition of >= prep_sms SMs (rounded up to the hardware's granularity,
-// 8 on sm_100) and an accumulate partition of the rest; one stream in each.  Needs the workspace lock and an idle device.
+// 8 on sm_100) and an accumulate partition of the rest; one stream in each.  Needs the workspace lock and an idle
+// device.  Partitions are created once per requested size and kept (prep_sms = 0 only deactivates).
 static int green_setup(Workspace* ws, int dev, int prep_sms) {
-  green_teardown(ws);
+  green_deactivate(ws);
   if (prep_sms <= 0) return VSM_OK;
+  for (const Workspace::GreenPart& gp : ws->green_parts)
+    if (gp.requested == prep_sms) {
+      for (int i = 0; i < 2; ++i) {
+        ws->green_ctx[i] = gp.ctx[i];
+        ws->green_stream[i] = gp.stream[i];
+        ws->green_sms[i] = gp.sms[i];
+      }
+      ws->green_on = true;
+      return VSM_OK;
+    }
   CUresult (*dev_get)(CUdevice*, int) = nullptr;
   CUresult (*get_res)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
   CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
@@ -1985,26 +2167,31 @@ static int green_setup(Workspace* ws, int dev, int prep_sms) {
     set_error("green contexts: cannot split %d SMs off the device (CUresult %d)", prep_sms, (int)r);
     return VSM_E_INVALID;
   }
+  Workspace::GreenPart gp{};
+  gp.requested = prep_sms;
   for (int i = 0; i < 2; ++i) {
     CUdevResourceDesc desc;
     CUgreenCtx ctx = nullptr;
     CUstream st = nullptr;
     r = gen_desc(&desc, &part[i], 1);
     if (r == CUDA_SUCCESS) r = ctx_create(&ctx, desc, cu_dev, CU_GREEN_CTX_DEFAULT_STREAM);
-    if (r == CUDA_SUCCESS) {
-      ws->green_ctx[i] = ctx;
-      r = stream_create(&st, ctx, CU_STREAM_NON_BLOCKING, 0);
-    }
+    if (r == CUDA_SUCCESS) r = stream_create(&st, ctx, CU_STREAM_NON_BLOCKING, 0);
     if (r != CUDA_SUCCESS) {
       set_error("green contexts: cannot create partition %d (CUresult %d)", i, (int)r);
-      green_teardown(ws);
-      return VSM_E_CUDA;
+      return VSM_E_CUDA;  // (a context created for i = 0 stays allocated: the failure is not expected to repeat)
     }
-    ws->green_stream[i] = reinterpret_cast<cudaStream_t>(st);
-    ws->green_sms[i] = (int)part[i].sm.smCount;
+    gp.ctx[i] = ctx;
+    gp.stream[i] = reinterpret_cast<cudaStream_t>(st);
+    gp.sms[i] = (int)part[i].sm.smCount;
   }
   if (!ws->ev_fork) VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
   if (!ws->ev_prep_join) VSM_CUDA(cudaEventCreateWithFlags(&ws->ev_prep_join, cudaEventDisableTiming));
+  ws->green_parts.push_back(gp);
+  for (int i = 0; i < 2; ++i) {
+    ws->green_ctx[i] = gp.ctx[i];
+    ws->green_stream[i] = gp.stream[i];
+    ws->green_sms[i] = gp.sms[i];
+  }
   ws->green_on = true;
   return VSM_OK;
 }
@@ -2837,6 +3024,10 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
     g_range_policy = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_ring") && (value == 0 || value == 1)) {
+    g_acc_ring = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "small_tables") && (value == 0 || value == 1)) {

@@ -153,9 +153,18 @@ struct Workspace {
   // `green_sms[1]`, so that the HBM-bound accumulate of call i and the latency / issue-bound preparation of call
   // i+1 run side by side without competing for registers and warp slots on the same SM.
   bool green_on = false;
-  void* green_ctx[2] = {nullptr, nullptr};  // CUgreenCtx
+  void* green_ctx[2] = {nullptr, nullptr};  // CUgreenCtx of the active partition
   cudaStream_t green_stream[2] = {nullptr, nullptr};  // [0] preparation, [1] accumulate
   int green_sms[2] = {0, 0};
+  // every partition ever asked for stays alive (a handful of contexts): switching between splits, or off and on
+  // again, creates and destroys nothing
+  struct GreenPart {
+    int requested;
+    void* ctx[2];
+    cudaStream_t stream[2];
+    int sms[2];
+  };
+  std::vector<GreenPart> green_parts;
   cudaEvent_t ev_fork = nullptr, ev_prep_join = nullptr;
 };
 Workspace* workspace_for_device(int device);
