@@ -939,6 +939,7 @@ def main():
 
     cap_hint = [1 << 18]
     round_cap = [1 << 18]
+    dist_transport = ["auto"]
 
     def step():
         if world > 1 and args.round_submaps > 0:
@@ -946,7 +947,7 @@ def main():
                                                      owner_capacity=cap_hint[0], profile=True)
             round_cap[0] = max(round_cap[0], int(1.3 * max(s["n_submap_voxels"] for s in stats) * args.round_submaps))
         elif world > 1:
-            m, stats = vdist.build_sharded(gm, args.voxel_size, capacity_hint=cap_hint[0], profile=True)
+            m, stats = vdist.build_sharded(gm, args.voxel_size, capacity_hint=cap_hint[0], profile=True, transport=dist_transport[0])
         else:
             m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], profile=True)
             stats = gm.last_build_stats
@@ -990,11 +991,15 @@ def main():
     CANDS = (0, 64)
     partition = {"prep_sms": 0, "mode": args.sm_partition}
     if args.sm_partition == "auto" and world > 1:
-        # On several GPUs the partition stays off: the fuse calls gain as on one GPU (16.5 instead of 19.4 ms per step
-        # at N=2) but steps then stall at random for 35-120 ms (10 steps at N=2: 20.2 19.7 113 109 56 143 93 143 19.8
-        # 19.7 ms) -- kernels of the exchange, the finalisation and NCCL run in the primary context beside the green
-        # contexts; not understood well enough to ship.  `--sm-partition 64` forces it.
-        partition["note"] = "off at N > 1 (random stalls beside NCCL / peer kernels, see bench.py)"
+        # On several GPUs the partition goes with the COLLECTIVE exchange (pack -> NCCL all-to-all -> merge).  With the
+        # one-sided peer-memory exchange the fuse calls gain as on one GPU (16.5 instead of 19.4 ms per step at N=2) but
+        # steps then stall at random for 35-120 ms (10 steps at N=2: 20.2 19.7 113 109 56 143 93 143 19.8 19.7 ms);
+        # with the collective exchange every step takes 20.8-21.3 ms (peer exchange without the partition: 22.5-22.9).
+        # Kernels that touch IPC-mapped peer memory beside green contexts: not understood well enough to ship.  This
+        # workload exchanges 0.3 GB per step; the long-trajectory block below keeps the peer exchange (no partition).
+        partition.update({"prep_sms": 64, "exchange": "collective (NCCL all-to-all) beside the partition"})
+        dist_transport[0] = "collective"
+        set_partition(64)
     elif args.sm_partition == "auto":
         tuned = {}
         for cand in CANDS:
@@ -1017,6 +1022,8 @@ def main():
     elif args.sm_partition != "off":
         partition["prep_sms"] = int(args.sm_partition)
         set_partition(partition["prep_sms"])
+        if world > 1 and os.environ.get("VSM_PEER_DISABLE") != "1" and os.environ.get("VSM_BENCH_PEER_WITH_PARTITION") != "1":
+            dist_transport[0] = "collective"
     for _ in range(n_warm):
         m, stats = step()
     n_fused_step = sum(s["n_fused"] for s in stats)
@@ -1256,6 +1263,12 @@ def main():
     if rank == 0:
         cfg = workload_config(args, world)
         cfg.update({"voxels": int(n_vox), "points_fused_per_step_per_gpu": int(n_fused_step)})
+        if world > 1 and dist_transport[0] == "collective":
+            cfg["parallelism"] = (f"submaps sharded over {world} GPU(s), voxels owned by key hash: packed by owner on the device, one NCCL "
+                                  "all-to-all per array, merged by the owner (the one-sided peer-memory exchange is used without the "
+                                  "SM partition and by the long-trajectory block)")
+        cfg["sm_partition"] = ("64 SMs for the preparation kernels of call i+1, 84 for the accumulate kernel of call i (CUDA green contexts)"
+                               if partition.get("prep_sms") else "off")
         cfg.update(extra)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
