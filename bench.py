@@ -465,25 +465,16 @@ def workload_config(args, world):
 # secondary measurements
 # ---------------------------------------------------------------------------
 def query_latency(args, dev):
-    """BASELINE configs[3]: V voxels x P prompts, top-10, whole vsm_query call (tensor-core engine + exact
-    re-scoring), CUDA events, 5 calls after 2 warm-ups.  The V x 512 fp32 sums (20 GB at 10 M) are far larger than L2."""
+    """BASELINE configs[3]: V voxels x P prompts, top-10, whole vsm_query call (thresholds from nested samples, tensor-core
+    pass, exact re-scoring, top-k), CUDA events, 5 calls after 2 warm-ups, for engine 2 (TF32 on the fp32 sums: V x d x 4
+    bytes per call, 20 GB at 10 M voxels) and engine 3 (bf16 shadow: V x d x 2 bytes); both must return the indices of
+    the exact engine 1 (checked here on the first prompts).  Sizes: 10 M (args.query_voxels), 30 M and 70 M voxels on one
+    GPU -- the last without the shadow, which would not fit beside 143 GB of sums."""
     import torch
     from vsm import _native as N
     from vsm import voxel_map as vm
 
-    V, d, k = int(args.query_voxels), args.dim, 10
-    g = torch.Generator(device=dev)
-    g.manual_seed(1)
-    feats = torch.empty((V, d), dtype=torch.float32, device=dev)
-    for r0 in range(0, V, 1 << 20):
-        r1 = min(V, r0 + (1 << 20))
-        x = torch.randn((r1 - r0, d), dtype=torch.float32, device=dev, generator=g)
-        feats[r0:r1] = x / x.norm(dim=1, keepdim=True) * (0.3 + 0.7 * torch.rand((r1 - r0, 1), device=dev, generator=g))
-    centers = torch.rand((V, 3), dtype=torch.float32, device=dev, generator=g) * 1000.0
-    dm = vm.DeviceVoxelMap(0.05, d, N.F32, capacity=V)
-    dm.load_dense(centers, feats)
-    del feats, centers
-    torch.cuda.empty_cache()
+    d, k = args.dim, 10
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -491,27 +482,75 @@ def query_latency(args, dev):
     except Exception:
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    out = {"voxels": V, "dim": d, "top_k": k, "bytes_per_call": V * d * 4, "points": []}
-    rng = np.random.default_rng(0)
-    for P in (1, 64, 256):
-        q = rng.normal(size=(P, d)).astype(np.float32)
-        q /= np.linalg.norm(q, axis=1, keepdims=True)
-        qt = torch.from_numpy(q).to(dev)
-        for _ in range(2):
-            dm.query(qt, top_k=k)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(5):
-            dm.query(qt, top_k=k)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        gbs = V * d * 4 / ms * 1e-6
-        out["points"].append({"prompts": P, "ms": ms, "hbm_GBps": gbs, "hbm_frac": gbs / hbm,
-                              "TFLOPs_tf32": 2.0 * V * d * P / ms * 1e-9})
-    dm.close()
-    N.lib.vsm_map_cache_release()
-    torch.cuda.empty_cache()
+
+    def one_size(V, engines, prompts):
+        g = torch.Generator(device=dev)
+        g.manual_seed(1)
+        dm = vm.DeviceVoxelMap(0.05, d, N.F32, capacity=V)
+        import ctypes as C
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N.check(N.lib.vsm_map_load_begin(dm._h, V, stream))
+        for r0 in range(0, V, 1 << 20):  # rows generated and loaded block by block: nothing of size V x d beside the map
+            r1 = min(V, r0 + (1 << 20))
+            x = torch.randn((r1 - r0, d), dtype=torch.float32, device=dev, generator=g)
+            x = x / x.norm(dim=1, keepdim=True) * (0.3 + 0.7 * torch.rand((r1 - r0, 1), device=dev, generator=g))
+            c = torch.rand((r1 - r0, 3), dtype=torch.float32, device=dev, generator=g) * 1000.0
+            N.check(N.lib.vsm_map_load_rows(dm._h, r0, r1 - r0, C.c_void_p(c.data_ptr()), C.c_void_p(x.data_ptr()), stream))
+            torch.cuda.synchronize()
+        dm.finalize()
+        torch.cuda.empty_cache()
+        out = {"voxels": V, "dim": d, "top_k": k, "bytes_per_call": V * d * 4, "bytes_per_call_bf16_shadow": V * d * 2, "points": []}
+        rng = np.random.default_rng(0)
+        for P in prompts:
+            q = rng.normal(size=(P, d)).astype(np.float32)
+            q /= np.linalg.norm(q, axis=1, keepdims=True)
+            qt = torch.from_numpy(q).to(dev)
+            pt = {"prompts": P}
+            ref = dm.query(qt[: min(P, 8)], top_k=k, engine=1)[0]
+            for eng in engines:
+                for _ in range(2):
+                    got = dm.query(qt, top_k=k, engine=eng)[0]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    dm.query(qt, top_k=k, engine=eng)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                agree = bool(torch.equal(got[: ref.shape[0]], ref))
+                if eng == 2:
+                    gbs = V * d * 4 / ms * 1e-6
+                    pt.update({"ms": ms, "hbm_GBps": gbs, "hbm_frac": gbs / hbm, "TFLOPs_tf32": 2.0 * V * d * P / ms * 1e-9,
+                               "equals_exact_engine": agree})
+                else:
+                    gbs = V * d * 2 / ms * 1e-6
+                    pt["bf16_shadow"] = {"ms": ms, "hbm_GBps": gbs, "hbm_frac": gbs / hbm, "TFLOPs_bf16": 2.0 * V * d * P / ms * 1e-9,
+                                         "equals_exact_engine": agree}
+            out["points"].append(pt)
+        out["fallbacks_to_exact_engine"] = dm.query_stats()["fallbacks"]
+        dm.close()
+        N.lib.vsm_map_cache_release()
+        N.lib.vsm_pool_trim()  # the next size needs the room the pool is holding
+        torch.cuda.empty_cache()
+        return out
+
+    out = one_size(int(args.query_voxels), (2, 3), (1, 64, 256))
+    sweep = []
+    for V, engines in ((30_000_000, (2, 3)), (70_000_000, (2,))):
+        if int(args.query_voxels) != 10_000_000:
+            break  # the sweep belongs to the default run
+        try:
+            need = V * d * 4 * (1.5 if 3 in engines else 1.0) + 6e9
+            if torch.cuda.mem_get_info(dev)[0] < need:
+                sweep.append({"voxels": V, "skipped": "not enough free device memory"})
+                continue
+            sweep.append(one_size(V, engines, (1, 64, 256)))
+        except Exception as e:  # noqa: BLE001
+            sweep.append({"voxels": V, "error": repr(e)})
+            N.lib.vsm_map_cache_release()
+            N.lib.vsm_pool_trim()
+            torch.cuda.empty_cache()
+    out["sweep"] = sweep
     return out
 
 

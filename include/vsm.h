@@ -141,6 +141,9 @@ VSM_API int vsm_map_create(const vsm_config* cfg, vsm_map** out);
  * vsm_map_cache_release frees the parked maps of every device. */
 VSM_API int vsm_map_destroy(vsm_map* m);
 VSM_API int vsm_map_cache_release(void);
+/* libvsm keeps every block it has freed in the current device's stream-ordered pool (re-creating maps and scratch costs
+ * microseconds); this hands the unused ones back to the device, e.g. before another allocator needs the room */
+VSM_API int vsm_pool_trim(void);
 VSM_API int vsm_map_clear(vsm_map* m, void* stream);
 VSM_API int vsm_map_reserve(vsm_map* m, int64_t voxel_capacity, void* stream);
 /* room for `entries` contributor-log entries (one per fuse call and voxel, or per received contributor record) */
@@ -251,13 +254,19 @@ VSM_API int vsm_lookup(vsm_map* m, const float* pos_dev, int64_t M, int64_t* idx
  * scores[p, v] = features[v] . q[p]  (features = sum / count; normalize != 0 divides by ||features[v]||).
  * Returns per prompt the top-k sorted voxel indices (ties: lower index first) and float32 scores.
  * q_dev float[P*d]; idx_dev int64[P*k]; score_dev float[P*k].
- * engine: 0 = auto, 1 = exact fp32 CUDA-core kernel, 2 = tcgen05 tensor-core kernel + exact fp32 rescoring */
+ * engine: 0 = auto, 1 = exact fp32 CUDA-core kernel, 2 = tcgen05 tensor-core kernel (TF32 on the fp32 sums) + exact
+ * fp32 rescoring, 3 = the same on a bf16 shadow of the sums (tcgen05 kind::f16; half the bytes per query, +2 bytes per
+ * value of memory, built on the first query after a finalisation).  Every engine returns the same answer.
+ * vsm_set_option("query_shadow", 1) makes engine 0 choose 3 on large maps. */
 VSM_API int vsm_query(vsm_map* m, const float* q_dev, int32_t P, int32_t k, int normalize, int engine, int64_t* idx_dev,
               float* score_dev, void* stream);
 
 /* engine-2 diagnostics: longest candidate list of the last tensor-core query, and how many engine-2 queries were
  * answered by engine 1 because a candidate list overflowed */
 VSM_API int vsm_query_stats(const vsm_map* m, int64_t* last_candidates_host, int64_t* fallbacks_host);
+
+/* frees the bf16 shadow of engine 3 (it is rebuilt by the next engine-3 query) */
+VSM_API int vsm_query_shadow_release(vsm_map* m);
 
 /* ---- multi-GPU exchange (no reference counterpart) ------------- *
  * Voxels are owned by mix64(key) % world.  pack: groups this map's voxels by owner and writes

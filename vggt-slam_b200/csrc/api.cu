@@ -278,6 +278,16 @@ extern "C" int vsm_map_cache_release(void) {
   return VSM_OK;
 }
 
+extern "C" int vsm_pool_trim(void) {
+  int dev = 0;
+  cudaMemPool_t pool;
+  VSM_CUDA(cudaGetDevice(&dev));
+  VSM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  VSM_CUDA(cudaDeviceSynchronize());
+  VSM_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return VSM_OK;
+}
+
 static int map_destroy_now(vsm_map* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
@@ -287,7 +297,7 @@ static int map_destroy_now(vsm_map* m) {
                          &m->stage_pts, &m->stage_conf, &m->stage_emb[0], &m->stage_emb[1], &m->sorted_keys,
                          &m->id_of_rank, &m->rank_of_id, &m->csr_off,  &m->csr_sub,   &m->csr_mask,   &m->dense_centers,
                          &m->ck_keys,   &m->ck_val,    &m->q_cand,     &m->q_tmp,     &m->q_norm,
-                         &m->q_tc,      &m->q_tc_cand,  &m->xch_tmp,   &m->drain_report};
+                         &m->q_tc,      &m->q_tc_cand,  &m->q_shadow,  &m->xch_tmp,   &m->drain_report};
   for (auto* b : bufs) b->release();
   for (auto& f : m->fuses) f.point_gid.release();
   if (m->pinned) cudaFreeHost(m->pinned);

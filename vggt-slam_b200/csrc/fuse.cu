@@ -36,6 +36,7 @@ namespace vsm {
 constexpr uint32_t kFuseForceRadix = 1u << 30;  // internal flag: this call must use the three-pass radix select
 constexpr uint32_t kFuseForceBigTables = 1u << 28;  // internal flag: this call must use the full-size submap-local tables
 std::atomic<int> g_small_tables{1};             // "small_tables": size the submap-local tables from earlier calls
+extern std::atomic<int> g_query_shadow;          // query.cu
 std::atomic<int> g_select_mode{0};              // 0 default (= 3), 1 radix, 2 bracket in the world kernel, 3 deferred box ("select_mode")
 // preparation kernels (vsm_set_option "prep_variant"): bit 0 = a warp takes a 4x8 pixel patch instead of 32 pixels of a
 // row; bit 1 = read the frame-mask word before the atomic OR; bit 2 = select with merged one-block steps; bit 3 = one-table
@@ -3024,6 +3025,10 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "coord_range_policy") && (value == 0 || value == 1)) {
     g_range_policy = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "query_shadow") && (value == 0 || value == 1)) {
+    g_query_shadow = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "acc_ring") && (value == 0 || value == 1)) {

@@ -8,6 +8,7 @@
 // materialised -- each CTA keeps a running top-k per prompt behind a threshold and a last kernel merges the
 // per-CTA lists.  Engine 1 (this file) is exact fp32 FMA on the CUDA cores and is HBM-bound for up to ~8
 // prompts; engine 2 (query_tc.cu) runs the contraction on the tcgen05 tensor cores.
+#include <atomic>
 #include "state.cuh"
 
 namespace vsm {
@@ -291,7 +292,7 @@ static int launch_query_exact(const QueryArgs& a, int grid, size_t smem, cudaStr
 }
 
 int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_t* idx_dev, float* score_dev,
-             cudaStream_t s);  // query_tc.cu
+             cudaStream_t s, bool bf16_shadow);  // query_tc.cu
 
 int query_exact_rows(vsm_map* m, const float* q_dev, int P, int k, int normalize, uint32_t row_stride, uint32_t n_rows,
                      int64_t* idx_dev, float* score_dev, cudaStream_t s);
@@ -363,6 +364,9 @@ int query_exact_rows(vsm_map* m, const float* q_dev, int P, int k, int normalize
 
 }  // namespace vsm
 
+namespace vsm {
+std::atomic<int> g_query_shadow{0};  // "query_shadow": engine 0 (auto) uses the bf16 shadow on large maps
+}
 using namespace vsm;
 
 extern "C" int vsm_query(vsm_map* m, const float* q_dev, int32_t P, int32_t k, int normalize, int engine,
@@ -388,8 +392,12 @@ extern "C" int vsm_query(vsm_map* m, const float* q_dev, int32_t P, int32_t k, i
   cudaStream_t s = (cudaStream_t)stream;
   // engine 0 (auto): on maps of some size the tensor-core engine is faster for every P (measured on 10 M voxels:
   // 3.7 ms vs 3.9 ms at P=1, 3.8 ms vs 11 ms at P=8); small maps are latency-bound and take the simpler path
+  // engine 3: the tensor-core passes read a bf16 shadow of the sums (half the bytes, twice the tensor rate, a wider
+  // selection margin; +2 bytes per value of memory): the same answer, chosen explicitly or with "query_shadow" = 1
+  if (engine == 3 || (engine == 0 && g_query_shadow.load() && m->n_vox >= 65536 && m->d % 64 == 0 && m->d <= 1024))
+    return query_tc(m, q_dev, P, k, normalize, idx_dev, score_dev, s, true);
   if (engine == 2 || (engine == 0 && m->n_vox >= 65536 && m->d % 32 == 0 && m->d <= 1024))
-    return query_tc(m, q_dev, P, k, normalize, idx_dev, score_dev, s);
+    return query_tc(m, q_dev, P, k, normalize, idx_dev, score_dev, s, false);
   return query_exact(m, q_dev, P, k, normalize, idx_dev, score_dev, s);
 }
 

@@ -19,6 +19,7 @@
 // The result is therefore identical to engine 1 (vggt_slam/semantic_voxel.py:97-116 semantics).  If a candidate
 // list overflows, the call falls back to engine 1.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "state.cuh"
 
@@ -41,6 +42,10 @@ constexpr uint32_t kHalfBytes = kTileM * kChunkK * 4;  // 128 voxels x 32 channe
 // reads 10 explicit mantissa bits of each fp32 operand) -- Cauchy-Schwarz; the fp32 accumulation of d <= 1024 terms adds
 // less than 1e-4 ||a|| ||b||.  1.5 x 2^-9 leaves half of the bound as slack.
 constexpr float kTf32Margin = 1.5f * 0.001953125f;
+// bf16 shadow (engine 3): both operands are ROUNDED to 8 significant bits (relative error <= 2^-9 each), so
+// |a_bf . b_bf - a . b| <= sum |a_i b_i| (2 * 2^-9 + 2^-18) <= (2^-8 + 2^-18) ||a|| ||b||; 1.5 x 2^-8 again leaves half of the
+// bound as slack (and covers the fp32 accumulation, < 1e-4 ||a|| ||b||).
+constexpr float kBf16Margin = 1.5f * 0.00390625f;
 constexpr int kWarpStage = 128;  // candidates an epilogue warp stages in shared memory before one global append
 
 // TN prompts per pass.  Streamed prompt slices are re-read from L2 for every voxel tile, so a streamed tile takes
@@ -182,6 +187,28 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with BF16 inputs (kind::f16, K = 16 per instruction)
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
 // arrives on the mbarrier when all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -220,9 +247,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
   return d;
 }
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N=tile_n, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int tile_n, int tile_m = kTileM) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(tile_n >> 3) << 17) | ((uint32_t)(tile_m >> 4) << 24);
+// instruction descriptor: D=F32, A=B=TF32 (kind::tf32 format 2) or BF16 (kind::f16 format 1), both K-major, N=tile_n, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int tile_n, int tile_m = kTileM, bool bf16 = false) {
+  return (1u << 4) | ((bf16 ? 1u : 2u) << 7) | ((bf16 ? 1u : 2u) << 10) | ((uint32_t)(tile_n >> 3) << 17) |
+         ((uint32_t)(tile_m >> 4) << 24);
 }
 
 struct TcArgs {
@@ -238,13 +266,15 @@ struct TcArgs {
   unsigned long long* pairs;  // flat candidate list: (prompt << 32 | voxel id), in arrival order
   uint32_t* pair_cnt;         // [1] entries appended (can exceed pair_cap: overflow)
   uint32_t pair_cap;
-  int n_kchunks;         // d / 32
+  int n_kchunks;         // 128-byte slices of a row: d / 32 (fp32 sums) or d / 64 (bf16 shadow)
+  float margin;          // kTf32Margin or kBf16Margin
 };
 
-template <int TN>
+template <int TN, bool BF>
 __global__ void __launch_bounds__(Cfg<TN>::kThreads, 1)
 query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   using C = Cfg<TN>;
+  constexpr int kChunkE = BF ? 2 * kChunkK : kChunkK;  // elements of a 128-byte slice
   constexpr int kStages = C::kStages;
   constexpr int kThreads = C::kThreads;
   constexpr uint32_t kABytes = C::kABytes;
@@ -294,7 +324,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (!C::kStream) {
       mbar_expect_tx(bfull, (uint32_t)a.n_kchunks * C::kBChunkBytes);
       for (int kc = 0; kc < a.n_kchunks; ++kc)
-        tma_load_2d(smem_b + (size_t)kc * C::kBChunkBytes, &map_b, bfull, kc * kChunkK, 0);
+        tma_load_2d(smem_b + (size_t)kc * C::kBChunkBytes, &map_b, bfull, kc * kChunkE, 0);
     }
     uint32_t stage = 0, phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -302,8 +332,8 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], C::kStageBytes);
         uint8_t* st = smem_a + (size_t)stage * C::kStageBytes;
-        tma_load_2d(st, &map_a, &full[stage], kc * kChunkK, (int)(tile * C::kTileRows));
-        if (C::kStream) tma_load_2d(st + kABytes, &map_b, &full[stage], kc * kChunkK, 0);
+        tma_load_2d(st, &map_a, &full[stage], kc * kChunkE, (int)(tile * C::kTileRows));
+        if (C::kStream) tma_load_2d(st + kABytes, &map_b, &full[stage], kc * kChunkE, 0);
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -312,7 +342,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(TN);
+    constexpr uint32_t idesc = make_idesc(TN, kTileM, BF);
     if (!C::kStream) mbar_wait(bfull, 0);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -328,8 +358,12 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int h = 0; h < C::kMH; ++h) {
           const uint64_t adesc = make_smem_desc(smem_u32(st + (size_t)h * kHalfBytes));
 #pragma unroll
-          for (int k = 0; k < kChunkK / 8; ++k)  // K = 8 tf32 (32 bytes) per instruction: advance 32 bytes inside the atom
-            mma_tf32(tmem_d + h * TN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {  // K = 8 tf32 / 16 bf16 (32 bytes) per instruction: advance 32 bytes inside the atom
+            if (BF)
+              mma_bf16(tmem_d + h * TN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+            else
+              mma_tf32(tmem_d + h * TN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          }
         }
         mma_commit(&empty[stage]);  // frees the smem stage when these MMAs are done
         if (++stage == kStages) {
@@ -381,7 +415,7 @@ query_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;  // scored quantity is f/||f||: unit norm (NaN sums stay NaN)
       }
-      const float margin = kTf32Margin * fn;
+      const float margin = a.margin * fn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (acc * C::kMH + mh) * TN;
@@ -456,10 +490,11 @@ struct PairCfg {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 256;
 };
 
-template <int TN>
+template <int TN, bool BF>
 __global__ void __launch_bounds__(256, 1)
 query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcArgs a) {
   using PC = PairCfg<TN>;
+  constexpr int kChunkE = BF ? 2 * kChunkK : kChunkK;
   constexpr int kTN = PC::kTN, kStages = PC::kStages, kThreads = PC::kThreads, kTmemCols = PC::kTmemCols;
   constexpr uint32_t kABytes = PC::kABytes, kStageBytes = PC::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -509,8 +544,8 @@ query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint32_t lfull = smem_u32(&full[stage]) & kPeerBitMask;
         mbar_expect_tx_cluster(lfull, kStageBytes);
         uint8_t* st = smem + (size_t)stage * kStageBytes;
-        tma_load_2d_pair(st, &map_a, lfull, kc * kChunkK, (int)(tile * 2 * kTileM + crank * kTileM));
-        tma_load_2d_pair(st + kABytes, &map_b, lfull, kc * kChunkK, (int)(crank * (kTN / 2)));
+        tma_load_2d_pair(st, &map_a, lfull, kc * kChunkE, (int)(tile * 2 * kTileM + crank * kTileM));
+        tma_load_2d_pair(st + kABytes, &map_b, lfull, kc * kChunkE, (int)(crank * (kTN / 2)));
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -519,7 +554,7 @@ query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else if (warp == 1 && lane == 0 && crank == 0) {
     // ===== MMA issuer (leader CTA only) =====
-    constexpr uint32_t idesc = make_idesc(kTN, 2 * kTileM);
+    constexpr uint32_t idesc = make_idesc(kTN, 2 * kTileM, BF);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (uint32_t tile = pair0; tile < n_tiles; tile += pair_step) {
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // both epilogues have drained this accumulator set
@@ -532,8 +567,12 @@ query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const uint64_t adesc = make_smem_desc(smem_u32(st));
         const uint64_t bdesc = make_smem_desc(smem_u32(st + kABytes));
 #pragma unroll
-        for (int k = 0; k < kChunkK / 8; ++k)
-          mma_tf32_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {
+          if (BF)
+            mma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+          else
+            mma_tf32_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) ? 1u : 0u);
+        }
         mma_commit_pair(&empty[stage], 3);  // both producers may refill this stage
         if (++stage == kStages) {
           stage = 0;
@@ -580,7 +619,7 @@ query_tc_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         inv = a.normalize ? __fdiv_rn(1.0f, fmaxf(nrm, 1e-12f * cnt)) : __fdiv_rn(1.0f, cnt);
         if (a.normalize) fn = (nrm == nrm) ? 1.0f : nrm;
       }
-      const float margin = kTf32Margin * fn;
+      const float margin = a.margin * fn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * kTN;
@@ -678,6 +717,24 @@ __global__ void pad_prompts_kernel(const float* __restrict__ q, int p0, int pb, 
   }
 }
 
+// bf16 shadow of the voxel sums (engine 3): round-to-nearest-even, 8 values per thread
+__global__ void __launch_bounds__(256) shadow_kernel(const float* __restrict__ vsum, size_t n8, __nv_bfloat16* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(vsum)[2 * i], b = reinterpret_cast<const float4*>(vsum)[2 * i + 1];
+    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w), __floats2bfloat162_rn(b.x, b.y),
+                           __floats2bfloat162_rn(b.z, b.w)};
+    reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(o);
+  }
+}
+// zero-padded bf16 copy of the prompts of one pass: [tile_n][d]
+__global__ void pad_prompts_bf16_kernel(const float* __restrict__ q, int p0, int pb, int d, int tile_n, __nv_bfloat16* __restrict__ out) {
+  const int n = tile_n * d;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int p = i / d;
+    out[i] = __float2bfloat16_rn(p < pb ? q[(size_t)(p0 + p) * d + (i - p * d)] : 0.f);
+  }
+}
+
 // exact fp32 re-scoring of the candidates: one warp per (prompt, voxel) entry of the flat list; the key
 // (ordered(score) << 32 | ~rank) goes to the prompt's own list
 __global__ void __launch_bounds__(256) rescore_kernel(const float* __restrict__ vsum, const uint32_t* __restrict__ vcount,
@@ -724,8 +781,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // rows x cols fp32 matrix whose rows start row_stride_elems floats apart (a strided sample of the voxel rows when
 // row_stride_elems > cols)
-static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                       uint64_t row_stride_elems = 0) {
+static int make_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint64_t row_stride_elems = 0, bool bf16 = false) {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -738,10 +795,10 @@ static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint6
     fn = (EncodeTiledFn)p;
   }
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {(row_stride_elems ? row_stride_elems : cols) * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kChunkK, box_rows};
+  const cuuint64_t strides[1] = {(row_stride_elems ? row_stride_elems : cols) * (bf16 ? 2 : 4)};
+  const cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * kChunkK : kChunkK), box_rows};  // 128 bytes wide either way
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  const CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -756,6 +813,8 @@ static int make_map_2d(CUtensorMap* out, const float* base, uint64_t rows, uint6
 namespace tc {
 
 struct Scratch {
+  bool bf;                    // tensor-core passes read the bf16 shadow (engine 3) instead of the fp32 sums
+  const __nv_bfloat16* shadow;
   float *qnorm, *thr, *qpad, *ssc;
   int64_t* sidx;
   uint32_t* cand_cnt;         // [P] keys per prompt, then [1] entries of the flat list
@@ -774,7 +833,8 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
                     const Scratch& sc, int tile_n, size_t smem, int64_t* idx_dev, float* score_dev, bool* fell_back,
                     cudaStream_t s) {
   const int d = m->d;
-  const int n_kchunks = d / kChunkK;
+  const bool bf = sc.bf;
+  const int n_kchunks = bf ? d / (2 * kChunkK) : d / kChunkK;
   if (fell_back) *fell_back = false;
   VSM_CUDA(cudaMemsetAsync(sc.cand_cnt, 0, (size_t)(P + 1) * 4, s));
   uint32_t* pair_cnt = sc.cand_cnt + P;
@@ -786,17 +846,23 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
   const bool pair = tile_n == 256 && use_pair;
   const uint32_t tile_rows = pair ? 2 * kTileM
                                   : (tile_n == 64 ? Cfg<64>::kTileRows : (tile_n == 128 ? Cfg<128>::kTileRows : Cfg<256>::kTileRows));
-  VSM_TRY(make_map_2d(&map_a, m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d, pair ? kTileM : tile_rows, (uint64_t)stride * d));
-  VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)(pair ? tile_n / 2 : tile_n)));
+  VSM_TRY(make_map_2d(&map_a, bf ? (const void*)sc.shadow : (const void*)m->vsum.as<float>(), (uint64_t)n_rows, (uint64_t)d,
+                      pair ? kTileM : tile_rows, (uint64_t)stride * d, bf));
+  VSM_TRY(make_map_2d(&map_b, sc.qpad, (uint64_t)tile_n, (uint64_t)d, (uint32_t)(pair ? tile_n / 2 : tile_n), 0, bf));
   const int n_sm = sm_count();
   const uint32_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
   const int grid = pair ? 2 * (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm / 2) : (int)std::min<uint32_t>(n_tiles, (uint32_t)n_sm);
   const size_t pair_smem = PairCfg<256>::kSmemBytes;
-  if (pair)
-    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+  if (pair) {
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_pair_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+  }
   for (int p0 = 0; p0 < P; p0 += tile_n) {
     const int pb = std::min(tile_n, P - p0);
-    pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, sc.qpad);
+    if (bf)
+      pad_prompts_bf16_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, reinterpret_cast<__nv_bfloat16*>(sc.qpad));
+    else
+      pad_prompts_kernel<<<64, 256, 0, s>>>(q_dev, p0, pb, d, tile_n, sc.qpad);
     VSM_LAUNCHED();
     TcArgs a;
     a.vcount = m->vcount.as<uint32_t>();
@@ -812,12 +878,19 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
     a.pair_cnt = pair_cnt;
     a.pair_cap = pair_cap;
     a.n_kchunks = n_kchunks;
-    if (tile_n == 64)
-      query_tc_kernel<64><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
+    a.margin = bf ? kBf16Margin : kTf32Margin;
+    if (tile_n == 64 && bf)
+      query_tc_kernel<64, true><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
+    else if (tile_n == 64)
+      query_tc_kernel<64, false><<<grid, Cfg<64>::kThreads, smem, s>>>(map_a, map_b, a);
+    else if (!pair && tile_n == 128 && bf)
+      query_tc_kernel<128, true><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
     else if (!pair && tile_n == 128)
-      query_tc_kernel<128><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
+      query_tc_kernel<128, false><<<grid, Cfg<128>::kThreads, smem, s>>>(map_a, map_b, a);
+    else if (!pair && bf)
+      query_tc_kernel<256, true><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
     else if (!pair)
-      query_tc_kernel<256><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
+      query_tc_kernel<256, false><<<grid, Cfg<256>::kThreads, smem, s>>>(map_a, map_b, a);
     else {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3((unsigned)grid);
@@ -831,7 +904,10 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel<256>, map_a, map_b, a));
+      if (bf)
+        VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel<256, true>, map_a, map_b, a));
+      else
+        VSM_CUDA(cudaLaunchKernelEx(&cfg, query_tc_pair_kernel<256, false>, map_a, map_b, a));
     }
     VSM_LAUNCHED();
   }
@@ -859,15 +935,15 @@ static int tc_level(vsm_map* m, const float* q_dev, int P, int k, int normalize,
 }  // namespace tc
 
 int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_t* idx_dev, float* score_dev,
-             cudaStream_t s) {
+             cudaStream_t s, bool bf) {
   using namespace tc;
   const uint32_t V = (uint32_t)m->n_vox;
   const int d = m->d;
-  if (d % kChunkK != 0 || d > 1024) {
-    set_error("vsm_query engine 2 needs d to be a multiple of 32 and <= 1024 (d=%d)", d);
+  if (d % (bf ? 2 * kChunkK : kChunkK) != 0 || d > 1024) {
+    set_error("vsm_query engine %d needs d to be a multiple of %d and <= 1024 (d=%d)", bf ? 3 : 2, bf ? 2 * kChunkK : kChunkK, d);
     return VSM_E_INVALID;
   }
-  const int n_kchunks = d / kChunkK;
+  const int n_kchunks = bf ? d / (2 * kChunkK) : d / kChunkK;
   // prompts per pass: 64 with the prompt block resident in shared memory, 128 / 256 with its slices streamed
   const int tile_n = P <= 64 ? 64 : (P <= 128 ? 128 : 256);
   const size_t smem = tile_n == 64    ? (size_t)n_kchunks * Cfg<64>::kBChunkBytes + (size_t)Cfg<64>::kStages * Cfg<64>::kStageBytes + 256
@@ -877,20 +953,40 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
     set_error("vsm_query engine 2: d=%d needs %zu bytes of shared memory", d, smem);
     return VSM_E_INVALID;
   }
-  if (tile_n == 64)
-    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (tile_n == 64 && bf)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (tile_n == 64)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (tile_n == 128 && bf)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else if (tile_n == 128)
-    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (bf)
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   else
-    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSM_CUDA(cudaFuncSetAttribute(query_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // ---- scratch: norms (cached per finalisation), thresholds, candidates ------------------------------------
   Scratch sc;
   sc.cap = 1u << 16;
+  sc.bf = bf;
+  sc.shadow = nullptr;
   VSM_TRY(m->q_norm.ensure((size_t)std::max<uint32_t>(V, 1) * 4, s));
   if (!m->norms_valid) {
     row_norm_kernel<<<sm_count() * 8, 256, 0, s>>>(m->vsum.as<float>(), V, d, m->q_norm.as<float>());
     VSM_LAUNCHED();
     m->norms_valid = true;
+    m->shadow_valid = false;
+  }
+  if (bf) {
+    // the bf16 shadow of the sums: built once per finalisation (norms_valid is reset whenever the sums change), 2 bytes
+    // per value beside the exact fp32 store -- the tensor-core passes then read half the bytes
+    VSM_TRY(m->q_shadow.ensure((size_t)std::max<uint32_t>(V, 1) * d * 2, s));
+    if (!m->shadow_valid) {
+      shadow_kernel<<<sm_count() * 16, 256, 0, s>>>(m->vsum.as<float>(), (size_t)V * d / 8, m->q_shadow.as<__nv_bfloat16>());
+      VSM_LAUNCHED();
+      m->shadow_valid = true;
+    }
+    sc.shadow = m->q_shadow.as<__nv_bfloat16>();
   }
   // layout of q_tc: [qnorm P][thr P][padded prompts kMaxTileN*d][sample idx P*k (i64)][sample scores P*k][cand_cnt P + 1]
   const size_t off_qn = 0, off_thr = off_qn + (size_t)P * 4, off_pad = (off_thr + (size_t)P * 4 + 255) & ~(size_t)255;
@@ -948,3 +1044,15 @@ int query_tc(vsm_map* m, const float* q_dev, int P, int k, int normalize, int64_
 }
 
 }  // namespace vsm
+
+extern "C" int vsm_query_shadow_release(vsm_map* m) {
+  if (!m) {
+    vsm::set_error("null map");
+    return VSM_E_INVALID;
+  }
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  m->q_shadow.release();
+  m->shadow_valid = false;
+  return VSM_OK;
+}

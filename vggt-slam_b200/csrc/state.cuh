@@ -249,6 +249,8 @@ struct vsm_map {
   vsm::DevBuf q_cand, q_tmp, q_norm;
   vsm::DevBuf q_tc, q_tc_cand;     // tensor-core engine: thresholds / padded prompts; candidate ids + keys
   bool norms_valid = false;        // q_norm holds ||sum_v|| for the current contents
+  vsm::DevBuf q_shadow;            // bf16 copy of the sums for the tensor-core passes of engine 3 (built on demand)
+  bool shadow_valid = false;
   uint32_t tc_last_candidates = 0; // longest candidate list of the last engine-2 query
   int64_t tc_fallbacks = 0;        // engine-2 queries answered by engine 1 (candidate overflow)
 };

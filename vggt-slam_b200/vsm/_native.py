@@ -92,6 +92,8 @@ SIGNATURES = {
     "vsm_lookup": (C.c_int, [_vp, _vp, _i64, _vp, C.c_int, _vp]),
     "vsm_query": (C.c_int, [_vp, _vp, _i32, _i32, C.c_int, C.c_int, _vp, _vp, _vp]),
     "vsm_query_stats": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
+    "vsm_query_shadow_release": (C.c_int, [_vp]),
+    "vsm_pool_trim": (C.c_int, []),
     "vsm_partials_pack": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _P(_i64), _vp]),
     "vsm_partials_merge": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "vsm_contrib_pack": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _P(_i64), _vp]),
