@@ -1,4 +1,5 @@
-"""Text-query sweep (BASELINE config 4): V voxels x P prompts, top-k, engines 1 (exact fp32) and 2 (tcgen05).
+"""Text-query sweep (BASELINE config 4): V voxels x P prompts, top-k, engines 1 (exact fp32), 2 (tcgen05, TF32 on the fp32 sums)
+and 3 (tcgen05, bf16 shadow); the tensor-core engines must return engine 1's indices.
 Prints one JSON line per point: latency, effective HBM GB/s over V*d*4 bytes, TFLOP/s, candidates."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -30,7 +31,7 @@ for P in prompts:
     q = rng.normal(size=(P, d)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
     qt = torch.from_numpy(q).to(dev)
     res = {}
-    for eng in (1, 2):
+    for eng in (1, 2, 3):
         if eng == 1 and P > 64 and V > 20_000_000:
             continue
         for _ in range(2):
@@ -46,5 +47,6 @@ for P in prompts:
         print(json.dumps({"V": V, "P": P, "k": k, "engine": eng, "ms": round(ms, 3), "GBps_over_Vd4": round(V * d * 4 / ms * 1e-6, 1),
                           "TFLOPs": round(2.0 * V * d * P / ms * 1e-9, 1), "candidates": st["last_candidates"],
                           "fallbacks": st["fallbacks"]}), flush=True)
-    if 1 in res and 2 in res:
-        assert torch.equal(res[1][1], res[2][1]), "engines disagree"
+    for eng in (2, 3):
+        if 1 in res and eng in res:
+            assert torch.equal(res[1][1], res[eng][1]), "engines disagree"
