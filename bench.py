@@ -43,8 +43,8 @@ import numpy as np  # noqa: E402
 
 # accumulate_kernel DRAM traffic per launch from the committed `ncu --set full` capture of this workload's submap shape
 # (mean of 3 launches: 3.861 GB read + 0.066 GB written against 3.73 GB algorithmic)
-NCU_ACC_TRAFFIC_BYTES = 3.926e9
-NCU_ACC_TRAFFIC_SRC = "profiles/r01_accumulate_ncu_full_summary.txt"
+NCU_ACC_TRAFFIC_BYTES = 3.917e9  # dram__bytes_read.sum + dram__bytes_write.sum of one accumulate launch (3.855 GB + 61 MB)
+NCU_ACC_TRAFFIC_SRC = "profiles/r02_fuse_kernels_ncu_full_summary.txt"
 
 METRIC = "points fused/sec"
 UNIT = "points/s"
@@ -1010,6 +1010,9 @@ def main():
             m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], profile=True)
             stats = gm.last_build_stats
         cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.3) + 1024 if world > 1 else int(m._dm.num_voxels * 1.05) + 1024)
+        if world > 1 and os.environ.get("VSM_BENCH_STEP_BARRIER") == "1":
+            torch.cuda.synchronize()
+            dist.barrier()
         return m, stats
 
     # the clock poller (a child process) starts before the warm-up, so that its NVML client set-up is long over

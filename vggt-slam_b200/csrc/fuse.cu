@@ -1344,7 +1344,13 @@ __global__ void __launch_bounds__(256) scatter7_kernel(const uint2* __restrict__
         if (sl->lid != kLidReject) {
           const unsigned long long m0 = sl->mask[0];
           gid = (int)(uint32_t)(m0 >> 32);
-          if (entries != nullptr && gid >= 0) entries[(uint32_t)m0 + ps.y] = make_entry(gid, pix);
+          if (entries != nullptr && gid >= 0) {
+            const uint32_t pos = (uint32_t)m0 + ps.y;  // segment start + ordinal: inside the list by construction
+            if (pos < n_fused)
+              entries[pos] = make_entry(gid, pix);
+            else
+              atomicAdd(&ctr->internal_err, 1u);
+          }
         }
       }
     }
