@@ -1010,9 +1010,6 @@ def main():
             m = gm.build_semantic_voxel_map(args.voxel_size, capacity_hint=cap_hint[0], profile=True)
             stats = gm.last_build_stats
         cap_hint[0] = max(cap_hint[0], int(m._dm.num_voxels * 1.3) + 1024 if world > 1 else int(m._dm.num_voxels * 1.05) + 1024)
-        if world > 1 and os.environ.get("VSM_BENCH_STEP_BARRIER") == "1":
-            torch.cuda.synchronize()
-            dist.barrier()
         return m, stats
 
     # the clock poller (a child process) starts before the warm-up, so that its NVML client set-up is long over
@@ -1052,12 +1049,14 @@ def main():
     CANDS = (0, 64)
     partition = {"prep_sms": 0, "mode": args.sm_partition}
     if args.sm_partition == "auto" and world > 1:
-        # On several GPUs the partition goes with the COLLECTIVE exchange (pack -> NCCL all-to-all -> merge).  With the
-        # one-sided peer-memory exchange the fuse calls gain as on one GPU (16.5 instead of 19.4 ms per step at N=2) but
-        # steps then stall at random for 35-120 ms (10 steps at N=2: 20.2 19.7 113 109 56 143 93 143 19.8 19.7 ms);
-        # with the collective exchange every step takes 20.8-21.3 ms (peer exchange without the partition: 22.5-22.9).
-        # Kernels that touch IPC-mapped peer memory beside green contexts: not understood well enough to ship.  This
-        # workload exchanges 0.3 GB per step; the long-trajectory block below keeps the peer exchange (no partition).
+        # On several GPUs the partition (the split measured fastest on one GPU) goes with the COLLECTIVE exchange (pack ->
+        # NCCL all-to-all -> merge).  Beside the one-sided peer-memory exchange the fuse calls gain as on one GPU (16.5
+        # instead of 19.4 ms per step) but steps stall at random: a rank's next fuse kernels, in green contexts, beside
+        # peers still finishing the exchange against its memory -- 10 steps at N=2: 20.2 19.7 113 109 56 143 93 143 19.8
+        # 19.7 ms.  Settling the device and the group at the end of every build (vsm.dist does that for the peer route)
+        # cures it at N=2 (18.8-19.3 ms) but not at N=8 (26-41 ms); with the collective exchange every step takes
+        # 21.6-21.9 ms at N=2 and N=8 (peer exchange without the partition: 22.5-22.9).  This workload exchanges 0.3 GB
+        # per step; the long-trajectory block below keeps the peer exchange, without the partition.
         partition.update({"prep_sms": 64, "exchange": "collective (NCCL all-to-all) beside the partition"})
         dist_transport[0] = "collective"
         set_partition(64)
@@ -1083,8 +1082,7 @@ def main():
     elif args.sm_partition != "off":
         partition["prep_sms"] = int(args.sm_partition)
         set_partition(partition["prep_sms"])
-        if world > 1 and os.environ.get("VSM_PEER_DISABLE") != "1" and os.environ.get("VSM_BENCH_PEER_WITH_PARTITION") != "1":
-            dist_transport[0] = "collective"
+
     for _ in range(n_warm):
         m, stats = step()
     n_fused_step = sum(s["n_fused"] for s in stats)

@@ -151,8 +151,17 @@ DEFAULT_PREP_VARIANT = 13  # csrc/fuse.cu g_prep_variant
 DEFAULT_SELECT_MODE = 0    # 0 = the library's default (deferred percentile box)
 
 
+_OPTIONS: dict = {}  # what this process has set (the library has no getter)
+
+
 def set_option(key: str, value: int) -> None:
     check(lib.vsm_set_option(key.encode(), int(value)))
+    _OPTIONS[key] = int(value)
+
+
+def option(key: str, default: int = 0) -> int:
+    """The value last set through set_option in this process (default if never set)."""
+    return _OPTIONS.get(key, default)
 
 
 def get_counter(key: str) -> int:

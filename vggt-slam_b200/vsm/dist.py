@@ -202,7 +202,20 @@ def _sizes_all(values, group, device) -> np.ndarray:
     return torch.stack(out).cpu().numpy()
 
 
-def _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs=None):
+def _settle_before_next_build(dev, group) -> None:
+    """With SM partitions on (vsm_set_option("green_prep_sms")), a rank must not start the fuse kernels of its next build
+    -- they run in green contexts -- while a peer is still finishing this build's exchange / collectives against this
+    rank's memory: measured on 2 x B200, steps then stall at random for 35-150 ms (10 steps: 20.2 19.7 113 109 56 143 93
+    143 19.8 19.7 ms); with the device synchronised and a barrier at the end of every build all steps take 18.8-19.3 ms.
+    (On 8 GPUs that is not enough: 26-41 ms per step.  There the partition goes with the collective exchange, bench.py.)"""
+    from . import _native as N
+
+    if N.option("green_prep_sms", 0) > 0 and dev is not None and dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+
+
+def _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs=None, settle=False):
     """Tail of a sharded build: finalise the owner shard, learn every rank's frame ids (contributor lists name frames
     of remote submaps too), wrap the shard and rank its voxels among all shards."""
     from .map import wrap_device_map
@@ -247,6 +260,8 @@ def _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs=None):
     ph.mark("wrap")
     gidx, n_global = global_ranks(owner.export_packed_keys(), group)
     ph.mark("ranks")
+    if settle:  # (the peer-memory exchange; the collective route synchronises the host at every step anyway)
+        _settle_before_next_build(dev, group)
     ph.report()
     return ShardedVoxelMap(local, owner, gidx, n_global, group)
 
@@ -330,7 +345,7 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
         del r_keys, r_counts, r_sums
     if transport not in ("peer", "collective"):
         raise ValueError(f"unknown transport {transport!r}")
-    return _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs), stats
+    return _finish_shard(owner, fused, voxel_size, group, dev, ph, names_sigs, settle=transport == "peer"), stats
 
 
 _XCHG_STREAMS: dict = {}
@@ -443,7 +458,7 @@ def build_sharded_streaming(graph_map, voxel_size: float, round_submaps: int, st
             L.close()
     graph_map.last_build_stats = stats_all
     graph_map.last_profile = prof
-    shard = _finish_shard(owner, fused_all, voxel_size, group, dev, ph)
+    shard = _finish_shard(owner, fused_all, voxel_size, group, dev, ph, settle=True)
     if round_ev:
         torch.cuda.synchronize(dev)
         timings["per_round_ms"] = {"push": [m[0].elapsed_time(m[1]) for m in round_ev],
