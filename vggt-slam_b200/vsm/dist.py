@@ -327,21 +327,33 @@ def build_sharded(graph_map, voxel_size: float, stride: int = 1, ignore_loop_clo
     if transport == "collective":
         # ---- voxels -> owners ------------------------------------------------------
         keys, counts, sums, send = dm.partials_pack(world)
-        recv = exchange_counts(send.tolist(), group, dev)
+        ckeys, csubs, cmasks, csend = dm.contrib_pack(world)
+        ph.mark("pack")
+        # one small all-to-all tells every rank what it will receive from whom -- voxel rows, contributor entries --
+        # and carries the senders' frame-name signatures (which decide whether the pickled all-gather of names is needed)
+        my_sig = _names_signature(fused)
+        meta = torch.tensor([[int(send[r]), int(csend[r]), my_sig] for r in range(world)], dtype=torch.int64, device=dev)
+        got = torch.empty_like(meta)
+        dist.all_to_all_single(got, meta, group=group)
+        got = got.cpu().numpy()
+        recv, crecv, names_sigs = [int(x) for x in got[:, 0]], [int(x) for x in got[:, 1]], got[:, 2]
+        ph.mark("counts")
         r_keys = exchange_rows(keys, send.tolist(), recv, group)
         r_counts = exchange_rows(counts, send.tolist(), recv, group)
         r_sums = exchange_rows(sums, send.tolist(), recv, group)
-        ckeys, csubs, cmasks, csend = dm.contrib_pack(world)
-        crecv = exchange_counts(csend.tolist(), group, dev)
+        ph.mark("a2a_rows")
         rc_keys = exchange_rows(ckeys, csend.tolist(), crecv, group)
         rc_subs = exchange_rows(csubs, csend.tolist(), crecv, group)
         rc_masks = exchange_rows(cmasks, csend.tolist(), crecv, group)
+        ph.mark("a2a_contrib")
         del keys, counts, sums, ckeys, csubs, cmasks
         dm.close()
+        ph.mark("close")
         # ---- owner merge --------------------------------------------------------------
         owner = vm.DeviceVoxelMap(float(voxel_size), d, code, capacity=max(int(sum(recv)), 1024), device=dev)
         owner.partials_merge(r_keys, r_counts, r_sums)
         owner.contrib_merge(rc_keys, rc_subs, rc_masks)
+        ph.mark("merge")
         del r_keys, r_counts, r_sums
     if transport not in ("peer", "collective"):
         raise ValueError(f"unknown transport {transport!r}")
