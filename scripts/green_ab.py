@@ -21,7 +21,14 @@ N.set_option("prep_variant", variant)
 N.set_option("select_mode", sel)
 ring = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 N.set_option("acc_ring", ring)
-print("prep_variant", variant, "select_mode", sel, "acc_ring", ring)
+tma = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+N.set_option("acc_tma", tma)
+splits = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0, 48, 56, 64, 72, 80, 88, 96]
+mix = int(sys.argv[8]) if len(sys.argv) > 8 else 0
+N.set_option("acc_mix", mix)
+run = int(sys.argv[9]) if len(sys.argv) > 9 else 0
+N.set_option("acc_tmarun", run)
+print("prep_variant", variant, "select_mode", sel, "acc_ring", ring, "acc_tma", tma, "acc_mix", mix, "acc_tmarun", run)
 gm = vsm.GraphMap()
 for i in range(n_sub):
     d = synth_device.make_submap_device(1234, i, first_frame_number=32 * i)
@@ -51,7 +58,7 @@ def run(vs, reps=4):
 print(f"{'voxel':>6} {'prep SMs':>9} {'acc CTAs/SM':>12} {'ms/submap':>10}  signature (voxels, points, sum|f|)")
 for vs in sizes:
     ref = None
-    for prep_sms, ctas in ((0, 2), (48, 3), (56, 3), (64, 3), (72, 3), (80, 3), (88, 3), (96, 3), (-1, 2)):
+    for prep_sms, ctas in [(p, 3 if p else 2) for p in splits]:
         if prep_sms < 0:  # overlap on two plain streams, no partition (round-1 experiment)
             N.set_option("green_prep_sms", 0)
             N.set_option("overlap", 1)
@@ -72,4 +79,7 @@ N.set_option("overlap", 0)
 N.set_option("acc_ctas_per_sm", 2)
 N.set_option("prep_variant", N.DEFAULT_PREP_VARIANT)
 N.set_option("select_mode", 0)
-N.set_option("acc_ring", 1)
+N.set_option("acc_ring", 0)
+N.set_option("acc_tma", 0)
+N.set_option("acc_mix", 0)
+N.set_option("acc_tmarun", 0)

@@ -1154,6 +1154,585 @@ __global__ void __launch_bounds__(256, 2) accumulate_ring_kernel(AccArgs a) {
   }
 }
 
+// ---- the same accumulate with the rows fetched by TMA bulk copies ------------------------------------------------------
+// scripts/cu/sm_bw_probe*.cu: through the load/store path an SM pulls at most ~57 GB/s from L2/HBM whatever is in
+// flight (148 SMs: 6.6 TB/s; 84 SMs: 4.6 TB/s; 60 SMs: 3.4 TB/s) -- which is why accumulate_kernel needs every SM and why
+// the cp.async ring changed nothing.  cp.async.bulk does not share that limit: 60 SMs pull 7.2 TB/s, 37 SMs 6.3 TB/s.
+// Here lane 0 of every warp issues ONE bulk copy per row (1 KB, global -> the warp's ring in shared memory, completion on
+// the slot's mbarrier), DEPTH rows ahead; the warp waits for a slot's barrier, reads its 16-byte pieces, re-issues the
+// slot and adds.  A slot is written by the async proxy only after every lane has read it (__syncwarp before the
+// re-issue); the mbarrier wait makes the bytes visible to the readers.
+__device__ __forceinline__ void mbar_init_cta(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cta(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cta(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+template <bool BF16, int VPL, bool CHECK, int DEPTH>
+__global__ void __launch_bounds__(256, 2) accumulate_tma_kernel(AccArgs a) {
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr uint32_t ROW = (uint32_t)VPL * 512u;  // bytes per row
+  constexpr int U = 4;                            // rows taken out of the ring per step
+  static_assert(DEPTH % U == 0 && DEPTH <= 32, "ring depth: a multiple of the step, one phase bit per slot");
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  const int lane = lane_id(), wib = (int)(threadIdx.x >> 5);
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(tma_smem) + (uint32_t)wib * (uint32_t)DEPTH * ROW;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(tma_smem) + 8u * (uint32_t)DEPTH * ROW + (uint32_t)wib * (uint32_t)DEPTH * 8u;
+  if (lane < DEPTH) mbar_init_cta(bar0 + (uint32_t)lane * 8u, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (a.ctr->abort) return;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_entries = (int64_t)a.ctr->n_fused;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const uint8_t* emb_row0 = a.emb - a.pix_base * a.row_bytes;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  unsigned n_bad = 0;
+
+  float acc[VPL * EPV];
+#pragma unroll
+  for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      bool ok = true;
+      if (CHECK) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);  // NaN iff some accumulator is Inf/NaN
+        ok = !__any_sync(0xffffffffu, t != t);
+        if (!ok && lane == 0) ++n_bad;
+      }
+      if (ok) {
+        float* dst = vsum0 + (size_t)cur * d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int q = 0; q < EPV / 4; ++q)
+            red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1], acc[v * EPV + 4 * q + 2],
+                       acc[v * EPV + 4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  };
+  auto load_entries = [&](int64_t chunk, uint32_t& pix, int& gid) {
+    pix = 0u;
+    gid = -1;
+    if (chunk < n_chunks) {
+      const int64_t i = (chunk << 5) + lane;
+      if (i < n_entries) {
+        const unsigned long long e = a.entries[i];
+        pix = (uint32_t)e;
+        gid = (int)(uint32_t)(e >> 32);
+      }
+    }
+  };
+  uint32_t pixC, pixN;
+  int gidC, gidN;
+  load_entries(warp, pixC, gidC);
+  load_entries(warp + n_warps, pixN, gidN);
+  // one bulk copy per row, issued by lane 0; rows of empty list positions (the last chunk's tail) are not fetched
+  auto issue = [&](uint32_t pix, int gid, int src_lane, uint32_t slot) {
+    const uint32_t pj = __shfl_sync(0xffffffffu, pix, src_lane);
+    const int gj = __shfl_sync(0xffffffffu, gid, src_lane);
+    if (gj >= 0 && lane == 0) {
+      const uint32_t bar = bar0 + slot * 8u;
+      mbar_expect_tx_cta(bar, ROW);
+      bulk_g2s(ring0 + slot * ROW, emb_row0 + (unsigned long long)pj * rb, ROW, bar);
+    }
+  };
+#pragma unroll
+  for (int r = 0; r < DEPTH; ++r) issue(pixC, gidC, r, (uint32_t)r);
+  uint32_t slot = 0, phases = 0u;
+  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+#pragma unroll 1
+    for (int j = 0; j < 32; j += U) {
+      int g[U];
+      uint4 rows[U][VPL];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        g[u] = __shfl_sync(0xffffffffu, gidC, j + u);
+        if (g[u] >= 0) {  // warp-uniform
+          const uint32_t su = slot + (uint32_t)u;
+          mbar_wait_cta(bar0 + su * 8u, (phases >> su) & 1u);
+          phases ^= 1u << su;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) rows[u][v] = lds_v4(ring0 + su * ROW + (uint32_t)v * 512u + (uint32_t)lane * 16u);
+        }
+      }
+      __syncwarp();  // every lane has read its pieces: the slots may be overwritten
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int jj = j + u + DEPTH;
+        if (jj < 32)
+          issue(pixC, gidC, jj, slot + (uint32_t)u);
+        else
+          issue(pixN, gidN, jj - 32, slot + (uint32_t)u);
+      }
+      slot = slot + (uint32_t)U == (uint32_t)DEPTH ? 0u : slot + (uint32_t)U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (g[u] < 0) continue;
+        if (g[u] != cur) {
+          flush();
+          cur = g[u];
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+      }
+    }
+    pixC = pixN;
+    gidC = gidN;
+    load_entries(chunk + 2 * n_warps, pixN, gidN);
+  }
+  flush();
+
+  if (CHECK) {
+    const uint8_t* emb0 = emb_row0 + (size_t)lane * 16;
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+    if (n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+  }
+}
+
+// ---- both paths at once -------------------------------------------------------------------------------------------------
+// Measured (scripts/green_ab.py): accumulate_tma_kernel alone is no faster -- a bulk copy costs the SM's TMA unit ~46
+// cycles whatever its size, so 1 KB rows give ~43 GB/s per SM, below even the load/store path's ~57 GB/s.  But the two
+// limits are different units of the SM: half of a CTA's warps fetch their rows with bulk copies, the other half with
+// register loads, and the SM pulls the sum.  The chunks of the sorted list are split between the two kinds of warps in
+// the ratio of their speeds (tma_share).
+template <bool BF16, int VPL, bool CHECK, int DEPTH, int TMA_WARPS>
+__global__ void __launch_bounds__(256, (VPL <= 2) ? 3 : 2) accumulate_mix_kernel(AccArgs a, float tma_share) {
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr uint32_t ROW = (uint32_t)VPL * 512u;
+  constexpr int U = 4;
+  static_assert(DEPTH % U == 0 && DEPTH <= 32 && TMA_WARPS >= 1 && TMA_WARPS < 8, "ring depth / warp roles");
+  extern __shared__ __align__(128) uint8_t mix_smem[];
+  const int lane = lane_id(), wib = (int)(threadIdx.x >> 5);
+  const bool tma_warp = wib < TMA_WARPS;
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(mix_smem) + (uint32_t)wib * (uint32_t)DEPTH * ROW;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(mix_smem) + (uint32_t)TMA_WARPS * (uint32_t)DEPTH * ROW +
+                        (uint32_t)wib * (uint32_t)DEPTH * 8u;
+  if (tma_warp && lane < DEPTH) mbar_init_cta(bar0 + (uint32_t)lane * 8u, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (a.ctr->abort) return;
+  const int64_t n_entries = (int64_t)a.ctr->n_fused;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
+  const int64_t split = min(n_chunks, (int64_t)((double)n_chunks * (double)tma_share));  // chunks [0, split): bulk copies
+  // my index among the warps of my kind, their number, and my kind's range of chunks
+  const int64_t kidx = tma_warp ? (int64_t)blockIdx.x * TMA_WARPS + wib : (int64_t)blockIdx.x * (8 - TMA_WARPS) + (wib - TMA_WARPS);
+  const int64_t n_kind = (int64_t)gridDim.x * (tma_warp ? TMA_WARPS : 8 - TMA_WARPS);
+  const int64_t lo = tma_warp ? 0 : split, hi = tma_warp ? split : n_chunks;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const uint8_t* emb_row0 = a.emb - a.pix_base * a.row_bytes;
+  const uint8_t* emb0 = emb_row0 + (size_t)lane * 16;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  unsigned n_bad = 0;
+
+  float acc[VPL * EPV];
+#pragma unroll
+  for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      bool ok = true;
+      if (CHECK) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);
+        ok = !__any_sync(0xffffffffu, t != t);
+        if (!ok && lane == 0) ++n_bad;
+      }
+      if (ok) {
+        float* dst = vsum0 + (size_t)cur * d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int q = 0; q < EPV / 4; ++q)
+            red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1], acc[v * EPV + 4 * q + 2],
+                       acc[v * EPV + 4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  };
+  auto load_entries = [&](int64_t chunk, uint32_t& pix, int& gid) {
+    pix = 0u;
+    gid = -1;
+    if (chunk < hi) {
+      const int64_t i = (chunk << 5) + lane;
+      if (i < n_entries) {
+        const unsigned long long e = a.entries[i];
+        pix = (uint32_t)e;
+        gid = (int)(uint32_t)(e >> 32);
+      }
+    }
+  };
+
+  if (tma_warp) {
+    uint32_t pixC, pixN;
+    int gidC, gidN;
+    load_entries(lo + kidx, pixC, gidC);
+    load_entries(lo + kidx + n_kind, pixN, gidN);
+    auto issue = [&](uint32_t pix, int gid, int src_lane, uint32_t slot) {
+      const uint32_t pj = __shfl_sync(0xffffffffu, pix, src_lane);
+      const int gj = __shfl_sync(0xffffffffu, gid, src_lane);
+      if (gj >= 0 && lane == 0) {
+        const uint32_t bar = bar0 + slot * 8u;
+        mbar_expect_tx_cta(bar, ROW);
+        bulk_g2s(ring0 + slot * ROW, emb_row0 + (unsigned long long)pj * rb, ROW, bar);
+      }
+    };
+#pragma unroll
+    for (int r = 0; r < DEPTH; ++r) issue(pixC, gidC, r, (uint32_t)r);
+    uint32_t slot = 0, phases = 0u;
+    for (int64_t chunk = lo + kidx; chunk < hi; chunk += n_kind) {
+#pragma unroll 1
+      for (int j = 0; j < 32; j += U) {
+        int g[U];
+        uint4 rows[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          g[u] = __shfl_sync(0xffffffffu, gidC, j + u);
+          if (g[u] >= 0) {
+            const uint32_t su = slot + (uint32_t)u;
+            mbar_wait_cta(bar0 + su * 8u, (phases >> su) & 1u);
+            phases ^= 1u << su;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) rows[u][v] = lds_v4(ring0 + su * ROW + (uint32_t)v * 512u + (uint32_t)lane * 16u);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = j + u + DEPTH;
+          if (jj < 32)
+            issue(pixC, gidC, jj, slot + (uint32_t)u);
+          else
+            issue(pixN, gidN, jj - 32, slot + (uint32_t)u);
+        }
+        slot = slot + (uint32_t)U == (uint32_t)DEPTH ? 0u : slot + (uint32_t)U;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (g[u] < 0) continue;
+          if (g[u] != cur) {
+            flush();
+            cur = g[u];
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+        }
+      }
+      pixC = pixN;
+      gidC = gidN;
+      load_entries(chunk + 2 * n_kind, pixN, gidN);
+    }
+    flush();
+  } else {
+    // register loads, U rows in flight per warp (the hot loop of accumulate_kernel)
+    for (int64_t chunk = lo + kidx; chunk < hi; chunk += n_kind) {
+      uint32_t my_pix;
+      int my_gid;
+      load_entries(chunk, my_pix, my_gid);
+#pragma unroll 1
+      for (int j = 0; j < 32; j += U) {
+        uint4 rows[U][VPL];
+        int g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t pj = __shfl_sync(0xffffffffu, my_pix, j + u);
+          g[u] = __shfl_sync(0xffffffffu, my_gid, j + u);
+          const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) rows[u][v] = g[u] >= 0 ? ld_stream_v4(row + v * 512) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (g[u] < 0) continue;
+          if (g[u] != cur) {
+            flush();
+            cur = g[u];
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+        }
+      }
+      flush();
+    }
+  }
+
+  if (CHECK) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+    if (n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+  }
+}
+
+std::atomic<int> g_acc_mix{0};            // "acc_mix": per mille of the sorted list fetched with bulk copies (0: off)
+std::atomic<int> g_acc_mix_ctas{3};       // "acc_mix_ctas": resident CTAs per SM of the mixed kernel
+
+template <bool BF16, int VPL>
+static int launch_accumulate_mix(const AccArgs& a, bool check, cudaStream_t s, int n_sm) {
+  constexpr int DEPTH = VPL == 1 ? 24 : (VPL == 2 ? 12 : 4);
+  constexpr int TW = 2;
+  constexpr size_t smem = (size_t)TW * DEPTH * VPL * 512 + (size_t)TW * DEPTH * 8;
+  static const cudaError_t opt0 = cudaFuncSetAttribute(accumulate_mix_kernel<BF16, VPL, false, DEPTH, TW>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const cudaError_t opt1 = cudaFuncSetAttribute(accumulate_mix_kernel<BF16, VPL, true, DEPTH, TW>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  VSM_CUDA(opt0);
+  VSM_CUDA(opt1);
+  const int grid = (n_sm > 0 ? n_sm : sm_count()) * std::max(1, std::min(3, g_acc_mix_ctas.load()));
+  const float share = (float)g_acc_mix.load() * 1e-3f;
+  if (check)
+    accumulate_mix_kernel<BF16, VPL, true, DEPTH, TW><<<grid, 256, smem, s>>>(a, share);
+  else
+    accumulate_mix_kernel<BF16, VPL, false, DEPTH, TW><<<grid, 256, smem, s>>>(a, share);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
+// ---- bulk copies of RUNS of rows --------------------------------------------------------------------------------------
+// A bulk copy costs ~46 cycles of the SM's TMA unit whatever its size: 1 KB rows cap an SM at ~43 GB/s (measured: the
+// kernel above is no faster than register loads).  But consecutive entries of a voxel are often NEIGHBOURING PIXELS of an
+// image row (the insert hands out ordinals in lane order of a 4x8 patch), whose embedding rows are contiguous in memory:
+// a run of n such entries is ONE copy of n KB.  Rows are staged in groups of 8 entries (3 groups per warp in flight or
+// being read, one mbarrier per group); inside a group, every run start issues its run.
+template <bool BF16, int VPL, bool CHECK>
+__global__ void __launch_bounds__(256, 1) accumulate_tmarun_kernel(AccArgs a) {
+  constexpr int EPV = RowVec<BF16>::EPV;
+  constexpr uint32_t ROW = (uint32_t)VPL * 512u;
+  constexpr int G = 8, NB = 3, U = 4;
+  extern __shared__ __align__(128) uint8_t run_smem[];
+  const int lane = lane_id(), wib = (int)(threadIdx.x >> 5);
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(run_smem) + (uint32_t)wib * (uint32_t)(NB * G) * ROW;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(run_smem) + 8u * (uint32_t)(NB * G) * ROW + (uint32_t)wib * (uint32_t)NB * 8u;
+  if (lane < NB) mbar_init_cta(bar0 + (uint32_t)lane * 8u, 1u);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (a.ctr->abort) return;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_entries = (int64_t)a.ctr->n_fused;
+  const int64_t n_chunks = (n_entries + 31) >> 5;
+  const uint32_t rb = (uint32_t)a.row_bytes;
+  const uint8_t* emb_row0 = a.emb - a.pix_base * a.row_bytes;
+  float* const vsum0 = a.vsum + (size_t)lane * EPV;
+  const uint32_t d = (uint32_t)a.d;
+  unsigned n_bad = 0;
+
+  float acc[VPL * EPV];
+#pragma unroll
+  for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur >= 0) {
+      bool ok = true;
+      if (CHECK) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * EPV; ++i) t = fmaf(acc[i], 0.f, t);
+        ok = !__any_sync(0xffffffffu, t != t);
+        if (!ok && lane == 0) ++n_bad;
+      }
+      if (ok) {
+        float* dst = vsum0 + (size_t)cur * d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int q = 0; q < EPV / 4; ++q)
+            red_add_v4(dst + v * 32 * EPV + 4 * q, acc[v * EPV + 4 * q], acc[v * EPV + 4 * q + 1], acc[v * EPV + 4 * q + 2],
+                       acc[v * EPV + 4 * q + 3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPL * EPV; ++i) acc[i] = 0.f;
+  };
+  auto load_entries = [&](int64_t chunk, uint32_t& pix, int& gid) {
+    pix = 0u;
+    gid = -1;
+    if (chunk < n_chunks) {
+      const int64_t i = (chunk << 5) + lane;
+      if (i < n_entries) {
+        const unsigned long long e = a.entries[i];
+        pix = (uint32_t)e;
+        gid = (int)(uint32_t)(e >> 32);
+      }
+    }
+  };
+  // group q (0..3) of the chunk whose entries the lanes hold, into buffer b: the valid entries' bytes are announced
+  // on the buffer's barrier, then every run start copies its run.  Returns nothing; an empty group issues nothing.
+  auto issue_group = [&](uint32_t pix, int gid, int q, uint32_t b) {
+    const uint32_t ppix = __shfl_up_sync(0xffffffffu, pix, 1);
+    const int pgid = __shfl_up_sync(0xffffffffu, gid, 1);
+    const bool in_group = (lane >> 3) == q;
+    const bool valid = in_group && gid >= 0;
+    const bool start = valid && ((lane & 7) == 0 || pgid < 0 || pix != ppix + 1u);
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned smask = __ballot_sync(0xffffffffu, start);
+    if (vmask == 0u) return;
+    const uint32_t bar = bar0 + b * 8u;
+    if (lane == (q << 3)) mbar_expect_tx_cta(bar, (uint32_t)__popc(vmask) * ROW);
+    __syncwarp();
+    if (start) {
+      // my run ends before the next run start, the end of the valid entries, or the end of the group
+      const unsigned after = (smask | ~vmask) & ~((2u << lane) - 1u) & (0xFFu << (q << 3));
+      const int end = after ? __ffs(after) - 1 : ((q << 3) + 8);
+      const uint32_t len = (uint32_t)(end - lane);
+      bulk_g2s(ring0 + (b * (uint32_t)G + (uint32_t)(lane & 7)) * ROW, emb_row0 + (unsigned long long)pix * rb, len * ROW, bar);
+    }
+  };
+  uint32_t pixC, pixN;
+  int gidC, gidN;
+  load_entries(warp, pixC, gidC);
+  load_entries(warp + n_warps, pixN, gidN);
+  // prologue: the first NB groups (all in the first chunk: NB <= 4)
+#pragma unroll
+  for (int g = 0; g < NB; ++g) issue_group(pixC, gidC, g, (uint32_t)g);
+  uint32_t buf = 0, phases = 0u;
+  for (int64_t chunk = warp; chunk < n_chunks; chunk += n_warps) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      const unsigned vmask = __ballot_sync(0xffffffffu, (lane >> 3) == q && gidC >= 0);
+      if (vmask) {
+        mbar_wait_cta(bar0 + buf * 8u, (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+      }
+#pragma unroll
+      for (int h = 0; h < G / U; ++h) {
+        int g[U];
+        uint4 rows[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          g[u] = __shfl_sync(0xffffffffu, gidC, (q << 3) + h * U + u);
+          if (g[u] >= 0) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+              rows[u][v] = lds_v4(ring0 + (buf * (uint32_t)G + (uint32_t)(h * U + u)) * ROW + (uint32_t)v * 512u + (uint32_t)lane * 16u);
+          }
+        }
+        if (h == G / U - 1) {
+          // the group has been read: its buffer takes the group NB ahead (this chunk's, or the next chunk's)
+          __syncwarp();
+          const int qq = q + NB;
+          if (qq < 4)
+            issue_group(pixC, gidC, qq, buf);
+          else
+            issue_group(pixN, gidN, qq - 4, buf);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (g[u] < 0) continue;
+          if (g[u] != cur) {
+            flush();
+            cur = g[u];
+          }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) RowVec<BF16>::add(acc + v * EPV, rows[u][v]);
+        }
+      }
+      buf = buf + 1u == (uint32_t)NB ? 0u : buf + 1u;
+    }
+    pixC = pixN;
+    gidC = gidN;
+    load_entries(chunk + 2 * n_warps, pixN, gidN);
+  }
+  flush();
+
+  if (CHECK) {
+    const uint8_t* emb0 = emb_row0 + (size_t)lane * 16;
+    const int64_t n_check = (int64_t)a.ctr->n_check;
+    for (int64_t i = warp; i < n_check; i += n_warps) {
+      const uint32_t pj = (uint32_t)a.entries[n_entries + i];
+      const uint8_t* row = emb0 + (unsigned long long)pj * rb;
+      bool bad = false;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) bad |= RowVec<BF16>::nonfinite(ld_stream_v4(row + v * 512));
+      if (__any_sync(0xffffffffu, bad) && lane == 0) ++n_bad;
+    }
+    if (n_bad) atomicAdd(&a.ctr->n_bad_emb, (unsigned long long)n_bad);
+  }
+}
+
+std::atomic<int> g_acc_tmarun{0};  // "acc_tmarun": bulk copies of runs of neighbouring rows
+
+template <bool BF16, int VPL>
+static int launch_accumulate_tmarun(const AccArgs& a, bool check, cudaStream_t s, int n_sm) {
+  constexpr size_t smem = (size_t)8 * 24 * VPL * 512 + (size_t)8 * 3 * 8;
+  static const cudaError_t opt0 = cudaFuncSetAttribute(accumulate_tmarun_kernel<BF16, VPL, false>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const cudaError_t opt1 = cudaFuncSetAttribute(accumulate_tmarun_kernel<BF16, VPL, true>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  VSM_CUDA(opt0);
+  VSM_CUDA(opt1);
+  const int grid = n_sm > 0 ? n_sm : sm_count();
+  if (check)
+    accumulate_tmarun_kernel<BF16, VPL, true><<<grid, 256, smem, s>>>(a);
+  else
+    accumulate_tmarun_kernel<BF16, VPL, false><<<grid, 256, smem, s>>>(a);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
+std::atomic<int> g_acc_tma{0};  // "acc_tma": the TMA bulk-copy accumulate for voxel-sorted lists with full rows
+
+template <bool BF16, int VPL>
+static int launch_accumulate_tma(const AccArgs& a, bool check, cudaStream_t s, int n_sm) {
+  constexpr int DEPTH = VPL == 1 ? 24 : (VPL == 2 ? 12 : (VPL == 4 ? 4 : 4));
+  constexpr size_t smem = (size_t)8 * DEPTH * VPL * 512 + (size_t)8 * DEPTH * 8;
+  static const cudaError_t opt0 = cudaFuncSetAttribute(accumulate_tma_kernel<BF16, VPL, false, DEPTH>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const cudaError_t opt1 = cudaFuncSetAttribute(accumulate_tma_kernel<BF16, VPL, true, DEPTH>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  VSM_CUDA(opt0);
+  VSM_CUDA(opt1);
+  const int grid = (n_sm > 0 ? n_sm : sm_count()) * 2;
+  if (check)
+    accumulate_tma_kernel<BF16, VPL, true, DEPTH><<<grid, 256, smem, s>>>(a);
+  else
+    accumulate_tma_kernel<BF16, VPL, false, DEPTH><<<grid, 256, smem, s>>>(a);
+  VSM_LAUNCHED();
+  return VSM_OK;
+}
+
 // Measured on B200 (config 2, 8 submaps): 1.08 ms per submap against 1.01 ms with accumulate_kernel on the whole device,
 // 0.95 against 0.90 with 64 SMs set aside for the preparation kernels, and no better on 60 SMs -- twice the bytes in
 // flight per SM do not buy bandwidth on fewer SMs here.  Kept as an option ("acc_ring"), off by default.
@@ -1191,6 +1770,19 @@ static int launch_accumulate_t(const AccArgs& a, bool sorted, bool check, cudaSt
     grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n_chunks, block / 32), 1), (int64_t)sm_count() * 6);
   }
   const bool full = a.nvec == 32 * VPL;
+  static const bool env_run = getenv("VSM_ACC_TMARUN") && getenv("VSM_ACC_TMARUN")[0] == '1';
+  if (sorted && full && VPL <= 2 && a.emb_index == nullptr && (g_acc_tmarun.load() || env_run) &&
+      (reinterpret_cast<uintptr_t>(a.emb) & 15u) == 0)
+    return launch_accumulate_tmarun<BF16, VPL>(a, check, s, n_sm);
+  static const int env_mix = getenv("VSM_ACC_MIX") ? atoi(getenv("VSM_ACC_MIX")) : 0;
+  if (sorted && full && VPL <= 4 && a.emb_index == nullptr && (g_acc_mix.load() > 0 || env_mix > 0) &&
+      (reinterpret_cast<uintptr_t>(a.emb) & 15u) == 0) {
+    if (g_acc_mix.load() == 0) g_acc_mix = env_mix;
+    return launch_accumulate_mix<BF16, VPL>(a, check, s, n_sm);
+  }
+  static const bool env_tma = getenv("VSM_ACC_TMA") && getenv("VSM_ACC_TMA")[0] == '1';  // (for running the test suite on it)
+  if (sorted && full && VPL <= 4 && a.emb_index == nullptr && (g_acc_tma.load() || env_tma) && (reinterpret_cast<uintptr_t>(a.emb) & 15u) == 0)
+    return launch_accumulate_tma<BF16, VPL>(a, check, s, n_sm);
   if (sorted && full && a.emb_index == nullptr && g_acc_ring.load()) return launch_accumulate_ring<BF16, VPL>(a, check, s, n_sm);
   if (sorted && full && a.emb_index != nullptr) {
     if (check)
@@ -2364,6 +2956,22 @@ extern "C" int vsm_set_option(const char* key, int64_t value) {
   }
   if (!strcmp(key, "query_shadow") && (value == 0 || value == 1)) {
     g_query_shadow = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_tmarun") && (value == 0 || value == 1)) {
+    g_acc_tmarun = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_mix") && value >= 0 && value <= 1000) {
+    g_acc_mix = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_mix_ctas") && value >= 1 && value <= 3) {
+    g_acc_mix_ctas = (int)value;
+    return VSM_OK;
+  }
+  if (!strcmp(key, "acc_tma") && (value == 0 || value == 1)) {
+    g_acc_tma = (int)value;
     return VSM_OK;
   }
   if (!strcmp(key, "acc_ring") && (value == 0 || value == 1)) {
