@@ -10,19 +10,27 @@ the three outlier filters on) + finalisation.  Synthetic inputs (vsm.synth_devic
              point maps, confidences and embeddings host->device inside the timed region and reads the
              finished map (centres + features + contributor tables) back device->host; `e2e.f32` is the same with
              numpy float32 embeddings (the reference's contract, submap.py:41-65: twice the bytes)
-  roofline   accumulate kernel: algorithmic bytes / CUDA-event time (events recorded inside libvsm on the
-             launching stream) against MEASURED_PEAKS.json's HBM copy bandwidth
+  roofline   accumulate kernel: algorithmic bytes / CUDA-event time (events recorded inside libvsm on the stream
+             the kernel is launched on) against MEASURED_PEAKS.json's HBM copy bandwidth: `frac` inside the timed
+             region (beside the next call's preparation kernels when the SM partition is on), `frac_alone` on the
+             whole device, `fuse_calls_frac` for the whole fuse calls; `sm_partition`: what was tried and kept
   cpu_baseline  the numpy oracle (a port of the reference's CPU path) on a bounded sample, 1 core (the path is
                 single-threaded numpy); `.parity`: the same sample fused by the GPU path and compared with the
                 oracle's output; `.parallel`: as many independent copies as the host has cores (an extra figure)
   cuda_library_baseline  the reference's own torch-CUDA branch of the global voxelisation (map.py:322-348:
                 torch.unique + index_add_ over 1000-row host chunks) restated with torch, timed on this GPU
+  secondary  text query (10 M / 30 M / 70 M voxels, tensor-core engines on the fp32 sums and on the bf16 shadow, each
+             checked against the exact engine), per-frame streaming, indexed embeddings, the long trajectory
 
-`--impl reference` times the CPU port alone (the reference arm).  N>1 (torchrun): every rank fuses its own 20
-submaps (weak scaling) in rounds; each round's voxels are pushed to their owners (key hash) over NVLink peer memory and
-merged there on an exchange stream while the next round is fused; `dist_parity` is an in-process correctness check of
-that build (union of the shards == single-GPU map) run before the timing, and `secondary.long_trajectory` is BASELINE
-configs[2] (200 submaps of a corridor at 2 cm voxels, sharded over the ranks).
+`--impl reference` times the CPU port alone (the reference arm).  One GPU: the preparation kernels of fuse call i+1 run
+on 64 SMs beside the accumulate kernel of call i on the other 84 (CUDA green contexts) if that measures faster than the
+plain launch order before the warm-up.  N>1 (torchrun): every rank fuses its own 20 submaps (weak scaling) with the same
+partition; the voxels are owned by key hash and exchanged once, after the last submap, through NCCL all-to-alls (the
+one-sided NVLink peer-memory exchange does not mix with the partition: see the comment at `--sm-partition`);
+`dist_parity` is an in-process correctness check of the sharded builds (union of the shards == single-GPU map, one-shot
+and streaming peer exchange) run before the timing, and `secondary.long_trajectory` is BASELINE configs[2] (200 submaps
+of a 1.6 km corridor at 2 cm voxels, sharded over the ranks, fused in rounds whose voxels are pushed to their owners
+over NVLink peer memory while the next round is fused).
 """
 from __future__ import annotations
 
@@ -42,7 +50,7 @@ for p in (ROOT, os.path.join(ROOT, "vggt-slam_b200"), os.path.join(ROOT, "tests"
 import numpy as np  # noqa: E402
 
 # accumulate_kernel DRAM traffic per launch from the committed `ncu --set full` capture of this workload's submap shape
-# (mean of 3 launches: 3.861 GB read + 0.066 GB written against 3.73 GB algorithmic)
+# (round 2: 3.855 GB read + 0.061 GB written against 3.73 GB algorithmic)
 NCU_ACC_TRAFFIC_BYTES = 3.917e9  # dram__bytes_read.sum + dram__bytes_write.sum of one accumulate launch (3.855 GB + 61 MB)
 NCU_ACC_TRAFFIC_SRC = "profiles/r02_fuse_kernels_ncu_full_summary.txt"
 
