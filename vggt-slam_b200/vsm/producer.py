@@ -9,7 +9,6 @@ the same preparation runs as libvsm kernels and the Submap keeps device tensors,
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional
 
 import numpy as np

@@ -14,7 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 

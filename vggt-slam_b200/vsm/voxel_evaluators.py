@@ -9,11 +9,9 @@
 """
 from __future__ import annotations
 
-import bisect
 import json
 import os
 import re
-import time
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np

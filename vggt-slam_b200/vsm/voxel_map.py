@@ -6,7 +6,7 @@ and streams only; every computation is a libvsm kernel.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch
