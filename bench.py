@@ -1064,9 +1064,18 @@ def main():
         # cures it at N=2 (18.8-19.3 ms) but not at N=8 (26-41 ms); with the collective exchange every step takes
         # 21.6-21.9 ms at N=2 and N=8 (peer exchange without the partition: 22.5-22.9).  This workload exchanges 0.3 GB
         # per step; the long-trajectory block below keeps the peer exchange, without the partition.
-        partition.update({"prep_sms": 64, "exchange": "collective (NCCL all-to-all) beside the partition"})
-        dist_transport[0] = "collective"
-        set_partition(64)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            set_partition(64)
+        except Exception as e:  # noqa: BLE001 -- e.g. a driver without green contexts
+            ok.zero_()
+            partition["error"] = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank or none
+        if int(ok.item()):
+            partition.update({"prep_sms": 64, "exchange": "collective (NCCL all-to-all) beside the partition"})
+            dist_transport[0] = "collective"
+        else:
+            set_partition(0)
     elif args.sm_partition == "auto":
         tuned = {}
         for cand in CANDS:
